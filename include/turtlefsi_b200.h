@@ -1,0 +1,156 @@
+/* turtlefsi_b200 — C ABI of the B200-native monolithic FSI assembly hot path.
+ *
+ * Every entry point replaces one DOLFIN/PETSc call made by turtleFSI's Newton solver
+ * (reference: turtleFSI/modules/newtonsolver.py) — the line it replaces is cited at each
+ * declaration.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Memory: `tfsi_create` copies its inputs (host OR device pointers, resolved through UVA) into
+ * handle-owned device memory.  All vectors/values passed to the assemble/apply calls are DEVICE
+ * pointers owned by the caller (a torch.Tensor.data_ptr(), a cudaMalloc, ...); the `_host`
+ * variants take HOST pointers and include the host<->device copies.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Calls are asynchronous on `stream` unless
+ * they return a host scalar.
+ *
+ * Return value: 0 on success, negative error code otherwise; `tfsi_last_error` gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry fails with TFSI_ERR_CUDA.
+ */
+#ifndef TURTLEFSI_B200_H
+#define TURTLEFSI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFSI_OK 0
+#define TFSI_ERR_ARG (-1)
+#define TFSI_ERR_CUDA (-2)
+#define TFSI_ERR_PATTERN (-3)
+#define TFSI_ERR_UNSUPPORTED (-4)
+
+#define TFSI_KIND_FLUID 0
+#define TFSI_KIND_SOLID 1
+
+#define TFSI_EXT_NONE 0        /* modules/no_extrapolation.py */
+#define TFSI_EXT_LAPLACE 1     /* modules/laplace.py          */
+#define TFSI_EXT_BIHARMONIC 2  /* modules/biharmonic.py (cell terms) */
+
+#define TFSI_LAPLACE_CONSTANT 0        /* laplace.py:39-40 */
+#define TFSI_LAPLACE_SMALL_CONSTANT 1  /* laplace.py:37-38 */
+#define TFSI_LAPLACE_VOLUME 2          /* laplace.py:35-36 */
+
+typedef struct tfsi_handle tfsi_handle;
+
+/* one entry per cell-marker id that carries integrals: dx_f[i] / dx_s[i]
+ * (turtleFSI/modules/domain.py:54-103) */
+typedef struct {
+    int32_t marker;   /* value of the `domains` MeshFunction selecting this region     */
+    int32_t kind;     /* TFSI_KIND_FLUID | TFSI_KIND_SOLID                              */
+    double rho;       /* rho_f | rho_s                                                  */
+    double mu;        /* mu_f  | mu_s                                                   */
+    double lambda;    /* lambda_s (solid, St.Venant-Kirchhoff: common.py:104-109)       */
+} tfsi_region;
+
+typedef struct {
+    int32_t gdim;             /* 2 | 3                                                  */
+    int32_t biharmonic;       /* 1: DVP has the 4th sub-space w (monolithic.py:86-89)   */
+    int64_t num_vertices;
+    int64_t num_cells;
+    int64_t num_dofs;         /* N                                                      */
+    const double* coords;         /* [num_vertices * gdim]                              */
+    const int32_t* cell_vertices; /* [num_cells * (gdim+1)], ascending per cell         */
+    const int32_t* cell_dofs;     /* [num_cells * ndof], local layout d|v|p(|w); taken
+                                     as INPUT so DOLFIN's dofmap is honoured bit-exactly */
+    const int32_t* cell_marker;   /* [num_cells]                                        */
+    const int64_t* rowptr;        /* [N+1]  CSR pattern, taken as INPUT                 */
+    const int32_t* colidx;        /* [nnz]  ascending within a row                      */
+    int32_t num_regions;
+    const tfsi_region* regions;
+    double dt;                /* k      (monolithic.py:82)                              */
+    double theta;             /* theta  (fluid.py:18-19, solid.py:32-33)                */
+    int32_t fluid_on;         /* 0 = --fluid no_fluid                                   */
+    int32_t solid_on;         /* 0 = --solid no_solid                                   */
+    int32_t extrapolation;    /* TFSI_EXT_*                                             */
+    int32_t extrapolation_sub_type; /* TFSI_LAPLACE_* (laplace only)                    */
+    double hmin;              /* mesh.hmin() (laplace small_constant)                   */
+    double gravity;           /* solid.py:65-68; used iff has_gravity                   */
+    int32_t has_gravity;
+    /* quadrature rules on the UFC reference simplex (weights sum to the reference volume).
+     * Jacobian: compiler_parameters["quadrature_degree"] (problems/__init__.py:16-17);
+     * residual: the global form-compiler degree. */
+    int32_t nq_jacobian;
+    const double* qpts_jacobian;  /* [nq * gdim] */
+    const double* qwts_jacobian;  /* [nq]        */
+    int32_t nq_residual;
+    const double* qpts_residual;
+    const double* qwts_residual;
+    int32_t verify_pattern;   /* 1: check that every cell block fits the CSR pattern    */
+} tfsi_problem;
+
+/* newtonsolver.py:13-31 (solver_setup): uploads mesh, dofmap, pattern; builds scatter maps. */
+int tfsi_create(const tfsi_problem* prob, tfsi_handle** out);
+void tfsi_destroy(tfsi_handle* h);
+/* message of the last failing call on `h` (or of the last failing tfsi_create if h == NULL) */
+const char* tfsi_last_error(const tfsi_handle* h);
+int64_t tfsi_nnz(const tfsi_handle* h);
+int32_t tfsi_ndof_cell(const tfsi_handle* h);
+
+/* A_pre = assemble(J_linear, keep_diagonal=True)            newtonsolver.py:26-27
+ * x, x1: state at n and n-1 [N]; Apre_vals [nnz] is overwritten. */
+int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, double* Apre_vals,
+                        void* stream);
+
+/* assemble(J_nonlinear, tensor=A, keep_diagonal=True); A.axpy(1.0, A_pre, True)
+ *                                                           newtonsolver.py:75-79
+ * A_vals [nnz] is overwritten with J_nonlinear(x, x1) + A_pre (A_pre may be NULL = 0). */
+int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1,
+                           const double* Apre_vals, double* A_vals, void* stream);
+
+/* b = assemble(-F)                                          newtonsolver.py:86-88 */
+int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b,
+                           void* stream);
+
+/* A.ident_zeros()  (rows with sum |a_ij| < DOLFIN_EPS get a unit diagonal)  newtonsolver.py:81 */
+int tfsi_ident_zeros(tfsi_handle* h, double* A_vals, void* stream);
+
+/* Dirichlet dof index set (fixed for the run; values change)  — DirichletBC objects of the
+ * problem file's create_bcs, flattened in list order, later entries win.  bc_dofs: HOST or
+ * DEVICE int32 [n]. */
+int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc_dofs, int64_t n);
+/* [bc.apply(A) for bc in bcs]            newtonsolver.py:82  zero rows, unit diagonal */
+int tfsi_apply_bc_matrix(tfsi_handle* h, double* A_vals, void* stream);
+/* [bc.apply(b, x) for bc in bcs]         newtonsolver.py:91  b_i = g_i - x_i ; g [n] values */
+int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, void* stream);
+/* [bc.apply(x) for bc in bcs]            newtonsolver.py:98  x_i = g_i */
+int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream);
+
+/* b.norm('l2') / norm(dvp_res, 'l2')     newtonsolver.py:105-106 ; synchronises, writes the
+ * SUM OF SQUARES to *out_sumsq (caller takes sqrt, after an all-reduce when distributed). */
+int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out_sumsq, void* stream);
+
+/* Host-buffer variants (reference-facing end-to-end call): x, x1 HOST [N]; b_host HOST [N];
+ * A_vals stays on the device (consumer is the device sparse LU).  Includes H2D of x, x1, the
+ * Jacobian (+A_pre, ident_zeros, BC rows) and residual (+BC) assembly, and D2H of b.
+ * g_host: BC values [nbc] or NULL. Synchronous. */
+int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host,
+                              const double* g_host, const double* Apre_vals, double* A_vals,
+                              double* b_host, double* out_sumsq_b, int32_t recompute_jacobian);
+
+/* Halo update of the Newton iterate before an assembly (multi-GPU): packs x[send_idx] into
+ * send_buf and unpacks recv_buf into x[recv_idx]; the NCCL send/recv between the two is
+ * issued by the host language (torch.distributed) on the same stream. */
+int tfsi_halo_pack(tfsi_handle* h, const double* x, const int32_t* send_idx, int64_t n,
+                   double* send_buf, void* stream);
+int tfsi_halo_unpack(tfsi_handle* h, double* x, const int32_t* recv_idx, int64_t n,
+                     const double* recv_buf, void* stream);
+
+/* kernels launched since creation (for bench.py's gpu_launches) */
+int64_t tfsi_launch_count(const tfsi_handle* h);
+
+/* FP64 FMA peak probe: runs a register-resident DFMA loop on every SM, returns TFLOP/s. */
+int tfsi_probe_fp64_peak(double* out_tflops, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

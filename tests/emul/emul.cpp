@@ -1,0 +1,167 @@
+// TEST-ONLY host harness (never loaded by the product): compiles the per-point mathematics of
+// turtlefsi_b200/csrc/tfsi_math.cuh with g++ and drives it cell by cell exactly as the CUDA
+// kernels do (phase 0 base items -> tasks -> block updates), returning DENSE element matrices /
+// vectors so that the formulas can be checked against oracle/forms.py without a GPU.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define TFSI_NO_CUDA 1
+#include "../../turtlefsi_b200/csrc/tfsi_math.cuh"
+
+using namespace tfsi;
+
+namespace {
+
+template <int G>
+void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* Xp, const double* u,
+              const double* u1, int ndof, double* Ae)
+{
+    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    double X[G + 1][G];
+    for (int v = 0; v <= G; ++v) for (int c = 0; c < G; ++c) X[v][c] = Xp[v * G + c];
+    double K[G][G];
+    double adet = cell_geometry<G>(X, K);
+    const int nq = tab.nq;
+    auto cf = [&](int k) { return u[k]; };
+    auto cf1 = [&](int k) { return u1[k]; };
+    auto addblock = [&](int r0, int c0, int nr, int ncl, const double* Z, int ldz) {
+        for (int i = 0; i < nr; ++i) for (int j = 0; j < ncl; ++j) Ae[(r0 + i) * ndof + c0 + j] += Z[i * ldz + j];
+    };
+    if (rc.kind == 0) {
+        typedef FluidBase<G> FB;
+        std::vector<double> base((size_t)FB::COUNT * nq);
+        for (int q = 0; q < nq; ++q) {
+            auto out = [&](int item, double v) { base[(size_t)item * nq + q] = v; };
+            fluid_base<G>(tab, q, K, adet, rc, cf, cf1, out);
+        }
+        constexpr int NJ = N2 / 2;
+        for (int fld = 0; fld < 2; ++fld)
+            for (int a = 0; a < G; ++a)
+                for (int b = 0; b < G; ++b)
+                    for (int half = 0; half < 2; ++half) {
+                        double Z[N2][NJ];
+                        memset(Z, 0, sizeof Z);
+                        for (int q = 0; q < nq; ++q) {
+                            auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
+                            double C[G + 1][G + 1];
+                            if (fld == 0) fluid_C_psi_dd<G>(bv, rc, a, b, C); else fluid_C_psi_dv<G>(bv, rc, a, b, C);
+                            if (half == 0) block_p2p2<G, 0, NJ, 7>(tab, q, C, Z); else block_p2p2<G, NJ, NJ, 7>(tab, q, C, Z);
+                        }
+                        addblock(G * N2 + a * N2, fld * G * N2 + b * N2 + half * NJ, N2, NJ, &Z[0][0], NJ);
+                    }
+        for (int a = 0; a < G; ++a) {
+            double Z[N2][N1];
+            memset(Z, 0, sizeof Z);
+            for (int q = 0; q < nq; ++q) {
+                auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
+                double c[G];
+                fluid_c_psi_dp<G>(bv, a, c);
+                block_gradp2_p1<G>(tab, q, c, Z);
+            }
+            addblock(G * N2 + a * N2, 2 * G * N2, N2, N1, &Z[0][0], N1);
+        }
+        for (int fld = 0; fld < 2; ++fld)
+            for (int b = 0; b < G; ++b) {
+                double Z[N1][N2];
+                memset(Z, 0, sizeof Z);
+                for (int q = 0; q < nq; ++q) {
+                    auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
+                    double c[G];
+                    if (fld == 0) fluid_c_gamma_dd<G>(bv, b, c); else fluid_c_gamma_dv<G>(bv, b, c);
+                    block_p1_gradp2<G>(tab, q, c, Z);
+                }
+                addblock(2 * G * N2, fld * G * N2 + b * N2, N1, N2, &Z[0][0], N2);
+            }
+    } else {
+        typedef SolidBase<G> SB;
+        std::vector<double> base((size_t)SB::COUNT * nq);
+        for (int q = 0; q < nq; ++q) {
+            auto out = [&](int item, double v) { base[(size_t)item * nq + q] = v; };
+            solid_base<G>(tab, q, K, adet, rc, cf, out);
+        }
+        constexpr int NJ = N2 / 2;
+        for (int a = 0; a < G; ++a)
+            for (int b = 0; b < G; ++b)
+                for (int half = 0; half < 2; ++half) {
+                    double Z[N2][NJ];
+                    memset(Z, 0, sizeof Z);
+                    for (int q = 0; q < nq; ++q) {
+                        auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
+                        double C[G + 1][G + 1];
+                        solid_C_psi_dd<G>(bv, rc, a, b, C);
+                        if (half == 0) block_p2p2<G, 0, NJ, 4>(tab, q, C, Z); else block_p2p2<G, NJ, NJ, 4>(tab, q, C, Z);
+                    }
+                    addblock(G * N2 + a * N2, b * N2 + half * NJ, N2, NJ, &Z[0][0], NJ);
+                }
+    }
+}
+
+template <int G>
+void res_cell(const QuadTab<MAXQ_R>& tab, const RegionConst& rc, const double* Xp, const double* u,
+              const double* u1, int ndof, double* Fe)
+{
+    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    double X[G + 1][G];
+    for (int v = 0; v <= G; ++v) for (int c = 0; c < G; ++c) X[v][c] = Xp[v * G + c];
+    double K[G][G];
+    double adet = cell_geometry<G>(X, K);
+    double alfa_cell = rc.alfa;
+    if (rc.ext == 1 && rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
+    auto cf = [&](int k) { return u[k]; };
+    auto cf1 = [&](int k) { return u1[k]; };
+    const bool bih = ndof > 2 * G * N2 + N1;
+    for (int q = 0; q < tab.nq; ++q) {
+        PointFlux<G> f;
+        residual_point<G>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        for (int c = 0; c < G; ++c)
+            for (int i = 0; i < N2; ++i) {
+                double zp = tab.phi2[q][i] * f.psi_val[c], zd = tab.phi2[q][i] * f.phi_val[c], zb = tab.phi2[q][i] * f.beta_val[c];
+                for (int s = 0; s < G; ++s) {
+                    zp += tab.dphi2[q][i][s] * f.psi_grad[c][s];
+                    zd += tab.dphi2[q][i][s] * f.phi_grad[c][s];
+                    zb += tab.dphi2[q][i][s] * f.beta_grad[c][s];
+                }
+                Fe[c * N2 + i] += zd;
+                Fe[G * N2 + c * N2 + i] += zp;
+                if (bih) Fe[2 * G * N2 + N1 + c * N2 + i] += zb;
+            }
+        for (int m = 0; m < N1; ++m) Fe[2 * G * N2 + m] += tab.phi1[q][m] * f.gamma;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Ae[nc][ndof][ndof] += element matrices of J_nonlinear ; X[nc][(g+1)*g], u/u1[nc][ndof]
+int emul_jacobian(int g, int nq, const double* pts, const double* wts, int kind, double rho, double mu,
+                  double lambda, double dt, double theta, int64_t nc, const double* X, const double* u,
+                  const double* u1, int ndof, double* Ae)
+{
+    QuadTab<MAXQ_J> tab;
+    if (tabulate<MAXQ_J>(g, nq, pts, wts, tab)) return -1;
+    RegionConst rc = make_region_const(kind, rho, mu, lambda, dt, theta, 1, 1, 1, 0, 0.0, 0.0);
+    for (int64_t c = 0; c < nc; ++c) {
+        if (g == 3) jac_cell<3>(tab, rc, X + c * 12, u + c * ndof, u1 + c * ndof, ndof, Ae + c * ndof * ndof);
+        else jac_cell<2>(tab, rc, X + c * 6, u + c * ndof, u1 + c * ndof, ndof, Ae + c * ndof * ndof);
+    }
+    return 0;
+}
+
+// Fe[nc][ndof] += element vectors of F = F_lin + F_nonlin
+int emul_residual(int g, int nq, const double* pts, const double* wts, int kind, double rho, double mu,
+                  double lambda, double dt, double theta, int fluid_on, int solid_on, int ext, int ext_sub,
+                  double hmin, double gravity, int64_t nc, const double* X, const double* u, const double* u1,
+                  int ndof, double* Fe)
+{
+    QuadTab<MAXQ_R> tab;
+    if (tabulate<MAXQ_R>(g, nq, pts, wts, tab)) return -1;
+    RegionConst rc = make_region_const(kind, rho, mu, lambda, dt, theta, fluid_on, solid_on, ext, ext_sub, hmin, gravity);
+    for (int64_t c = 0; c < nc; ++c) {
+        if (g == 3) res_cell<3>(tab, rc, X + c * 12, u + c * ndof, u1 + c * ndof, ndof, Fe + c * ndof);
+        else res_cell<2>(tab, rc, X + c * 6, u + c * ndof, u1 + c * ndof, ndof, Fe + c * ndof);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""CPU tests of the host logic: mesh generators, dof map, CSR pattern, the C-ABI library."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from tests.helpers import square_mesh
+from turtlefsi_b200.mesh import box_mesh, tube_mesh
+from turtlefsi_b200.space import MixedSpace, pattern_from_cell_dofs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_box_mesh_counts_and_orientation():
+    m = box_mesh(5)
+    assert m.num_cells == 6 * 125 and m.num_vertices == 216
+    assert (np.diff(m.cells, axis=1) > 0).all()
+    X = m.coords[m.cells]
+    vol = np.abs(np.linalg.det(np.swapaxes(X[:, 1:] - X[:, :1], 1, 2))) / 6
+    assert abs(vol.sum() - 1.0) < 1e-12 and vol.min() > 0
+    # sizes named in BASELINE.md: 6 n^3
+    assert 6 * 55 ** 3 == 998250 and 6 * 69 ** 3 == 1971054
+
+
+def test_tube_markers():
+    m = tube_mesh(6)
+    assert set(np.unique(m.markers)) == {1, 2}
+    cen = m.coords[m.cells].mean(axis=1)
+    assert ((np.hypot(cen[:, 0], cen[:, 1]) < 0.8) == (m.markers == 1)).all()
+
+
+def test_dofmap_and_pattern_all_numberings():
+    for mesh in (tube_mesh(3), square_mesh(4)):
+        for bih in (False, True):
+            ref = None
+            for numbering in ("interleaved", "blocked"):
+                sp = MixedSpace(mesh, biharmonic=bih, numbering=numbering)
+                g = mesh.gdim
+                assert sp.ndof_cell == {(2, False): 27, (2, True): 39, (3, False): 64, (3, True): 94}[(g, bih)]
+                # every dof is used, numbering is a bijection
+                assert np.array_equal(np.unique(sp.cell_dofs), np.arange(sp.num_dofs))
+                rp, ci = sp.pattern()
+                rp2, ci2 = pattern_from_cell_dofs(sp.cell_dofs, sp.num_dofs)
+                assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+                # sorted columns, diagonal present
+                for r in (0, sp.num_dofs // 2, sp.num_dofs - 1):
+                    seg = ci[rp[r]:rp[r + 1]]
+                    assert (np.diff(seg) > 0).all() and r in seg
+                ref = ref or len(ci)
+                assert len(ci) == ref       # nnz is numbering independent
+    sp = MixedSpace(box_mesh(6))
+    assert 1500 < len(sp.pattern()[1]) / (6 * 216) < 1800      # SURVEY: ~1550 nnz per tet on large meshes
+
+
+def test_shared_edge_dofs_consistent():
+    mesh = tube_mesh(3)
+    sp = MixedSpace(mesh)
+    X = sp.node_coords(mesh)
+    # the node of local P2 function i of a cell sits at the vertex / edge midpoint (UFC order)
+    from turtlefsi_b200.space import EDGES
+    c = 17
+    vx = mesh.coords[mesh.cells[c]]
+    loc = [vx[i] for i in range(4)] + [0.5 * (vx[i] + vx[j]) for i, j in EDGES[3]]
+    assert np.allclose(X[sp.cell_nodes[c]], np.array(loc))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from turtlefsi_b200 import lib
+    lib.build()
+    so = C.CDLL(lib.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "turtlefsi_b200.h")).read()
+    declared = set(re.findall(r"\b(tfsi_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.EXPORTS)
+    for name in declared:
+        assert hasattr(so, name), name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from turtlefsi_b200.assembler import FSIAssembler
+    mesh = tube_mesh(2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FSIAssembler(mesh, MixedSpace(mesh), [], 1e-3, 0.5)
+    # and the raw ABI refuses too
+    from turtlefsi_b200 import lib
+    L = lib.load()
+    tf, ms = C.c_double(), C.c_double()
+    assert L.tfsi_probe_fp64_peak(C.byref(tf), C.byref(ms)) != 0

@@ -1,0 +1,195 @@
+"""CPU tests of the oracle itself and of the kernels' per-point mathematics (host-compiled).
+
+The reference holds NO golden vector at matrix/residual-entry level; what can be
+pinned on the CPU is internal consistency between three independent derivations:
+  (1) numpy residual forms written from the UFL + complex-step Jacobian   (oracle/forms.py)
+  (2) plain-C FFC-style restatement with hand-derived Jacobian           (oracle/c)
+  (3) the CUDA kernels' C'-tensor / sum-factorised formulation, host-compiled (tests/emul)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import assembly as oa
+from oracle import cport
+from oracle import fem_tables as ft
+from oracle.forms import CellForms
+from tests.conftest import TUBE_PARAMS, TUBE_REGIONS
+from tests.helpers import square_mesh
+from turtlefsi_b200.mesh import synthetic_state, tube_mesh
+from turtlefsi_b200.space import MixedSpace
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "emul", "libtfsi_emul.so")
+    src = os.path.join(HERE, "emul", "emul.cpp")
+    hdr = os.path.join(HERE, "..", "turtlefsi_b200", "csrc", "tfsi_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _case(g, bih, amp):
+    mesh = tube_mesh(3) if g == 3 else square_mesh(5)
+    sp = MixedSpace(mesh, biharmonic=bih)
+    x = synthetic_state(mesh, sp, 2024, h=amp)
+    x1 = synthetic_state(mesh, sp, 2025, h=amp)
+    return mesh, sp, x, x1
+
+
+def test_quadrature_rules_exact():
+    import itertools
+    import math
+    for g in (2, 3):
+        for deg in range(1, 11):
+            P, W = ft.quadrature(g, deg)
+            assert abs(W.sum() - (0.5 if g == 2 else 1 / 6)) < 1e-14
+            for e in itertools.product(range(deg + 1), repeat=g):
+                if sum(e) > deg:
+                    continue
+                exact = np.prod([math.factorial(k) for k in e]) / math.factorial(sum(e) + g)
+                assert abs((W * np.prod(P ** np.array(e), axis=1)).sum() - exact) < 2e-14 * max(exact, 1e-3)
+    assert len(ft.quadrature(3, 4)[1]) == 14 and len(ft.quadrature(3, 6)[1]) == 24
+    assert len(ft.quadrature(2, 5)[1]) == 7 and len(ft.quadrature(2, 10)[1]) == 36
+
+
+def test_product_rule_equals_oracle_rule():
+    from turtlefsi_b200.quadrature import default_rule
+    for g in (2, 3):
+        for d in range(1, 12):
+            p, w = default_rule(g, d)
+            P, W = ft.quadrature(g, d)
+            a = np.lexsort(np.c_[p, w].T)
+            b = np.lexsort(np.c_[P, W].T)
+            assert np.abs(np.c_[p, w][a] - np.c_[P, W][b]).max() < 1e-15
+
+
+def test_p2_basis_is_nodal_and_partition_of_unity():
+    for g in (2, 3):
+        verts = np.vstack([np.zeros(g), np.eye(g)])
+        nodes = [verts[i] for i in range(g + 1)] + [0.5 * (verts[i] + verts[j]) for i, j in ft.EDGES[g]]
+        phi, dphi = ft.tabulate_p2(g, np.array(nodes))
+        assert np.allclose(phi, np.eye(len(nodes)), atol=1e-15)
+        pts = np.random.default_rng(0).dirichlet(np.ones(g + 1), size=7)[:, 1:]
+        phi, dphi = ft.tabulate_p2(g, pts)
+        assert np.allclose(phi.sum(axis=1), 1.0) and np.allclose(dphi.sum(axis=1), 0.0, atol=1e-14)
+
+
+def test_complex_step_matches_finite_difference():
+    mesh, sp, x, x1 = _case(3, False, 0.5)
+    cf = CellForms(3, False, 4)
+    prm = oa.region_params(TUBE_PARAMS, TUBE_REGIONS[0])
+    sel = np.nonzero(mesh.markers == 1)[0][:6]
+    X, u, u1 = mesh.coords[mesh.cells[sel]], x[sp.cell_dofs[sel]], x1[sp.cell_dofs[sel]]
+    J = cf.jacobian("fluid", X, u, u1, prm, "all")
+    eps = 1e-6
+    for j in (3, 17, 35, 44, 61):
+        up, um = u.copy(), u.copy()
+        up[:, j] += eps
+        um[:, j] -= eps
+        fd = (sum(cf.residual("fluid", X, up, u1, prm)) - sum(cf.residual("fluid", X, um, u1, prm))) / (2 * eps)
+        assert np.abs(fd - J[:, :, j]).max() < 1e-7 * np.abs(J).max()      # FD round-off scales with |R|
+
+
+def test_piola_identity():
+    """fluid.py:52 div(J F^-1 v): the literal expression (with second derivatives of d) equals
+    tr(J F^-1 grad v) because div(adj F) = 0 for a gradient field — checked by finite differences
+    of adj(F) on one P2 cell."""
+    rng = np.random.default_rng(5)
+    g = 3
+    dco = 0.05 * rng.uniform(-1, 1, size=(g, ft.n_p2(g)))
+
+    def adjF(pt):
+        _, dphi = ft.tabulate_p2(g, pt[None, :])
+        F = np.eye(g) + dco @ dphi[0]
+        return np.linalg.det(F) * np.linalg.inv(F)
+    pt = np.array([0.2, 0.3, 0.1])
+    h = 1e-5
+    div = np.zeros(g)
+    for a in range(g):
+        e = np.zeros(g)
+        e[a] = h
+        div += (adjF(pt + e)[a, :] - adjF(pt - e)[a, :]) / (2 * h)      # d_a A_ab
+    assert np.abs(div).max() < 1e-8
+
+
+@pytest.mark.parametrize("g,bih,deg,amp", [(3, False, 4, 0.5), (3, True, 4, 3.0), (2, False, 5, 0.2), (2, True, 4, 2.0)])
+def test_kernel_math_matches_oracle(emul, g, bih, deg, amp):
+    """host-compiled kernel mathematics (C' tensors, sum factorisation) vs complex-step oracle,
+    including a large-deformation state (amp=3: |grad d| ~ 0.2)."""
+    mesh, sp, x, x1 = _case(g, bih, amp)
+    common = dict(TUBE_PARAMS, extrapolation="biharmonic" if bih else "laplace")
+    cf = CellForms(g, bih, deg)
+    pts, wts = map(np.ascontiguousarray, ft.quadrature(g, deg))
+    X = np.ascontiguousarray(mesh.coords[mesh.cells])
+    u, u1 = np.ascontiguousarray(x[sp.cell_dofs]), np.ascontiguousarray(x1[sp.cell_dofs])
+    for reg in TUBE_REGIONS:
+        kind = 0 if reg["kind"] == "fluid" else 1
+        prm = oa.region_params(common, reg)
+        sel = mesh.markers == reg["marker"]
+        Xs, us, u1s = map(np.ascontiguousarray, (X[sel], u[sel], u1[sel]))
+        Jn = cf.jacobian(reg["kind"], Xs, us, u1s, prm, "nl")
+        Ae = np.zeros_like(Jn)
+        rc = emul.emul_jacobian(g, len(wts), _dp(pts), _dp(wts), kind, C.c_double(reg["rho"]), C.c_double(reg["mu"]),
+                                C.c_double(reg.get("lambda_", 0.0)), C.c_double(common["dt"]), C.c_double(common["theta"]),
+                                C.c_int64(len(Xs)), _dp(Xs), _dp(us), _dp(u1s), sp.ndof_cell, _dp(Ae))
+        assert rc == 0
+        scale = np.abs(Jn).max(axis=2, keepdims=True)
+        scale[scale == 0] = 1
+        assert (np.abs(Ae - Jn) / scale).max() < 1e-12
+        Rl, Rn = cf.residual(reg["kind"], Xs, us, u1s, prm)
+        Fe = np.zeros_like(Rl)
+        emul.emul_residual(g, len(wts), _dp(pts), _dp(wts), kind, C.c_double(reg["rho"]), C.c_double(reg["mu"]),
+                           C.c_double(reg.get("lambda_", 0.0)), C.c_double(common["dt"]), C.c_double(common["theta"]),
+                           1, 1, 2 if bih else 1, 0, C.c_double(0.0), C.c_double(0.0), C.c_int64(len(Xs)),
+                           _dp(Xs), _dp(us), _dp(u1s), sp.ndof_cell, _dp(Fe))
+        assert np.abs(Fe - (Rl + Rn)).max() < 1e-13 * np.abs(Rl + Rn).max()
+
+
+@pytest.mark.parametrize("g,n", [(3, 3), (2, 6)])
+def test_c_port_matches_numpy_oracle(g, n):
+    mesh = tube_mesh(n) if g == 3 else square_mesh(n)
+    sp = MixedSpace(mesh)
+    pat = sp.pattern()
+    x = synthetic_state(mesh, sp, 2024, h=1.0 / n)
+    x1 = synthetic_state(mesh, sp, 2025, h=1.0 / n)
+    degJ, degR = (4, 6) if g == 3 else (5, 10)
+    ref = oa.assemble_matrix(mesh, sp, TUBE_REGIONS, TUBE_PARAMS, x, x1, "nl", degJ, pat)
+    A = np.zeros(len(pat[1]))
+    cport.assemble_jacobian(mesh, sp, TUBE_REGIONS, 1e-3, 0.501, x, x1, ft.quadrature(g, degJ), pat, A)
+    rp = pat[0]
+    scale = np.maximum.reduceat(np.abs(ref), rp[:-1])
+    scale = np.repeat(np.where(scale > 0, scale, 1), np.diff(rp))
+    assert (np.abs(A - ref) / scale).max() < 1e-12
+    refb = oa.assemble_vector(mesh, sp, TUBE_REGIONS, TUBE_PARAMS, x, x1, degR)
+    b = np.zeros(sp.num_dofs)
+    cport.assemble_residual(mesh, sp, TUBE_REGIONS, 1e-3, 0.501, x, x1, ft.quadrature(g, degR), b)
+    assert np.abs(b - refb).max() < 1e-13 * np.abs(refb).max()
+
+
+def test_jacobian_block_structure():
+    """structurally non-zero blocks of J_nonlinear / J_linear."""
+    mesh, sp, x, x1 = _case(3, False, 0.5)
+    cf = CellForms(3, False, 4)
+    names = ["d"] * 30 + ["v"] * 30 + ["p"] * 4
+    X, u, u1 = mesh.coords[mesh.cells], x[sp.cell_dofs], x1[sp.cell_dofs]
+
+    def blocks(kind, marker, part):
+        sel = np.nonzero(mesh.markers == marker)[0][:4]
+        prm = oa.region_params(TUBE_PARAMS, TUBE_REGIONS[marker - 1])
+        nz = np.abs(cf.jacobian(kind, X[sel], u[sel], u1[sel], prm, part)).max(axis=0) > 0
+        return {(names[i], names[j]) for i in range(64) for j in range(64) if nz[i, j]}
+    assert blocks("fluid", 1, "nl") == {("v", "d"), ("v", "v"), ("v", "p"), ("p", "d"), ("p", "v")}
+    assert blocks("fluid", 1, "lin") == {("d", "d"), ("v", "v")}
+    assert blocks("solid", 2, "nl") == {("v", "d")}
+    assert blocks("solid", 2, "lin") == {("d", "d"), ("d", "v"), ("v", "v")}

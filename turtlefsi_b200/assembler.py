@@ -1,0 +1,192 @@
+"""Python host side of the hot path: owns the C-ABI handle and hands torch device buffers to it.
+
+Replaces, for turtleFSI's Newton solver (turtleFSI/modules/newtonsolver.py):
+  assemble(J_linear, keep_diagonal=True)                     :26-27  -> assemble_A_pre
+  assemble(J_nonlinear, tensor=A) ; A.axpy(1.0, A_pre, True) :75-79  -> assemble_jacobian
+  A.ident_zeros()                                            :81     -> ident_zeros
+  bc.apply(A) / bc.apply(b, x) / bc.apply(x)                 :82,91,98
+  assemble(-F, tensor=b)                                     :88     -> assemble_residual
+  b.norm('l2'), norm(dvp_res, 'l2')                          :105-106 -> norm
+PyTorch is plumbing only (device memory, streams, torch.distributed)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .quadrature import default_rule
+
+EXT_CODES = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2}
+LAPLACE_SUB = {"constant": 0, "small_constant": 1, "volume": 2}
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+class FSIAssembler:
+    """One handle = one mesh partition on one GPU.
+
+    regions: list of dicts {marker, kind ("fluid"|"solid"), rho, mu, lambda_} — what
+    turtleFSI/modules/domain.py:54-103 derives from dx_f_id / dx_s_id and the property lists.
+    """
+
+    def __init__(self, mesh, space, regions, dt, theta, fluid="fluid", solid="solid",
+                 extrapolation="laplace", extrapolation_sub_type="constant",
+                 quad_degree_jacobian=4, quad_degree_residual=None, gravity=None,
+                 pattern=None, device=None, verify_pattern=1, hmin=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("turtlefsi_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.mesh, self.space = mesh, space
+        g = mesh.gdim
+        if extrapolation not in EXT_CODES:
+            raise RuntimeError("extrapolation '%s' is not available on the B200 path" % extrapolation)
+        if extrapolation == "laplace" and extrapolation_sub_type not in LAPLACE_SUB:
+            raise RuntimeError("Could not find extrapolation method {}".format(extrapolation_sub_type))
+        if quad_degree_residual is None:
+            # assemble(-F) uses the global form-compiler degree; "auto" estimates
+            # 10 in 2-D; every 3-D problem file sets 6 (problem_aneu.py:12)
+            quad_degree_residual = 10 if g == 2 else 6
+        self.qJ = default_rule(g, quad_degree_jacobian)
+        self.qR = default_rule(g, quad_degree_residual)
+        if pattern is None:
+            pattern = space.pattern()
+        rowptr, colidx = pattern
+        dev = self.device
+
+        def to_dev(a, dtype):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=dev, dtype=dtype).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev)
+
+        self.rowptr = to_dev(rowptr, torch.int64)
+        self.colidx = to_dev(colidx, torch.int32)
+        self.num_dofs = int(space.num_dofs)
+        self.nnz = int(self.rowptr[-1].item())
+        coords = np.ascontiguousarray(mesh.coords, dtype=np.float64)
+        cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+        cdofs = np.ascontiguousarray(space.cell_dofs, dtype=np.int32)
+        marker = np.ascontiguousarray(mesh.markers, dtype=np.int32)
+        regs = (_lib.TfsiRegion * len(regions))()
+        for i, r in enumerate(regions):
+            regs[i].marker = int(r["marker"])
+            regs[i].kind = 0 if r["kind"] == "fluid" else 1
+            regs[i].rho = float(r["rho"])
+            regs[i].mu = float(r["mu"])
+            regs[i].lam = float(r.get("lambda_", 0.0))
+        p = _lib.TfsiProblem()
+        p.gdim, p.biharmonic = g, int(space.biharmonic)
+        p.num_vertices, p.num_cells, p.num_dofs = mesh.num_vertices, mesh.num_cells, self.num_dofs
+        p.coords, p.cell_vertices, p.cell_dofs = coords.ctypes.data, cells.ctypes.data, cdofs.ctypes.data
+        p.cell_marker = marker.ctypes.data
+        p.rowptr, p.colidx = self.rowptr.data_ptr(), self.colidx.data_ptr()
+        p.num_regions, p.regions = len(regions), regs
+        p.dt, p.theta = float(dt), float(theta)
+        p.fluid_on, p.solid_on = int(fluid == "fluid"), int(solid == "solid")
+        p.extrapolation = EXT_CODES[extrapolation]
+        p.extrapolation_sub_type = LAPLACE_SUB.get(extrapolation_sub_type, 0) if extrapolation == "laplace" else 0
+        p.hmin = float(hmin if hmin is not None else mesh.hmin())
+        p.gravity, p.has_gravity = (float(gravity), 1) if gravity is not None else (0.0, 0)
+        p.nq_jacobian, p.qpts_jacobian, p.qwts_jacobian = len(self.qJ[1]), self.qJ[0].ctypes.data, self.qJ[1].ctypes.data
+        p.nq_residual, p.qpts_residual, p.qwts_residual = len(self.qR[1]), self.qR[0].ctypes.data, self.qR[1].ctypes.data
+        p.verify_pattern = int(verify_pattern)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.tfsi_create(C.byref(p), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("tfsi_create failed (%d): %s" % (rc, self.lib.tfsi_last_error(None).decode()))
+        self.h = h
+        self.bc_dofs = None
+
+    # ------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("turtlefsi_b200 (%d): %s" % (rc, self.lib.tfsi_last_error(self.h).decode()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tfsi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def new_vector(self):
+        return torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
+
+    def new_matrix(self):
+        return torch.zeros(self.nnz, dtype=torch.float64, device=self.device)
+
+    def launch_count(self):
+        return int(self.lib.tfsi_launch_count(self.h))
+
+    # ------------------------------------------------------------------------------------
+    def assemble_A_pre(self, x, x1, out=None):
+        out = self.new_matrix() if out is None else out
+        self._check(self.lib.tfsi_assemble_A_pre(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
+        return out
+
+    def assemble_jacobian(self, x, x1, A_pre=None, out=None):
+        out = self.new_matrix() if out is None else out
+        self._check(self.lib.tfsi_assemble_jacobian(self.h, _ptr(x), _ptr(x1), _ptr(A_pre), _ptr(out), self._stream()))
+        return out
+
+    def assemble_residual(self, x, x1, out=None):
+        out = self.new_vector() if out is None else out
+        self._check(self.lib.tfsi_assemble_residual(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
+        return out
+
+    def ident_zeros(self, A):
+        self._check(self.lib.tfsi_ident_zeros(self.h, _ptr(A), self._stream()))
+
+    def set_bc_dofs(self, dofs):
+        d = np.ascontiguousarray(np.asarray(dofs), dtype=np.int32)
+        self._check(self.lib.tfsi_set_bc_dofs(self.h, C.c_void_p(d.ctypes.data), len(d)))
+        self.bc_dofs = d
+
+    def apply_bc_matrix(self, A):
+        self._check(self.lib.tfsi_apply_bc_matrix(self.h, _ptr(A), self._stream()))
+
+    def apply_bc_rhs(self, b, x, g):
+        self._check(self.lib.tfsi_apply_bc_rhs(self.h, _ptr(b), _ptr(x), _ptr(g), self._stream()))
+
+    def apply_bc_vec(self, x, g):
+        self._check(self.lib.tfsi_apply_bc_vec(self.h, _ptr(x), _ptr(g), self._stream()))
+
+    def sumsq(self, v):
+        out = C.c_double(0.0)
+        self._check(self.lib.tfsi_sumsq(self.h, _ptr(v), v.numel(), C.byref(out), self._stream()))
+        return out.value
+
+    def norm(self, v):
+        return float(np.sqrt(self.sumsq(v)))
+
+    def newton_assemble_host(self, x_host, x1_host, g_host, A_pre, A, b_host, recompute=True):
+        """reference-facing end-to-end call with HOST vectors (pinned torch tensors or numpy)."""
+        ss = C.c_double(0.0)
+        self._check(self.lib.tfsi_newton_assemble_host(
+            self.h, _ptr(x_host), _ptr(x1_host), _ptr(g_host), _ptr(A_pre), _ptr(A), _ptr(b_host),
+            C.byref(ss), int(bool(recompute))))
+        return ss.value
+
+
+def probe_fp64_peak():
+    """measured FP64 FMA throughput of the device (TFLOP/s) — the compute roofline denominator."""
+    lib = _lib.load()
+    tf, ms = C.c_double(0.0), C.c_double(0.0)
+    rc = lib.tfsi_probe_fp64_peak(C.byref(tf), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError("fp64 probe failed: %s" % lib.tfsi_last_error(None).decode())
+    return tf.value, ms.value

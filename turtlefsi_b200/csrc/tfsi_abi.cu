@@ -1,0 +1,466 @@
+// C ABI of libturtlefsi_b200.so (declared in include/turtlefsi_b200.h). Host orchestration only:
+// uploads, scatter-map construction, kernel launches. No CPU compute path exists.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/turtlefsi_b200.h"
+#include "tfsi_kernels.cuh"
+
+using namespace tfsi;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Region {
+    RegionConst rc;
+    int32_t marker;
+    int64_t ncells;
+    int32_t* cell_list;   // device
+};
+
+}  // namespace
+
+struct tfsi_handle {
+    int gdim, biharmonic, ndof, n2, n1;
+    int64_t nv, nc, N, nnz;
+    double *coords;
+    int32_t *cell_vertices, *cell_dofs, *colidx, *bc_dofs;
+    int64_t *rowptr, *diagpos;
+    uint16_t* rank;
+    double* scratch;          // 1 double (sumsq)
+    double *hx, *hx1, *hb, *hg;   // device staging for the _host entry
+    int64_t nbc;
+    std::vector<Region> regions;
+    QuadTab<MAXQ_J> tabJ;
+    QuadTab<MAXQ_R> tabR;
+    int fluid_on, solid_on, ext, ext_sub;
+    int64_t launches;
+    int sm_count;
+    std::string err;
+    int id;
+};
+
+namespace {
+
+int g_next_id = 1;
+int g_tab_owner = 0;     // id of the handle whose tables sit in constant memory
+
+int fail(tfsi_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, TFSI_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+    } while (0)
+
+template <class T>
+int upload(tfsi_handle* h, T** dst, const T* src, size_t n) {
+    CK(h, cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CK(h, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyDefault));
+    return 0;
+}
+
+int bind_tables(tfsi_handle* h, cudaStream_t st) {
+    if (g_tab_owner == h->id) return 0;
+    CK(h, cudaMemcpyToSymbolAsync(c_tabJ, &h->tabJ, sizeof h->tabJ, 0, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyToSymbolAsync(c_tabR, &h->tabR, sizeof h->tabR, 0, cudaMemcpyHostToDevice, st));
+    g_tab_owner = h->id;
+    return 0;
+}
+
+CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* x, const double* x1, double* out) {
+    CellArgs a;
+    a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
+    a.rank = h->rank; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.cell_alfa = nullptr;
+    a.ncell_region = r.ncells; a.ndof = h->ndof; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
+    return a;
+}
+
+int grid_for(int64_t n, int block, int sm) {
+    int64_t g = (n + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm * 16));
+}
+
+template <int G>
+int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A, cudaStream_t st) {
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
+        const int grid = (int)((r.ncells + 31) / 32);
+        if (r.rc.kind == TFSI_KIND_FLUID) {
+            if (!r.rc.fluid_on) continue;
+            size_t smem = JacSmem<G, FluidBase<G>::COUNT>::bytes(a.nq);
+            if (smem > 227 * 1024)
+                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
+            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_fluid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
+        } else {
+            if (!r.rc.solid_on) continue;
+            size_t smem = JacSmem<G, SolidBase<G>::COUNT>::bytes(a.nq);
+            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_solid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
+        }
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int G>
+int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, cudaStream_t st) {
+    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    const int off_d = 0, off_v = G * N2, off_w = 2 * G * N2 + N1;
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        LinArgs la;
+        la.c = cell_args(h, r, h->tabJ.nq, x, x1, A);
+        la.nblk = 0;
+        auto add = [&](int to, int tr, int mk, double cm, double ck, int per_vol) {
+            LinBlock b; b.test_off = to; b.trial_off = tr; b.mass_kind = mk; b.cm = cm; b.ck = ck;
+            b.ck_per_volume = per_vol; b.pad_ = 0; b.pad2_ = 0;
+            la.blk[la.nblk++] = b;
+        };
+        const RegionConst& rc = r.rc;
+        if (rc.kind == TFSI_KIND_FLUID) {
+            if (rc.fluid_on) add(off_v, off_v, 2, rc.c1lin, 0.0, 0);                  // fluid.py:33
+            if (rc.ext == TFSI_EXT_LAPLACE)                                             // laplace.py:45
+                add(off_d, off_d, 0, 0.0, rc.ext_sub == TFSI_LAPLACE_VOLUME ? 1.0 : rc.alfa,
+                    rc.ext_sub == TFSI_LAPLACE_VOLUME);
+            if (rc.ext == TFSI_EXT_BIHARMONIC) {                                        // biharmonic.py:35-36
+                add(off_w, off_w, 1, rc.alfa, 0.0, 0);
+                add(off_w, off_d, 0, 0.0, -rc.alfa, 0);
+                add(off_d, off_w, 0, 0.0, rc.alfa, 0);
+            }
+        } else if (rc.solid_on) {                                                       // solid.py:41-43
+            add(off_v, off_v, 1, rc.rho_s_k, 0.0, 0);
+            add(off_d, off_d, 1, rc.delta_rho_k, 0.0, 0);
+            add(off_d, off_v, 1, -rc.delta_rho * rc.th0, 0.0, 0);
+        }
+        if (la.nblk == 0) continue;
+        const int64_t ntask = r.ncells * la.nblk * 2;
+        lin_jacobian_kernel<G><<<(unsigned)((ntask + 127) / 128), 128, 0, st>>>(la);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int G, bool BIH>
+int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    constexpr int NDOF = (BIH ? 3 : 2) * G * Dim<G>::N2 + Dim<G>::N1;
+    const size_t smem = (size_t)NDOF * 32 * (2 * sizeof(double) + sizeof(int32_t));
+    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        const RegionConst& rc = r.rc;
+        if (rc.kind == TFSI_KIND_FLUID && !rc.fluid_on && rc.ext == 0) continue;
+        if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
+        CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
+        residual_kernel<G, BIH><<<(unsigned)((r.ncells + 31) / 32), RES_THREADS, smem, st>>>(a);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_residual(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    if (h->gdim == 3) return h->biharmonic ? launch_residual_t<3, true>(h, x, x1, b, st) : launch_residual_t<3, false>(h, x, x1, b, st);
+    return h->biharmonic ? launch_residual_t<2, true>(h, x, x1, b, st) : launch_residual_t<2, false>(h, x, x1, b, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tfsi_last_error(const tfsi_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t tfsi_nnz(const tfsi_handle* h) { return h ? h->nnz : -1; }
+int32_t tfsi_ndof_cell(const tfsi_handle* h) { return h ? h->ndof : -1; }
+int64_t tfsi_launch_count(const tfsi_handle* h) { return h ? h->launches : -1; }
+
+void tfsi_destroy(tfsi_handle* h) {
+    if (!h) return;
+    cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs); cudaFree(h->colidx);
+    cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
+    cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
+    for (Region& r : h->regions) cudaFree(r.cell_list);
+    if (g_tab_owner == h->id) g_tab_owner = 0;
+    delete h;
+}
+
+int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
+    if (!p || !out) return fail(nullptr, TFSI_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (p->gdim != 2 && p->gdim != 3) return fail(nullptr, TFSI_ERR_ARG, "gdim must be 2 or 3");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, TFSI_ERR_CUDA, "no CUDA device: turtlefsi_b200 has no CPU fallback");
+    tfsi_handle* h = new tfsi_handle();
+    h->id = g_next_id++;
+    const int g = p->gdim;
+    h->gdim = g; h->biharmonic = p->biharmonic ? 1 : 0;
+    h->n1 = g + 1; h->n2 = (g == 2) ? 6 : 10;
+    h->ndof = (h->biharmonic ? 3 : 2) * g * h->n2 + h->n1;
+    h->nv = p->num_vertices; h->nc = p->num_cells; h->N = p->num_dofs;
+    h->coords = nullptr; h->cell_vertices = h->cell_dofs = h->colidx = h->bc_dofs = nullptr;
+    h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
+    h->hx = h->hx1 = h->hb = h->hg = nullptr;
+    h->nbc = 0; h->launches = 0;
+    h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
+    if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+
+#define CKC(call) do { int rc_ = (call); if (rc_) { g_create_error = h->err; tfsi_destroy(h); return rc_; } } while (0)
+    if (tabulate<MAXQ_J>(g, p->nq_jacobian, p->qpts_jacobian, p->qwts_jacobian, h->tabJ) ||
+        tabulate<MAXQ_R>(g, p->nq_residual, p->qpts_residual, p->qwts_residual, h->tabR)) {
+        tfsi_destroy(h);
+        return fail(nullptr, TFSI_ERR_UNSUPPORTED, "quadrature rule too large (Jacobian <= %d, residual <= %d points)", MAXQ_J, MAXQ_R);
+    }
+    CKC(upload(h, &h->coords, p->coords, (size_t)h->nv * g));
+    CKC(upload(h, &h->cell_vertices, p->cell_vertices, (size_t)h->nc * (g + 1)));
+    CKC(upload(h, &h->cell_dofs, p->cell_dofs, (size_t)h->nc * h->ndof));
+    CKC(upload(h, &h->rowptr, p->rowptr, (size_t)h->N + 1));
+    {
+        int64_t nnz = 0;
+        cudaError_t e = cudaMemcpy(&nnz, h->rowptr + h->N, sizeof nnz, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "rowptr readback: %s", cudaGetErrorString(e)); }
+        h->nnz = nnz;
+    }
+    CKC(upload(h, &h->colidx, p->colidx, (size_t)h->nnz));
+    {
+        auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
+        CKC(cka(cudaMalloc((void**)&h->diagpos, (size_t)h->N * sizeof(int64_t))));
+        CKC(cka(cudaMalloc((void**)&h->rank, (size_t)h->nc * h->n2 * h->ndof * sizeof(uint16_t))));
+        CKC(cka(cudaMalloc((void**)&h->scratch, 64)));
+        CKC(cka(cudaMalloc((void**)&h->hx, (size_t)h->N * sizeof(double))));
+        CKC(cka(cudaMalloc((void**)&h->hx1, (size_t)h->N * sizeof(double))));
+        CKC(cka(cudaMalloc((void**)&h->hb, (size_t)h->N * sizeof(double))));
+    }
+    // regions: host pass over the markers
+    {
+        std::vector<int32_t> marker((size_t)h->nc);
+        cudaError_t e = cudaMemcpy(marker.data(), p->cell_marker, (size_t)h->nc * sizeof(int32_t), cudaMemcpyDefault);
+        if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "marker copy: %s", cudaGetErrorString(e)); }
+        for (int i = 0; i < p->num_regions; ++i) {
+            const tfsi_region& rg = p->regions[i];
+            Region r;
+            r.marker = rg.marker;
+            r.rc = make_region_const(rg.kind, rg.rho, rg.mu, rg.lambda, p->dt, p->theta, p->fluid_on, p->solid_on,
+                                     p->extrapolation, p->extrapolation_sub_type, p->hmin, p->has_gravity ? p->gravity : 0.0);
+            std::vector<int32_t> list;
+            for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
+            r.ncells = (int64_t)list.size();
+            r.cell_list = nullptr;
+            CKC(upload(h, &r.cell_list, list.data(), list.size()));
+            h->regions.push_back(r);
+        }
+    }
+    // scatter maps
+    {
+        int* derr = reinterpret_cast<int*>(h->scratch + 1);
+        cudaMemset(derr, 0, sizeof(int));
+        const int64_t total = h->nc * h->n2 * h->ndof;
+        build_rank_kernel<<<grid_for(total, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, h->nc, h->n2, h->ndof, derr);
+        diagpos_kernel<<<grid_for(h->N, 256, h->sm_count), 256>>>(h->rowptr, h->colidx, h->diagpos, h->N, derr);
+        int herr = 0;
+        cudaError_t e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "scatter-map kernels: %s", cudaGetErrorString(e)); }
+        if (herr) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_PATTERN, "%d cell-block entries (or diagonals) are missing from the CSR pattern, or a row exceeds 65535 entries", herr); }
+        if (p->verify_pattern) {
+            std::vector<int32_t> nol((size_t)h->ndof);
+            for (int r = 0; r < h->ndof; ++r) {
+                const int pofs = 2 * g * h->n2;
+                if (r < pofs) nol[r] = r % h->n2;
+                else if (r < pofs + h->n1) nol[r] = r - pofs;
+                else nol[r] = (r - pofs - h->n1) % h->n2;
+            }
+            int32_t* dnol = nullptr;
+            CKC(upload(h, &dnol, nol.data(), nol.size()));
+            const int64_t tot2 = h->nc * h->ndof * h->ndof;
+            const int64_t stride = (p->verify_pattern > 1) ? p->verify_pattern : 1;
+            verify_rank_kernel<<<grid_for(tot2 / stride + 1, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, dnol, h->nc, h->n2, h->ndof, stride, derr);
+            e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(dnol);
+            if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "verify kernel: %s", cudaGetErrorString(e)); }
+            if (herr) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_PATTERN, "CSR pattern is not a union of dense cell blocks with node-uniform column sets (%d mismatches)", herr); }
+        }
+    }
+#undef CKC
+    *out = h;
+    return TFSI_OK;
+}
+
+int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, double* Apre, void* stream) {
+    if (!h || !x || !x1 || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = bind_tables(h, st)) return rc;
+    CK(h, cudaMemsetAsync(Apre, 0, (size_t)h->nnz * sizeof(double), st));
+    return h->gdim == 3 ? launch_linear<3>(h, x, x1, Apre, st) : launch_linear<2>(h, x, x1, Apre, st);
+}
+
+int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, void* stream) {
+    if (!h || !x || !x1 || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = bind_tables(h, st)) return rc;
+    if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else CK(h, cudaMemsetAsync(A, 0, (size_t)h->nnz * sizeof(double), st));
+    return h->gdim == 3 ? launch_jacobian<3>(h, x, x1, A, st) : launch_jacobian<2>(h, x, x1, A, st);
+}
+
+int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b, void* stream) {
+    if (!h || !x || !x1 || !b) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = bind_tables(h, st)) return rc;
+    CK(h, cudaMemsetAsync(b, 0, (size_t)h->N * sizeof(double), st));
+    return launch_residual(h, x, x1, b, st);
+}
+
+int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {
+    if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    ident_zeros_kernel<<<grid_for(h->N * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, A, h->N, 3.0e-16);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc, int64_t n) {
+    if (!h || (n && !bc) || n < 0) return fail(h, TFSI_ERR_ARG, "bad argument");
+    cudaFree(h->bc_dofs); h->bc_dofs = nullptr;
+    cudaFree(h->hg); h->hg = nullptr;
+    h->nbc = n;
+    if (int rc = upload(h, &h->bc_dofs, bc, (size_t)n)) return rc;
+    CK(h, cudaMalloc((void**)&h->hg, std::max<size_t>((size_t)n, 1) * sizeof(double)));
+    return 0;
+}
+
+int tfsi_apply_bc_matrix(tfsi_handle* h, double* A, void* stream) {
+    if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (h->nbc == 0) return 0;
+    bc_matrix_kernel<<<grid_for(h->nbc * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, h->bc_dofs, h->nbc, A);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, void* stream) {
+    if (!h || !b || !x) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (h->nbc == 0) return 0;
+    if (!g) return fail(h, TFSI_ERR_ARG, "null BC values");
+    bc_rhs_kernel<<<grid_for(h->nbc, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->bc_dofs, h->nbc, b, x, g);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream) {
+    if (!h || !x) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (h->nbc == 0) return 0;
+    if (!g) return fail(h, TFSI_ERR_ARG, "null BC values");
+    bc_vec_kernel<<<grid_for(h->nbc, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->bc_dofs, h->nbc, x, g);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out, void* stream) {
+    if (!h || !v || !out) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(h, cudaMemsetAsync(h->scratch, 0, sizeof(double), st));
+    sumsq_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(v, n, h->scratch);
+    h->launches++;
+    CK(h, cudaMemcpyAsync(out, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host, const double* g_host,
+                              const double* Apre, double* A, double* b_host, double* out_sumsq_b, int32_t recompute) {
+    if (!h || !x_host || !x1_host || !b_host) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = 0;
+    const size_t nb = (size_t)h->N * sizeof(double);
+    CK(h, cudaMemcpyAsync(h->hx, x_host, nb, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, st));
+    if (h->nbc && g_host) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (recompute) {
+        if (!A) return fail(h, TFSI_ERR_ARG, "null A");
+        if (int rc = tfsi_assemble_jacobian(h, h->hx, h->hx1, Apre, A, st)) return rc;
+        if (int rc = tfsi_ident_zeros(h, A, st)) return rc;
+        if (int rc = tfsi_apply_bc_matrix(h, A, st)) return rc;
+    }
+    if (int rc = tfsi_assemble_residual(h, h->hx, h->hx1, h->hb, st)) return rc;
+    if (h->nbc && g_host) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, st)) return rc;
+    CK(h, cudaMemcpyAsync(b_host, h->hb, nb, cudaMemcpyDeviceToHost, st));
+    double ss = 0;
+    if (int rc = tfsi_sumsq(h, h->hb, h->N, &ss, st)) return rc;
+    if (out_sumsq_b) *out_sumsq_b = ss;
+    return 0;
+}
+
+int tfsi_halo_pack(tfsi_handle* h, const double* x, const int32_t* idx, int64_t n, double* buf, void* stream) {
+    if (!h || !x || (n && (!idx || !buf))) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (n == 0) return 0;
+    gather_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, idx, n, buf);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_halo_unpack(tfsi_handle* h, double* x, const int32_t* idx, int64_t n, const double* buf, void* stream) {
+    if (!h || !x || (n && (!idx || !buf))) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (n == 0) return 0;
+    scatter_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, idx, n, buf);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_probe_fp64_peak(double* out_tflops, double* out_ms) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, TFSI_ERR_CUDA, "no CUDA device");
+    int dev = 0, sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sm * 8, threads = 256, iters = 4096;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return fail(nullptr, TFSI_ERR_CUDA, "probe alloc");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_probe_kernel<<<blocks, threads>>>(d, iters, 1.0);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_probe_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return fail(nullptr, TFSI_ERR_CUDA, "probe: %s", cudaGetErrorString(e));
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (out_tflops) *out_tflops = flops / (best * 1e-3) / 1e12;
+    if (out_ms) *out_ms = best;
+    return 0;
+}
+
+}  // extern "C"

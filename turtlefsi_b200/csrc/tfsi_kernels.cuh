@@ -1,0 +1,624 @@
+// sm_100a kernels of the monolithic FSI assembly. FP64 vector pipe, no tensor cores (small
+// irregular contractions), HBM traffic = write-once CSR values + O(1 KB) of maps per cell.
+//
+// Thread mapping ("lane = cell"): one CTA owns 32 cells, lane l of EVERY warp works on cell l.
+//   stage  : the cell's dofs and the two state vectors are gathered into shared memory,
+//            lane-contiguous ([item][lane] => conflict-free, no bank replays);
+//   phase 0: thread (lane, q) evaluates the deformation-dependent per-point tensors of its cell
+//            at quadrature point q (fluid_base / solid_base) into shared memory;
+//   main   : the element matrix is cut into TASKS (one (test comp, trial comp) block half, or a
+//            small P2xP1 block). A warp fetches a task, every lane accumulates that block of ITS
+//            cell in registers over the quadrature loop. The reference tabulation is
+//            warp-uniform, so it is read through the constant bank / uniform registers and costs
+//            no shared-memory bandwidth: the inner loops are DFMA-only;
+//   scatter: fire-and-forget FP64 reductions (RED.E.ADD.F64) into the CSR values; the position
+//            of entry (row i, col j) is rowptr[row] + rank[cell][node(i)][j] with a 16-bit rank
+//            map (all dofs on one mesh node share their column set in a dense-cell-block
+//            pattern, so the map is per NODE, 1.3 KB/tet instead of 16 KB/tet of int32).
+#pragma once
+#include <cuda_runtime.h>
+#include "tfsi_math.cuh"
+
+namespace tfsi {
+
+__constant__ QuadTab<MAXQ_J> c_tabJ;
+__constant__ QuadTab<MAXQ_R> c_tabR;
+
+constexpr int CELLS_PER_CTA = 32;
+constexpr int JAC_WARPS = 12;
+constexpr int JAC_THREADS = JAC_WARPS * 32;
+constexpr int RES_WARPS = 8;
+constexpr int RES_THREADS = RES_WARPS * 32;
+
+struct CellArgs {
+    const double* coords;          // [nv][G]
+    const int32_t* cell_vertices;  // [nc][G+1]
+    const int32_t* cell_dofs;      // [nc][ndof]
+    const uint16_t* rank;          // [nc][N2][ndof]
+    const int64_t* rowptr;         // [N+1]
+    const int32_t* cell_list;      // cells of this region
+    const float* cell_alfa;        // unused (alfa computed in-kernel)
+    int64_t ncell_region;
+    int32_t ndof;                  // dofs per cell (27/39/64/94)
+    int32_t nq;
+    RegionConst rc;
+    const double* x;
+    const double* x1;
+    double* out;                   // A values or b
+};
+
+template <int G>
+__device__ __forceinline__ double load_geometry(const CellArgs& a, int64_t cell, double (&K)[G][G]) {
+    double X[G + 1][G];
+#pragma unroll
+    for (int v = 0; v <= G; ++v) {
+        int vid = a.cell_vertices[cell * (G + 1) + v];
+#pragma unroll
+        for (int c = 0; c < G; ++c) X[v][c] = a.coords[(int64_t)vid * G + c];
+    }
+    return cell_geometry<G>(X, K);
+}
+
+// shared-memory carve-up of the Jacobian kernels
+template <int G, int NBASE>
+struct JacSmem {
+    static constexpr int NCOEF = 2 * G * Dim<G>::N2 + Dim<G>::N1;       // d, v, p local dofs
+    static __host__ __device__ size_t bytes(int nq) {
+        return sizeof(double) * ((size_t)NBASE * nq * 32 + 2 * (size_t)NCOEF * 32) +
+               sizeof(int32_t) * (size_t)NCOEF * 32 + 16;
+    }
+};
+
+// scatter one P2xP2 half block: rows (row_off + i), cols (col_off + J0 + jj)
+template <int G, int J0, int NJ>
+__device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int32_t* sdofs, int lane,
+                                             int64_t cell, int row_off, int col_off,
+                                             const double (&Z)[Dim<G>::N2][NJ])
+{
+    constexpr int N2 = Dim<G>::N2;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        const int row = sdofs[(row_off + i) * 32 + lane];
+        double* dst = a.out + a.rowptr[row];
+        const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + col_off + J0;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj], Z[i][jj]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// FLUID non-linear Jacobian (fluid.py N1..N6 differentiated wrt d, v, p)
+template <int G, int FLD, int HALF>
+__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* base, const int32_t* sdofs,
+                                               int lane, int64_t cell, bool valid, int ca, int cb)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = N2 / 2, J0 = HALF * NJ;
+    double Z[N2][NJ];
+#pragma unroll
+    for (int i = 0; i < N2; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
+    const int nq = a.nq;
+    for (int q = 0; q < nq; ++q) {
+        auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+        double C[G + 1][G + 1];
+        if (FLD == 0) fluid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
+        else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
+        block_p2p2<G, J0, NJ, 7>(c_tabJ, q, C, Z);
+    }
+    if (valid)
+        scatter_p2p2<G, J0, NJ>(a, sdofs, lane, cell, G * N2 + ca * N2, FLD * G * N2 + cb * N2, Z);
+}
+
+template <int G>
+__global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
+{
+    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    typedef FluidBase<G> FB;
+    typedef JacSmem<G, FB::COUNT> SM;
+    constexpr int NCOEF = SM::NCOEF;
+    extern __shared__ double smem[];
+    const int nq = a.nq;
+    double* base = smem;
+    double* coef = base + (size_t)FB::COUNT * nq * 32;
+    double* coef1 = coef + NCOEF * 32;
+    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NCOEF * 32);
+    int* counter = sdofs + NCOEF * 32;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = idx < a.ncell_region;
+    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
+
+    if (threadIdx.x == 0) *counter = 0;
+    for (int k = warp; k < NCOEF; k += JAC_WARPS) {
+        int dof = a.cell_dofs[cell * a.ndof + k];
+        sdofs[k * 32 + lane] = dof;
+        coef[k * 32 + lane] = a.x[dof];
+        coef1[k * 32 + lane] = a.x1[dof];
+    }
+    __syncthreads();
+    {   // phase 0
+        double K[G][G];
+        const double adet = load_geometry<G>(a, cell, K);
+        auto cf = [&](int k) { return coef[k * 32 + lane]; };
+        auto cf1 = [&](int k) { return coef1[k * 32 + lane]; };
+        for (int q = warp; q < nq; q += JAC_WARPS) {
+            auto out = [&](int item, double v) { base[(item * nq + q) * 32 + lane] = v; };
+            fluid_base<G>(c_tabJ, q, K, adet, a.rc, cf, cf1, out);
+        }
+    }
+    __syncthreads();
+    constexpr int NBIG = 4 * G * G;                 // (field d|v) x a x b x half
+    constexpr int NTASK = NBIG + 3 * G;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= NTASK) break;
+        if (t < NBIG) {
+            const int fld = t / (2 * G * G), r = t % (2 * G * G);
+            const int ca = r / (2 * G), cb = (r >> 1) % G, half = r & 1;
+            if (fld == 0) {
+                if (half == 0) fluid_big_task<G, 0, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
+                else fluid_big_task<G, 0, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+            } else {
+                if (half == 0) fluid_big_task<G, 1, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
+                else fluid_big_task<G, 1, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+            }
+        } else if (t < NBIG + G) {                  // psi_a x delta p
+            const int ca = t - NBIG;
+            double Z[N2][N1];
+#pragma unroll
+            for (int i = 0; i < N2; ++i)
+#pragma unroll
+                for (int m = 0; m < N1; ++m) Z[i][m] = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+                double c[G];
+                fluid_c_psi_dp<G>(bv, ca, c);
+                block_gradp2_p1<G>(c_tabJ, q, c, Z);
+            }
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < N2; ++i) {
+                    const int row = sdofs[(G * N2 + ca * N2 + i) * 32 + lane];
+                    double* dst = a.out + a.rowptr[row];
+                    const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + 2 * G * N2;
+#pragma unroll
+                    for (int m = 0; m < N1; ++m) atomicAdd(dst + rk[m], Z[i][m]);
+                }
+            }
+        } else {                                    // gamma x delta d_b | delta v_b
+            const int r = t - NBIG - G;
+            const int fld = r / G, cb = r % G;
+            double Z[N1][N2];
+#pragma unroll
+            for (int m = 0; m < N1; ++m)
+#pragma unroll
+                for (int j = 0; j < N2; ++j) Z[m][j] = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+                double c[G];
+                if (fld == 0) fluid_c_gamma_dd<G>(bv, cb, c);
+                else fluid_c_gamma_dv<G>(bv, cb, c);
+                block_p1_gradp2<G>(c_tabJ, q, c, Z);
+            }
+            if (valid) {
+#pragma unroll
+                for (int m = 0; m < N1; ++m) {
+                    const int row = sdofs[(2 * G * N2 + m) * 32 + lane];
+                    double* dst = a.out + a.rowptr[row];
+                    const uint16_t* rk = a.rank + ((size_t)cell * N2 + m) * a.ndof + fld * G * N2 + cb * N2;
+#pragma unroll
+                    for (int j = 0; j < N2; ++j) atomicAdd(dst + rk[j], Z[m][j]);
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// SOLID non-linear Jacobian (solid.py:62, St.Venant-Kirchhoff)
+template <int G, int HALF>
+__device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* base, const int32_t* sdofs,
+                                               int lane, int64_t cell, bool valid, int ca, int cb)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = N2 / 2, J0 = HALF * NJ;
+    double Z[N2][NJ];
+#pragma unroll
+    for (int i = 0; i < N2; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
+    const int nq = a.nq;
+    for (int q = 0; q < nq; ++q) {
+        auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+        double C[G + 1][G + 1];
+        solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
+        block_p2p2<G, J0, NJ, 4>(c_tabJ, q, C, Z);
+    }
+    if (valid) scatter_p2p2<G, J0, NJ>(a, sdofs, lane, cell, G * N2 + ca * N2, cb * N2, Z);
+}
+
+template <int G>
+__global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
+{
+    constexpr int N2 = Dim<G>::N2;
+    typedef SolidBase<G> SB;
+    typedef JacSmem<G, SB::COUNT> SM;
+    constexpr int NCOEF = SM::NCOEF;
+    extern __shared__ double smem[];
+    const int nq = a.nq;
+    double* base = smem;
+    double* coef = base + (size_t)SB::COUNT * nq * 32;
+    double* coef1 = coef + NCOEF * 32;
+    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NCOEF * 32);
+    int* counter = sdofs + NCOEF * 32;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = idx < a.ncell_region;
+    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
+
+    if (threadIdx.x == 0) *counter = 0;
+    for (int k = warp; k < 2 * G * N2; k += JAC_WARPS) {
+        int dof = a.cell_dofs[cell * a.ndof + k];
+        sdofs[k * 32 + lane] = dof;
+        if (k < G * N2) coef[k * 32 + lane] = a.x[dof];
+    }
+    __syncthreads();
+    {
+        double K[G][G];
+        const double adet = load_geometry<G>(a, cell, K);
+        auto cf = [&](int k) { return coef[k * 32 + lane]; };
+        for (int q = warp; q < nq; q += JAC_WARPS) {
+            auto out = [&](int item, double v) { base[(item * nq + q) * 32 + lane] = v; };
+            solid_base<G>(c_tabJ, q, K, adet, a.rc, cf, out);
+        }
+    }
+    __syncthreads();
+    constexpr int NTASK = 2 * G * G;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= NTASK) break;
+        const int ca = t / (2 * G), cb = (t >> 1) % G, half = t & 1;
+        if (half == 0) solid_big_task<G, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
+        else solid_big_task<G, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// LINEAR part of the Jacobian (A_pre, assembled once): every block is delta_ab (cm phi_i phi_j +
+// ck grad phi_i . grad phi_j).  One thread per (cell, block descriptor, half); not a hot kernel.
+struct LinBlock {
+    int test_off;    // local dof offset of the test field (component 0)
+    int trial_off;   // local dof offset of the trial field
+    int mass_kind;   // 0 none, 1 constant cm, 2 cm * J(d^{n-1}) (fluid.py:33, frozen at setup)
+    int pad_;
+    double cm, ck;   // ck multiplies K K^T (already includes alfa for laplace "constant")
+    int ck_per_volume;   // laplace "volume": ck / cell volume
+    int pad2_;
+};
+constexpr int MAX_LINBLOCKS = 4;
+struct LinArgs {
+    CellArgs c;
+    LinBlock blk[MAX_LINBLOCKS];
+    int nblk;
+};
+
+template <int G>
+__global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = N2 / 2;
+    const CellArgs& a = la.c;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ntask = a.ncell_region * la.nblk * 2;
+    if (tid >= ntask) return;
+    const int64_t ci = tid / (la.nblk * 2);
+    const int r = (int)(tid % (la.nblk * 2));
+    const LinBlock blk = la.blk[r >> 1];
+    const int half = r & 1;
+    const int64_t cell = a.cell_list[ci];
+    double K[G][G];
+    const double adet = load_geometry<G>(a, cell, K);
+    const int32_t* dofs = a.cell_dofs + cell * a.ndof;
+    double KK[G][G];
+#pragma unroll
+    for (int s = 0; s < G; ++s)
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            double z = 0;
+#pragma unroll
+            for (int c = 0; c < G; ++c) z += K[s][c] * K[t][c];
+            KK[s][t] = z;
+        }
+    double ck = blk.ck;
+    if (blk.ck_per_volume) ck /= (adet / (G == 2 ? 2.0 : 6.0));
+    double Z[N2][NJ];
+#pragma unroll
+    for (int i = 0; i < N2; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
+    for (int q = 0; q < a.nq; ++q) {
+        const double jw = c_tabJ.w[q] * adet;
+        double cm = blk.cm;
+        if (blk.mass_kind == 2) {          // J(d^{n-1}) at this point
+            double F1[G][G];
+#pragma unroll
+            for (int aa = 0; aa < G; ++aa) {
+                double Gd[G];
+#pragma unroll
+                for (int t = 0; t < G; ++t) Gd[t] = 0;
+                for (int j = 0; j < N2; ++j) {
+                    double d1j = a.x1[dofs[aa * N2 + j]];
+#pragma unroll
+                    for (int t = 0; t < G; ++t) Gd[t] += d1j * c_tabJ.dphi2[q][j][t];
+                }
+#pragma unroll
+                for (int b = 0; b < G; ++b) {
+                    double s = (aa == b) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int t = 0; t < G; ++t) s += Gd[t] * K[t][b];
+                    F1[aa][b] = s;
+                }
+            }
+            cm *= det<G>(F1);
+        }
+        double C[G + 1][G + 1];
+        C[0][0] = (blk.mass_kind ? cm : 0.0) * jw;
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            C[0][1 + s] = 0; C[1 + s][0] = 0;
+#pragma unroll
+            for (int t = 0; t < G; ++t) C[1 + s][1 + t] = ck * jw * KK[s][t];
+        }
+        if (half == 0) block_p2p2<G, 0, NJ, 5>(c_tabJ, q, C, Z);
+        else block_p2p2<G, NJ, NJ, 5>(c_tabJ, q, C, Z);
+    }
+    const int j0 = half * NJ;
+    for (int comp = 0; comp < G; ++comp)
+        for (int i = 0; i < N2; ++i) {
+            const int row = dofs[blk.test_off + comp * N2 + i];
+            double* dst = a.out + a.rowptr[row];
+            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + blk.trial_off + comp * N2 + j0;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj], Z[i][jj]);
+        }
+}
+
+// -------------------------------------------------------------------------------------------
+// RESIDUAL b = -F.  lane = cell; warp w takes quadrature points w, w+8, ...; each thread keeps a
+// private partial cell vector in registers and reduces it into b with RED.ADD.F64.
+template <int G, bool BIH>
+__global__ void __launch_bounds__(RES_THREADS, 1) residual_kernel(CellArgs a)
+{
+    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    constexpr int NDOF = (BIH ? 3 : 2) * G * N2 + N1;
+    extern __shared__ double smem[];
+    double* coef = smem;
+    double* coef1 = coef + NDOF * 32;
+    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NDOF * 32);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = idx < a.ncell_region;
+    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
+    for (int k = warp; k < NDOF; k += RES_WARPS) {
+        int dof = a.cell_dofs[cell * a.ndof + k];
+        sdofs[k * 32 + lane] = dof;
+        coef[k * 32 + lane] = a.x[dof];
+        coef1[k * 32 + lane] = a.x1[dof];
+    }
+    __syncthreads();
+    double K[G][G];
+    const double adet = load_geometry<G>(a, cell, K);
+    double alfa_cell = a.rc.alfa;
+    if (a.rc.ext == 1 && a.rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
+    auto cf = [&](int k) { return coef[k * 32 + lane]; };
+    auto cf1 = [&](int k) { return coef1[k * 32 + lane]; };
+
+    double acc_psi[G][N2], acc_phi[G][N2], acc_gam[N1];
+    double acc_beta[BIH ? G : 1][N2];
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+#pragma unroll
+        for (int i = 0; i < N2; ++i) { acc_psi[c][i] = 0; acc_phi[c][i] = 0; if (BIH) acc_beta[c][i] = 0; }
+#pragma unroll
+    for (int m = 0; m < N1; ++m) acc_gam[m] = 0;
+
+    const bool fluid = a.rc.kind == 0;
+    const bool has_phi = fluid ? (a.rc.ext != 0) : (a.rc.solid_on != 0);
+    const bool has_psi = fluid ? (a.rc.fluid_on != 0) : (a.rc.solid_on != 0);
+    for (int q = warp; q < a.nq; q += RES_WARPS) {
+        PointFlux<G> f;
+        residual_point<G>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
+#pragma unroll
+        for (int i = 0; i < N2; ++i) {
+            const double ph = c_tabR.phi2[q][i];
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                double zp = acc_psi[c][i] + ph * f.psi_val[c];
+                double zd = acc_phi[c][i] + ph * f.phi_val[c];
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const double g = c_tabR.dphi2[q][i][s];
+                    zp += g * f.psi_grad[c][s];
+                    zd += g * f.phi_grad[c][s];
+                }
+                acc_psi[c][i] = zp; acc_phi[c][i] = zd;
+                if (BIH) {
+                    double zb = acc_beta[c][i] + ph * f.beta_val[c];
+#pragma unroll
+                    for (int s = 0; s < G; ++s) zb += c_tabR.dphi2[q][i][s] * f.beta_grad[c][s];
+                    acc_beta[c][i] = zb;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < N1; ++m) acc_gam[m] += c_tabR.phi1[q][m] * f.gamma;
+    }
+    if (!valid || warp >= a.nq) return;
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+#pragma unroll
+        for (int i = 0; i < N2; ++i) {
+            if (has_phi) atomicAdd(a.out + sdofs[(c * N2 + i) * 32 + lane], -acc_phi[c][i]);
+            if (has_psi) atomicAdd(a.out + sdofs[(G * N2 + c * N2 + i) * 32 + lane], -acc_psi[c][i]);
+            if (BIH && fluid && a.rc.ext == 2)
+                atomicAdd(a.out + sdofs[(2 * G * N2 + N1 + c * N2 + i) * 32 + lane], -acc_beta[c][i]);
+        }
+    if (fluid && a.rc.fluid_on) {
+#pragma unroll
+        for (int m = 0; m < N1; ++m) atomicAdd(a.out + sdofs[(2 * G * N2 + m) * 32 + lane], -acc_gam[m]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// set-up and vector kernels
+__device__ __forceinline__ int64_t find_col(const int32_t* colidx, int64_t lo, int64_t hi, int32_t col) {
+    while (lo < hi) {                 // first index with colidx >= col
+        int64_t mid = (lo + hi) >> 1;
+        if (colidx[mid] < col) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// rank[cell][node I][j] = position of column cell_dofs[cell][j] inside the CSR row of the first
+// dof (d_0) living on node I.  err[0] counts misses / overflows.
+__global__ void build_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
+                                  uint16_t* rank, int64_t ncells, int n2, int ndof, int* err)
+{
+    const int64_t total = ncells * n2 * ndof;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % ndof);
+        const int64_t ci = t / ndof;
+        const int i = (int)(ci % n2);
+        const int64_t cell = ci / n2;
+        const int32_t row = cell_dofs[cell * ndof + i];
+        const int32_t col = cell_dofs[cell * ndof + j];
+        const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+        const int64_t pos = find_col(colidx, lo, hi, col);
+        if (pos >= hi || colidx[pos] != col || pos - lo > 65535) { atomicAdd(err, 1); rank[t] = 0; }
+        else rank[t] = (uint16_t)(pos - lo);
+    }
+}
+
+// every row r of the cell (all fields) must see column j at rowptr[r] + rank[node(r)][j]
+__global__ void verify_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
+                                   const uint16_t* rank, const int32_t* node_of_local, int64_t ncells,
+                                   int n2, int ndof, int64_t stride, int* err)
+{
+    const int64_t total = ncells * ndof * ndof;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; t < total;
+         t += (int64_t)gridDim.x * blockDim.x * stride) {
+        const int j = (int)(t % ndof);
+        const int64_t cr = t / ndof;
+        const int r = (int)(cr % ndof);
+        const int64_t cell = cr / ndof;
+        const int32_t row = cell_dofs[cell * ndof + r];
+        const int64_t pos = rowptr[row] + rank[((size_t)cell * n2 + node_of_local[r]) * ndof + j];
+        if (pos >= rowptr[row + 1] || colidx[pos] != cell_dofs[cell * ndof + j]) atomicAdd(err, 1);
+    }
+}
+
+__global__ void diagpos_kernel(const int64_t* rowptr, const int32_t* colidx, int64_t* diagpos, int64_t n, int* err)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lo = rowptr[r], hi = rowptr[r + 1];
+        const int64_t pos = find_col(colidx, lo, hi, (int32_t)r);
+        if (pos >= hi || colidx[pos] != (int32_t)r) { atomicAdd(err, 1); diagpos[r] = lo; }
+        else diagpos[r] = pos;
+    }
+}
+
+// A.ident_zeros(): one warp per row
+__global__ void ident_zeros_kernel(const int64_t* rowptr, const int64_t* diagpos, double* A, int64_t n, double eps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = wid; r < n; r += nw) {
+        const int64_t lo = rowptr[r], hi = rowptr[r + 1];
+        double s = 0;
+        for (int64_t k = lo + lane; k < hi; k += 32) s += fabs(A[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s < eps) A[diagpos[r]] = 1.0;
+    }
+}
+
+__global__ void bc_matrix_kernel(const int64_t* rowptr, const int64_t* diagpos, const int32_t* bc, int64_t nbc, double* A)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = wid; b < nbc; b += nw) {
+        const int64_t r = bc[b];
+        const int64_t lo = rowptr[r], hi = rowptr[r + 1], dp = diagpos[r];
+        for (int64_t k = lo + lane; k < hi; k += 32) A[k] = (k == dp) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void bc_rhs_kernel(const int32_t* bc, int64_t nbc, double* b, const double* x, const double* g)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+        b[bc[i]] = g[i] - x[bc[i]];
+}
+
+__global__ void bc_vec_kernel(const int32_t* bc, int64_t nbc, double* x, const double* g)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+        x[bc[i]] = g[i];
+}
+
+__global__ void sumsq_kernel(const double* v, int64_t n, double* out)
+{
+    __shared__ double red[32];
+    double s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += v[i] * v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
+__global__ void gather_kernel(const double* x, const int32_t* idx, int64_t n, double* buf)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = x[idx[i]];
+}
+__global__ void scatter_kernel(double* x, const int32_t* idx, int64_t n, const double* buf)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[idx[i]] = buf[i];
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread, register resident
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tfsi
