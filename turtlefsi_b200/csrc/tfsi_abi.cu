@@ -28,7 +28,7 @@ struct Region {
 }  // namespace
 
 struct tfsi_handle {
-    int gdim, biharmonic, ndof, n2, n1;
+    int gdim, biharmonic, ndof, ndof_pad, n2, n1;
     int64_t nv, nc, N, nnz;
     double *coords;
     int32_t *cell_vertices, *cell_dofs, *colidx, *bc_dofs;
@@ -89,7 +89,7 @@ CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* 
     CellArgs a;
     a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
     a.rank = h->rank; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.cell_alfa = nullptr;
-    a.ncell_region = r.ncells; a.ndof = h->ndof; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
+    a.ncell_region = r.ncells; a.ndof = h->ndof; a.ndof_pad = h->ndof_pad; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
     return a;
 }
 
@@ -106,14 +106,14 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A
         const int grid = (int)((r.ncells + 31) / 32);
         if (r.rc.kind == TFSI_KIND_FLUID) {
             if (!r.rc.fluid_on) continue;
-            size_t smem = JacSmem<G, FluidBase<G>::COUNT>::bytes(a.nq);
+            size_t smem = FluidJac<G>::SM::bytes(a.nq);
             if (smem > 227 * 1024)
                 return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
             CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             jac_fluid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
         } else {
             if (!r.rc.solid_on) continue;
-            size_t smem = JacSmem<G, SolidBase<G>::COUNT>::bytes(a.nq);
+            size_t smem = SolidJac<G>::SM::bytes(a.nq);
             CK(h, cudaFuncSetAttribute(jac_solid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             jac_solid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
         }
@@ -217,6 +217,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->gdim = g; h->biharmonic = p->biharmonic ? 1 : 0;
     h->n1 = g + 1; h->n2 = (g == 2) ? 6 : 10;
     h->ndof = (h->biharmonic ? 3 : 2) * g * h->n2 + h->n1;
+    h->ndof_pad = (h->ndof + 7) & ~7;
     h->nv = p->num_vertices; h->nc = p->num_cells; h->N = p->num_dofs;
     h->coords = nullptr; h->cell_vertices = h->cell_dofs = h->colidx = h->bc_dofs = nullptr;
     h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
@@ -248,7 +249,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     {
         auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
         CKC(cka(cudaMalloc((void**)&h->diagpos, (size_t)h->N * sizeof(int64_t))));
-        CKC(cka(cudaMalloc((void**)&h->rank, (size_t)h->nc * h->n2 * h->ndof * sizeof(uint16_t))));
+        CKC(cka(cudaMalloc((void**)&h->rank, (size_t)h->nc * h->n2 * h->ndof_pad * sizeof(uint16_t))));
         CKC(cka(cudaMalloc((void**)&h->scratch, 64)));
         CKC(cka(cudaMalloc((void**)&h->hx, (size_t)h->N * sizeof(double))));
         CKC(cka(cudaMalloc((void**)&h->hx1, (size_t)h->N * sizeof(double))));
@@ -278,7 +279,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         int* derr = reinterpret_cast<int*>(h->scratch + 1);
         cudaMemset(derr, 0, sizeof(int));
         const int64_t total = h->nc * h->n2 * h->ndof;
-        build_rank_kernel<<<grid_for(total, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, h->nc, h->n2, h->ndof, derr);
+        build_rank_kernel<<<grid_for(total, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, h->nc, h->n2, h->ndof, h->ndof_pad, derr);
         diagpos_kernel<<<grid_for(h->N, 256, h->sm_count), 256>>>(h->rowptr, h->colidx, h->diagpos, h->N, derr);
         int herr = 0;
         cudaError_t e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
@@ -296,7 +297,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             CKC(upload(h, &dnol, nol.data(), nol.size()));
             const int64_t tot2 = h->nc * h->ndof * h->ndof;
             const int64_t stride = (p->verify_pattern > 1) ? p->verify_pattern : 1;
-            verify_rank_kernel<<<grid_for(tot2 / stride + 1, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, dnol, h->nc, h->n2, h->ndof, stride, derr);
+            verify_rank_kernel<<<grid_for(tot2 / stride + 1, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, dnol, h->nc, h->n2, h->ndof, h->ndof_pad, stride, derr);
             e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
             cudaFree(dnol);
             if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "verify kernel: %s", cudaGetErrorString(e)); }

@@ -25,7 +25,11 @@ __constant__ QuadTab<MAXQ_J> c_tabJ;
 __constant__ QuadTab<MAXQ_R> c_tabR;
 
 constexpr int CELLS_PER_CTA = 32;
-constexpr int JAC_WARPS = 12;
+#ifndef TFSI_JAC_WARPS
+#define TFSI_JAC_WARPS 8
+#endif
+// registers are allocated per 4 warps: 8 warps -> 255 regs/thread, 12 warps -> 168 (9..11 gain nothing)
+constexpr int JAC_WARPS = TFSI_JAC_WARPS;
 constexpr int JAC_THREADS = JAC_WARPS * 32;
 constexpr int RES_WARPS = 8;
 constexpr int RES_THREADS = RES_WARPS * 32;
@@ -34,12 +38,13 @@ struct CellArgs {
     const double* coords;          // [nv][G]
     const int32_t* cell_vertices;  // [nc][G+1]
     const int32_t* cell_dofs;      // [nc][ndof]
-    const uint16_t* rank;          // [nc][N2][ndof]
+    const uint16_t* rank;          // [nc][N2][ndof_pad]
     const int64_t* rowptr;         // [N+1]
     const int32_t* cell_list;      // cells of this region
     const float* cell_alfa;        // unused (alfa computed in-kernel)
     int64_t ncell_region;
     int32_t ndof;                  // dofs per cell (27/39/64/94)
+    int32_t ndof_pad;              // row stride of the rank map (multiple of 8 -> 16-byte rows)
     int32_t nq;
     RegionConst rc;
     const double* x;
@@ -59,38 +64,69 @@ __device__ __forceinline__ double load_geometry(const CellArgs& a, int64_t cell,
     return cell_geometry<G>(X, K);
 }
 
-// shared-memory carve-up of the Jacobian kernels
-template <int G, int NBASE>
+// shared-memory carve-up of the Jacobian kernels (byte offsets).
+//   base   [NBASE][nq][32] f64      per-point tensors, live for the whole CTA
+//   U      coef/coef1 [NCOEF][32] f64 during stage + phase 0; afterwards re-used (with TAIL) for
+//          srank [N2][NCOLS][32] u16 = scatter ranks of the 32 cells
+//   rowst  [NROWS][32] i64          CSR row starts of the rows this kernel scatters into
+template <int G, int NBASE, int NCOEF, int NCOLS, int NROWS>
 struct JacSmem {
-    static constexpr int NCOEF = 2 * G * Dim<G>::N2 + Dim<G>::N1;       // d, v, p local dofs
-    static __host__ __device__ size_t bytes(int nq) {
-        return sizeof(double) * ((size_t)NBASE * nq * 32 + 2 * (size_t)NCOEF * 32) +
-               sizeof(int32_t) * (size_t)NCOEF * 32 + 16;
-    }
+    static constexpr size_t U_BYTES = 2 * (size_t)NCOEF * 32 * sizeof(double);
+    static constexpr size_t RANK_BYTES = (size_t)Dim<G>::N2 * NCOLS * 32 * sizeof(uint16_t);
+    static constexpr size_t UR_BYTES = (U_BYTES > RANK_BYTES ? U_BYTES : RANK_BYTES);
+    static __host__ __device__ size_t off_u(int nq) { return sizeof(double) * (size_t)NBASE * nq * 32; }
+    static __host__ __device__ size_t off_rowst(int nq) { return off_u(nq) + UR_BYTES; }
+    static __host__ __device__ size_t off_counter(int nq) { return off_rowst(nq) + (size_t)NROWS * 32 * sizeof(int64_t); }
+    static __host__ __device__ size_t bytes(int nq) { return off_counter(nq) + 16; }
 };
 
-// scatter one P2xP2 half block: rows (row_off + i), cols (col_off + J0 + jj)
-template <int G, int J0, int NJ>
-__device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int32_t* sdofs, int lane,
-                                             int64_t cell, int row_off, int col_off,
+// copy the rank rows of the CTA's cells into shared memory, transposed to [i][col][lane]
+// (16-byte global loads: rows are padded to a multiple of 8 entries)
+template <int G, int NCOLS>
+__device__ __forceinline__ void stage_rank(const CellArgs& a, int64_t cell, int lane, int warp, int nwarps,
+                                           uint16_t* srank)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NCH = (NCOLS + 7) / 8;
+    for (int idx = warp; idx < N2 * NCH; idx += nwarps) {
+        const int i = idx / NCH, c0 = (idx % NCH) * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + c0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (c0 + t < NCOLS)
+                srank[((i * NCOLS) + c0 + t) * 32 + lane] = (uint16_t)(w[t >> 1] >> ((t & 1) * 16));
+    }
+}
+
+// scatter one P2xP2 half block: rows (row_loc + i) of the staged row starts, cols (col_off + J0 + jj)
+template <int G, int NCOLS, int J0, int NJ>
+__device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* rowst, const uint16_t* srank,
+                                             int lane, int row_loc, int col_off,
                                              const double (&Z)[Dim<G>::N2][NJ])
 {
     constexpr int N2 = Dim<G>::N2;
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
-        const int row = sdofs[(row_off + i) * 32 + lane];
-        double* dst = a.out + a.rowptr[row];
-        const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + col_off + J0;
+        double* dst = a.out + rowst[(row_loc + i) * 32 + lane];
+        const uint16_t* rk = srank + ((i * NCOLS) + col_off + J0) * 32 + lane;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj], Z[i][jj]);
+        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj * 32], Z[i][jj]);
     }
 }
 
 // -------------------------------------------------------------------------------------------
 // FLUID non-linear Jacobian (fluid.py N1..N6 differentiated wrt d, v, p)
+template <int G> struct FluidJac {
+    static constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    static constexpr int NCOEF = 2 * G * N2 + N1;     // local dofs d, v, p = trial columns
+    static constexpr int NROWS = G * N2 + N1;          // psi rows then gamma rows
+    typedef JacSmem<G, FluidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
+};
+
 template <int G, int FLD, int HALF>
-__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* base, const int32_t* sdofs,
-                                               int lane, int64_t cell, bool valid, int ca, int cb)
+__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
+                                               const uint16_t* srank, int lane, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = N2 / 2, J0 = HALF * NJ;
@@ -108,7 +144,7 @@ __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* 
         block_p2p2<G, J0, NJ, 7>(c_tabJ, q, C, Z);
     }
     if (valid)
-        scatter_p2p2<G, J0, NJ>(a, sdofs, lane, cell, G * N2 + ca * N2, FLD * G * N2 + cb * N2, Z);
+        scatter_p2p2<G, FluidJac<G>::NCOEF, J0, NJ>(a, rowst, srank, lane, ca * N2, FLD * G * N2 + cb * N2, Z);
 }
 
 template <int G>
@@ -116,15 +152,16 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     typedef FluidBase<G> FB;
-    typedef JacSmem<G, FB::COUNT> SM;
-    constexpr int NCOEF = SM::NCOEF;
-    extern __shared__ double smem[];
+    typedef typename FluidJac<G>::SM SM;
+    constexpr int NCOEF = FluidJac<G>::NCOEF, NROWS = FluidJac<G>::NROWS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = a.nq;
-    double* base = smem;
-    double* coef = base + (size_t)FB::COUNT * nq * 32;
+    double* base = reinterpret_cast<double*>(smem_raw);
+    double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     double* coef1 = coef + NCOEF * 32;
-    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NCOEF * 32);
-    int* counter = sdofs + NCOEF * 32;
+    uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
+    int64_t* rowst = reinterpret_cast<int64_t*>(smem_raw + SM::off_rowst(nq));
+    int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
@@ -133,10 +170,10 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 
     if (threadIdx.x == 0) *counter = 0;
     for (int k = warp; k < NCOEF; k += JAC_WARPS) {
-        int dof = a.cell_dofs[cell * a.ndof + k];
-        sdofs[k * 32 + lane] = dof;
+        const int dof = a.cell_dofs[cell * a.ndof + k];
         coef[k * 32 + lane] = a.x[dof];
         coef1[k * 32 + lane] = a.x1[dof];
+        if (k >= G * N2) rowst[(k - G * N2) * 32 + lane] = a.rowptr[dof];   // psi rows, gamma rows
     }
     __syncthreads();
     {   // phase 0
@@ -150,6 +187,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
         }
     }
     __syncthreads();
+    stage_rank<G, NCOEF>(a, cell, lane, warp, JAC_WARPS, srank);     // overwrites coef/coef1
+    __syncthreads();
     constexpr int NBIG = 4 * G * G;                 // (field d|v) x a x b x half
     constexpr int NTASK = NBIG + 3 * G;
     for (;;) {
@@ -161,11 +200,11 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
             const int fld = t / (2 * G * G), r = t % (2 * G * G);
             const int ca = r / (2 * G), cb = (r >> 1) % G, half = r & 1;
             if (fld == 0) {
-                if (half == 0) fluid_big_task<G, 0, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
-                else fluid_big_task<G, 0, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, 0, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+                else fluid_big_task<G, 0, 1>(a, base, rowst, srank, lane, valid, ca, cb);
             } else {
-                if (half == 0) fluid_big_task<G, 1, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
-                else fluid_big_task<G, 1, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, 1, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+                else fluid_big_task<G, 1, 1>(a, base, rowst, srank, lane, valid, ca, cb);
             }
         } else if (t < NBIG + G) {                  // psi_a x delta p
             const int ca = t - NBIG;
@@ -183,11 +222,10 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < N2; ++i) {
-                    const int row = sdofs[(G * N2 + ca * N2 + i) * 32 + lane];
-                    double* dst = a.out + a.rowptr[row];
-                    const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + 2 * G * N2;
+                    double* dst = a.out + rowst[(ca * N2 + i) * 32 + lane];
+                    const uint16_t* rk = srank + ((i * NCOEF) + 2 * G * N2) * 32 + lane;
 #pragma unroll
-                    for (int m = 0; m < N1; ++m) atomicAdd(dst + rk[m], Z[i][m]);
+                    for (int m = 0; m < N1; ++m) atomicAdd(dst + rk[m * 32], Z[i][m]);
                 }
             }
         } else {                                    // gamma x delta d_b | delta v_b
@@ -208,11 +246,10 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
             if (valid) {
 #pragma unroll
                 for (int m = 0; m < N1; ++m) {
-                    const int row = sdofs[(2 * G * N2 + m) * 32 + lane];
-                    double* dst = a.out + a.rowptr[row];
-                    const uint16_t* rk = a.rank + ((size_t)cell * N2 + m) * a.ndof + fld * G * N2 + cb * N2;
+                    double* dst = a.out + rowst[(G * N2 + m) * 32 + lane];
+                    const uint16_t* rk = srank + ((m * NCOEF) + fld * G * N2 + cb * N2) * 32 + lane;
 #pragma unroll
-                    for (int j = 0; j < N2; ++j) atomicAdd(dst + rk[j], Z[m][j]);
+                    for (int j = 0; j < N2; ++j) atomicAdd(dst + rk[j * 32], Z[m][j]);
                 }
             }
         }
@@ -221,9 +258,16 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 
 // -------------------------------------------------------------------------------------------
 // SOLID non-linear Jacobian (solid.py:62, St.Venant-Kirchhoff)
+template <int G> struct SolidJac {
+    static constexpr int N2 = Dim<G>::N2;
+    static constexpr int NCOEF = G * N2;               // d dofs = trial columns
+    static constexpr int NROWS = G * N2;               // psi rows
+    typedef JacSmem<G, SolidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
+};
+
 template <int G, int HALF>
-__device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* base, const int32_t* sdofs,
-                                               int lane, int64_t cell, bool valid, int ca, int cb)
+__device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
+                                               const uint16_t* srank, int lane, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = N2 / 2, J0 = HALF * NJ;
@@ -239,7 +283,7 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
         solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, J0, NJ, 4>(c_tabJ, q, C, Z);
     }
-    if (valid) scatter_p2p2<G, J0, NJ>(a, sdofs, lane, cell, G * N2 + ca * N2, cb * N2, Z);
+    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, J0, NJ>(a, rowst, srank, lane, ca * N2, cb * N2, Z);
 }
 
 template <int G>
@@ -247,15 +291,15 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
     typedef SolidBase<G> SB;
-    typedef JacSmem<G, SB::COUNT> SM;
-    constexpr int NCOEF = SM::NCOEF;
-    extern __shared__ double smem[];
+    typedef typename SolidJac<G>::SM SM;
+    constexpr int NCOEF = SolidJac<G>::NCOEF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = a.nq;
-    double* base = smem;
-    double* coef = base + (size_t)SB::COUNT * nq * 32;
-    double* coef1 = coef + NCOEF * 32;
-    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NCOEF * 32);
-    int* counter = sdofs + NCOEF * 32;
+    double* base = reinterpret_cast<double*>(smem_raw);
+    double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
+    uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
+    int64_t* rowst = reinterpret_cast<int64_t*>(smem_raw + SM::off_rowst(nq));
+    int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
@@ -264,9 +308,9 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
 
     if (threadIdx.x == 0) *counter = 0;
     for (int k = warp; k < 2 * G * N2; k += JAC_WARPS) {
-        int dof = a.cell_dofs[cell * a.ndof + k];
-        sdofs[k * 32 + lane] = dof;
+        const int dof = a.cell_dofs[cell * a.ndof + k];
         if (k < G * N2) coef[k * 32 + lane] = a.x[dof];
+        else rowst[(k - G * N2) * 32 + lane] = a.rowptr[dof];
     }
     __syncthreads();
     {
@@ -279,6 +323,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
         }
     }
     __syncthreads();
+    stage_rank<G, NCOEF>(a, cell, lane, warp, JAC_WARPS, srank);
+    __syncthreads();
     constexpr int NTASK = 2 * G * G;
     for (;;) {
         int t = 0;
@@ -286,8 +332,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= NTASK) break;
         const int ca = t / (2 * G), cb = (t >> 1) % G, half = t & 1;
-        if (half == 0) solid_big_task<G, 0>(a, base, sdofs, lane, cell, valid, ca, cb);
-        else solid_big_task<G, 1>(a, base, sdofs, lane, cell, valid, ca, cb);
+        if (half == 0) solid_big_task<G, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+        else solid_big_task<G, 1>(a, base, rowst, srank, lane, valid, ca, cb);
     }
 }
 
@@ -385,7 +431,7 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
         for (int i = 0; i < N2; ++i) {
             const int row = dofs[blk.test_off + comp * N2 + i];
             double* dst = a.out + a.rowptr[row];
-            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof + blk.trial_off + comp * N2 + j0;
+            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + blk.trial_off + comp * N2 + j0;
 #pragma unroll
             for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj], Z[i][jj]);
         }
@@ -491,7 +537,7 @@ __device__ __forceinline__ int64_t find_col(const int32_t* colidx, int64_t lo, i
 // rank[cell][node I][j] = position of column cell_dofs[cell][j] inside the CSR row of the first
 // dof (d_0) living on node I.  err[0] counts misses / overflows.
 __global__ void build_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
-                                  uint16_t* rank, int64_t ncells, int n2, int ndof, int* err)
+                                  uint16_t* rank, int64_t ncells, int n2, int ndof, int ndof_pad, int* err)
 {
     const int64_t total = ncells * n2 * ndof;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -504,15 +550,16 @@ __global__ void build_rank_kernel(const int32_t* cell_dofs, const int64_t* rowpt
         const int32_t col = cell_dofs[cell * ndof + j];
         const int64_t lo = rowptr[row], hi = rowptr[row + 1];
         const int64_t pos = find_col(colidx, lo, hi, col);
-        if (pos >= hi || colidx[pos] != col || pos - lo > 65535) { atomicAdd(err, 1); rank[t] = 0; }
-        else rank[t] = (uint16_t)(pos - lo);
+        const size_t o = ((size_t)cell * n2 + i) * ndof_pad + j;
+        if (pos >= hi || colidx[pos] != col || pos - lo > 65535) { atomicAdd(err, 1); rank[o] = 0; }
+        else rank[o] = (uint16_t)(pos - lo);
     }
 }
 
 // every row r of the cell (all fields) must see column j at rowptr[r] + rank[node(r)][j]
 __global__ void verify_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
                                    const uint16_t* rank, const int32_t* node_of_local, int64_t ncells,
-                                   int n2, int ndof, int64_t stride, int* err)
+                                   int n2, int ndof, int ndof_pad, int64_t stride, int* err)
 {
     const int64_t total = ncells * ndof * ndof;
     for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; t < total;
@@ -522,7 +569,7 @@ __global__ void verify_rank_kernel(const int32_t* cell_dofs, const int64_t* rowp
         const int r = (int)(cr % ndof);
         const int64_t cell = cr / ndof;
         const int32_t row = cell_dofs[cell * ndof + r];
-        const int64_t pos = rowptr[row] + rank[((size_t)cell * n2 + node_of_local[r]) * ndof + j];
+        const int64_t pos = rowptr[row] + rank[((size_t)cell * n2 + node_of_local[r]) * ndof_pad + j];
         if (pos >= rowptr[row + 1] || colidx[pos] != cell_dofs[cell * ndof + j]) atomicAdd(err, 1);
     }
 }
