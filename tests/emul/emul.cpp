@@ -34,7 +34,7 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
             auto out = [&](int item, double v) { base[(size_t)item * nq + q] = v; };
             fluid_base<G>(tab, q, K, adet, rc, cf, cf1, out);
         }
-        constexpr int NJ = N2 / 2;
+        constexpr int NJ = HalfCols<G, 0>::NJ;
         for (int fld = 0; fld < 2; ++fld)
             for (int a = 0; a < G; ++a)
                 for (int b = 0; b < G; ++b)
@@ -45,9 +45,12 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
                             auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
                             double C[G + 1][G + 1];
                             if (fld == 0) fluid_C_psi_dd<G>(bv, rc, a, b, C); else fluid_C_psi_dv<G>(bv, rc, a, b, C);
-                            if (half == 0) block_p2p2<G, 0, NJ, 7>(tab, q, C, Z); else block_p2p2<G, NJ, NJ, 7>(tab, q, C, Z);
+                            if (half == 0) block_p2p2<G, 0, 7>(tab, q, C, Z); else block_p2p2<G, 1, 7>(tab, q, C, Z);
                         }
-                        addblock(G * N2 + a * N2, fld * G * N2 + b * N2 + half * NJ, N2, NJ, &Z[0][0], NJ);
+                        for (int i = 0; i < N2; ++i) for (int jj = 0; jj < NJ; ++jj) {
+                            int j = half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj);
+                            Ae[(G * N2 + a * N2 + i) * ndof + fld * G * N2 + b * N2 + j] += Z[i][jj];
+                        }
                     }
         for (int a = 0; a < G; ++a) {
             double Z[N2][N1];
@@ -79,7 +82,7 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
             auto out = [&](int item, double v) { base[(size_t)item * nq + q] = v; };
             solid_base<G>(tab, q, K, adet, rc, cf, out);
         }
-        constexpr int NJ = N2 / 2;
+        constexpr int NJ = HalfCols<G, 0>::NJ;
         for (int a = 0; a < G; ++a)
             for (int b = 0; b < G; ++b)
                 for (int half = 0; half < 2; ++half) {
@@ -89,9 +92,12 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
                         auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
                         double C[G + 1][G + 1];
                         solid_C_psi_dd<G>(bv, rc, a, b, C);
-                        if (half == 0) block_p2p2<G, 0, NJ, 4>(tab, q, C, Z); else block_p2p2<G, NJ, NJ, 4>(tab, q, C, Z);
+                        if (half == 0) block_p2p2<G, 0, 4>(tab, q, C, Z); else block_p2p2<G, 1, 4>(tab, q, C, Z);
                     }
-                    addblock(G * N2 + a * N2, b * N2 + half * NJ, N2, NJ, &Z[0][0], NJ);
+                    for (int i = 0; i < N2; ++i) for (int jj = 0; jj < NJ; ++jj) {
+                        int j = half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj);
+                        Ae[(G * N2 + a * N2 + i) * ndof + b * N2 + j] += Z[i][jj];
+                    }
                 }
     }
 }

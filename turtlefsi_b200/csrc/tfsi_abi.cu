@@ -109,13 +109,24 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A
             size_t smem = FluidJac<G>::SM::bytes(a.nq);
             if (smem > 227 * 1024)
                 return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
-            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_fluid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
+            // compile-time quadrature size for the rule of the headline config (Keast 14-point)
+            if (G == 3 && a.nq == 14) {
+                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_fluid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
+            } else {
+                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_fluid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
+            }
         } else {
             if (!r.rc.solid_on) continue;
             size_t smem = SolidJac<G>::SM::bytes(a.nq);
-            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G><<<grid, JAC_THREADS, smem, st>>>(a);
+            if (G == 3 && a.nq == 14) {
+                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_solid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
+            } else {
+                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_solid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
+            }
         }
         h->launches++;
         CK(h, cudaGetLastError());

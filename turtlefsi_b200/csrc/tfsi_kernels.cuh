@@ -99,19 +99,20 @@ __device__ __forceinline__ void stage_rank(const CellArgs& a, int64_t cell, int 
     }
 }
 
-// scatter one P2xP2 half block: rows (row_loc + i) of the staged row starts, cols (col_off + J0 + jj)
-template <int G, int NCOLS, int J0, int NJ>
+// scatter one P2xP2 half block: rows (row_loc + i) of the staged row starts, cols col_off + HalfCols
+template <int G, int NCOLS, int HALF>
 __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* rowst, const uint16_t* srank,
                                              int lane, int row_loc, int col_off,
-                                             const double (&Z)[Dim<G>::N2][NJ])
+                                             const double (&Z)[Dim<G>::N2][HalfCols<G, HALF>::NJ])
 {
     constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = HalfCols<G, HALF>::NJ;
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
         double* dst = a.out + rowst[(row_loc + i) * 32 + lane];
-        const uint16_t* rk = srank + ((i * NCOLS) + col_off + J0) * 32 + lane;
+        const uint16_t* rk = srank + ((i * NCOLS) + col_off) * 32 + lane;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj * 32], Z[i][jj]);
+        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * 32], Z[i][jj]);
     }
 }
 
@@ -124,30 +125,31 @@ template <int G> struct FluidJac {
     typedef JacSmem<G, FluidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
 };
 
-template <int G, int FLD, int HALF>
+template <int G, int NQ, int FLD, int HALF>
 __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
                                                const uint16_t* srank, int lane, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
-    constexpr int NJ = N2 / 2, J0 = HALF * NJ;
+    constexpr int NJ = HalfCols<G, HALF>::NJ;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
-    const int nq = a.nq;
+    const int nq = NQ ? NQ : a.nq;
+#pragma unroll 1
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
         double C[G + 1][G + 1];
         if (FLD == 0) fluid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
-        block_p2p2<G, J0, NJ, 7>(c_tabJ, q, C, Z);
+        block_p2p2<G, HALF, 7>(c_tabJ, q, C, Z);
     }
     if (valid)
-        scatter_p2p2<G, FluidJac<G>::NCOEF, J0, NJ>(a, rowst, srank, lane, ca * N2, FLD * G * N2 + cb * N2, Z);
+        scatter_p2p2<G, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, lane, ca * N2, FLD * G * N2 + cb * N2, Z);
 }
 
-template <int G>
+template <int G, int NQ>
 __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
     typedef typename FluidJac<G>::SM SM;
     constexpr int NCOEF = FluidJac<G>::NCOEF, NROWS = FluidJac<G>::NROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nq = a.nq;
+    const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     double* coef1 = coef + NCOEF * 32;
@@ -200,11 +202,11 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
             const int fld = t / (2 * G * G), r = t % (2 * G * G);
             const int ca = r / (2 * G), cb = (r >> 1) % G, half = r & 1;
             if (fld == 0) {
-                if (half == 0) fluid_big_task<G, 0, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-                else fluid_big_task<G, 0, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+                else fluid_big_task<G, NQ, 0, 1>(a, base, rowst, srank, lane, valid, ca, cb);
             } else {
-                if (half == 0) fluid_big_task<G, 1, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-                else fluid_big_task<G, 1, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+                else fluid_big_task<G, NQ, 1, 1>(a, base, rowst, srank, lane, valid, ca, cb);
             }
         } else if (t < NBIG + G) {                  // psi_a x delta p
             const int ca = t - NBIG;
@@ -265,28 +267,29 @@ template <int G> struct SolidJac {
     typedef JacSmem<G, SolidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
 };
 
-template <int G, int HALF>
+template <int G, int NQ, int HALF>
 __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
                                                const uint16_t* srank, int lane, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
-    constexpr int NJ = N2 / 2, J0 = HALF * NJ;
+    constexpr int NJ = HalfCols<G, HALF>::NJ;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
-    const int nq = a.nq;
+    const int nq = NQ ? NQ : a.nq;
+#pragma unroll 1
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
         double C[G + 1][G + 1];
         solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
-        block_p2p2<G, J0, NJ, 4>(c_tabJ, q, C, Z);
+        block_p2p2<G, HALF, 4>(c_tabJ, q, C, Z);
     }
-    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, J0, NJ>(a, rowst, srank, lane, ca * N2, cb * N2, Z);
+    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, lane, ca * N2, cb * N2, Z);
 }
 
-template <int G>
+template <int G, int NQ>
 __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
     typedef typename SolidJac<G>::SM SM;
     constexpr int NCOEF = SolidJac<G>::NCOEF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nq = a.nq;
+    const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
@@ -332,8 +335,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= NTASK) break;
         const int ca = t / (2 * G), cb = (t >> 1) % G, half = t & 1;
-        if (half == 0) solid_big_task<G, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-        else solid_big_task<G, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+        if (half == 0) solid_big_task<G, NQ, 0>(a, base, rowst, srank, lane, valid, ca, cb);
+        else solid_big_task<G, NQ, 1>(a, base, rowst, srank, lane, valid, ca, cb);
     }
 }
 
@@ -360,7 +363,7 @@ template <int G>
 __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
 {
     constexpr int N2 = Dim<G>::N2;
-    constexpr int NJ = N2 / 2;
+    constexpr int NJ = HalfCols<G, 0>::NJ;
     const CellArgs& a = la.c;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ntask = a.ncell_region * la.nblk * 2;
@@ -423,17 +426,17 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
 #pragma unroll
             for (int t = 0; t < G; ++t) C[1 + s][1 + t] = ck * jw * KK[s][t];
         }
-        if (half == 0) block_p2p2<G, 0, NJ, 5>(c_tabJ, q, C, Z);
-        else block_p2p2<G, NJ, NJ, 5>(c_tabJ, q, C, Z);
+        if (half == 0) block_p2p2<G, 0, 5>(c_tabJ, q, C, Z);
+        else block_p2p2<G, 1, 5>(c_tabJ, q, C, Z);
     }
-    const int j0 = half * NJ;
     for (int comp = 0; comp < G; ++comp)
         for (int i = 0; i < N2; ++i) {
             const int row = dofs[blk.test_off + comp * N2 + i];
             double* dst = a.out + a.rowptr[row];
-            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + blk.trial_off + comp * N2 + j0;
+            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + blk.trial_off + comp * N2;
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[jj], Z[i][jj]);
+            for (int jj = 0; jj < NJ; ++jj)
+                atomicAdd(dst + rk[half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj)], Z[i][jj]);
         }
 }
 

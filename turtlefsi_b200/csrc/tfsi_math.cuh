@@ -37,6 +37,8 @@ struct QuadTab {
     double phi2[MAXQ][10];
     double dphi2[MAXQ][10][3];
     double phi1[MAXQ][4];
+    double d4[MAXQ][4];    // 4 lambda_v - 1   (P2 vertex-function gradient factor)
+    double l4[MAXQ][4];    // 4 lambda_v       (P2 edge-function gradient factors)
 };
 
 template <int G> struct Dim {
@@ -118,18 +120,19 @@ struct RegionConst {
 };
 
 // ---------------------------------------------------------------------------------------------
-// FLUID, non-linear Jacobian: per-point base items (stored lane-contiguous in shared memory)
+// FLUID, non-linear Jacobian: per-point base items (stored lane-contiguous in shared memory).
+// Items are PRE-SCALED in phase 0 so that every C' entry costs <= 4 FMAs and few loads:
+//   k4 = theta0 mu J w ;  sigma = mu (H + H^T)
 template <int G> struct FluidBase {
     static constexpr int JW = 0;                    // J w |detJgeo|
-    static constexpr int B = 1;                     // B[t][c]       G*G
-    static constexpr int H = B + G * G;             // H = grad v F^-1
-    static constexpr int M = H + G * G;             // M = B B^T     packed sym
-    static constexpr int BU = M + Dim<G>::NS;       // B u,  u = th0 rho v - rho/k (d - d1)
-    static constexpr int XA = BU + G;               // c1 (v - v1) + H u
-    static constexpr int P = XA + G;                // pressure
-    static constexpr int S = P + 1;                 // S = B sigma,  sigma = mu (H + H^T)
-    static constexpr int R = S + G * G;             // R = B H
-    static constexpr int COUNT = R + G * G;         // 50 (3-D), 25 (2-D)
+    static constexpr int B = 1;                     // B[t][c] = (K F^-1)[t][c]          G*G
+    static constexpr int H = B + G * G;             // H = grad v F^-1                    G*G
+    static constexpr int MJ = H + G * G;            // k4 * B B^T                         packed sym
+    static constexpr int BUJ = MJ + Dim<G>::NS;     // Jw * B u,  u = th0 rho v - rho/k (d - d1)
+    static constexpr int XJ = BUJ + G;              // Jw * (c1 (v - v1) + H u)
+    static constexpr int PJ = XJ + G;               // Jw * (theta0 B sigma - p B)        G*G
+    static constexpr int RJ = PJ + G * G;           // k4 * B H                           G*G
+    static constexpr int COUNT = RJ + G * G;        // 49 (3-D), 24 (2-D)
 };
 
 // coefficient access: cf(k) returns local dof k of the cell at time n, cf1(k) at n-1
@@ -198,15 +201,16 @@ TFSI_HD void fluid_base(const Tab& tab, int q, const double (&K)[G][G], double a
 #pragma unroll
     for (int a = 0; a < G; ++a) u[a] = rc.th0rho * v[a] - rc.rk * dd[a];
 
-    out(I::JW, J * tab.w[q] * adet);
-    out(I::P, p);
+    const double Jw = J * tab.w[q] * adet;
+    const double k4 = rc.th0 * rc.mu * Jw;
+    out(I::JW, Jw);
 #pragma unroll
     for (int t = 0; t < G; ++t) {
         double bu = 0, hu = 0;
 #pragma unroll
         for (int c = 0; c < G; ++c) { bu += Bm[t][c] * u[c]; hu += Hm[t][c] * u[c]; }
-        out(I::BU + t, bu);
-        out(I::XA + t, rc.c1 * dv[t] + hu);
+        out(I::BUJ + t, Jw * bu);
+        out(I::XJ + t, Jw * (rc.c1 * dv[t] + hu));
 #pragma unroll
         for (int c = 0; c < G; ++c) {
             out(I::B + t * G + c, Bm[t][c]);
@@ -217,13 +221,13 @@ TFSI_HD void fluid_base(const Tab& tab, int q, const double (&K)[G][G], double a
                 r += Bm[t][e] * Hm[e][c];
                 s += Bm[t][e] * (Hm[e][c] + Hm[c][e]);
             }
-            out(I::R + t * G + c, r);
-            out(I::S + t * G + c, rc.mu * s);
+            out(I::RJ + t * G + c, k4 * r);
+            out(I::PJ + t * G + c, k4 * s - Jw * p * Bm[t][c]);
             if (c >= t) {
                 double m = 0;
 #pragma unroll
                 for (int e = 0; e < G; ++e) m += Bm[t][e] * Bm[c][e];
-                out(I::M + symi(t, c, G), m);
+                out(I::MJ + symi(t, c, G), k4 * m);
             }
         }
     }
@@ -240,47 +244,46 @@ TFSI_HD void fluid_C_psi_dv(BV bv, const RegionConst& rc, int a, int b, double (
     const double dab = (a == b) ? 1.0 : 0.0;
     C[0][0] = Jw * (rc.c1 * dab + rc.th0rho * bv(I::H + a * G + b));
     const double k4 = Jw * rc.th0 * rc.mu;
+    double kBa[G];
 #pragma unroll
     for (int t = 0; t < G; ++t) {
-        C[0][1 + t] = dab * Jw * bv(I::BU + t);
+        C[0][1 + t] = dab * bv(I::BUJ + t);
+        C[1 + t][0] = 0.0;
+        kBa[t] = k4 * bv(I::B + t * G + a);
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+        const double Bsb = bv(I::B + s * G + b);
+#pragma unroll
+        for (int t = 0; t < G; ++t)
+            C[1 + s][1 + t] = dab * bv(I::MJ + symi(s, t, G)) + kBa[t] * Bsb;
+    }
+}
+
+// C' of the block  psi_a x delta d_b  (shape derivatives of N1..N4, N6):
+//   C'_st = PJ_sa B_tb - PJ_ta B_sb - H_ab MJ_st - B_ta RJ_sb
+template <int G, class BV>
+TFSI_HD void fluid_C_psi_dd(BV bv, const RegionConst& rc, int a, int b, double (&C)[G + 1][G + 1])
+{
+    typedef FluidBase<G> I;
+    const double Hab = bv(I::H + a * G + b);
+    const double XJa = bv(I::XJ + a);
+    C[0][0] = -bv(I::JW) * rc.rk * Hab;
+    double Ba[G], Bb[G], Pa[G], Rb[G];
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+        Ba[t] = bv(I::B + t * G + a);
+        Bb[t] = bv(I::B + t * G + b);
+        Pa[t] = bv(I::PJ + t * G + a);
+        Rb[t] = bv(I::RJ + t * G + b);
+        C[0][1 + t] = XJa * Bb[t] - Hab * bv(I::BUJ + t);
         C[1 + t][0] = 0.0;
     }
 #pragma unroll
     for (int s = 0; s < G; ++s)
 #pragma unroll
         for (int t = 0; t < G; ++t)
-            C[1 + s][1 + t] = k4 * (dab * bv(I::M + symi(s, t, G)) + bv(I::B + t * G + a) * bv(I::B + s * G + b));
-}
-
-// C' of the block  psi_a x delta d_b  (shape derivatives of N1..N4, N6)
-template <int G, class BV>
-TFSI_HD void fluid_C_psi_dd(BV bv, const RegionConst& rc, int a, int b, double (&C)[G + 1][G + 1])
-{
-    typedef FluidBase<G> I;
-    const double Jw = bv(I::JW);
-    const double Hab = bv(I::H + a * G + b);
-    const double Xa = bv(I::XA + a);
-    const double p = bv(I::P);
-    C[0][0] = -Jw * rc.rk * Hab;
-#pragma unroll
-    for (int t = 0; t < G; ++t) {
-        C[0][1 + t] = Jw * (Xa * bv(I::B + t * G + b) - Hab * bv(I::BU + t));
-        C[1 + t][0] = 0.0;
-    }
-    const double muH = rc.mu * Hab;
-#pragma unroll
-    for (int s = 0; s < G; ++s) {
-        const double Bsa = bv(I::B + s * G + a), Bsb = bv(I::B + s * G + b);
-        const double Ssa = bv(I::S + s * G + a), Rsb = bv(I::R + s * G + b);
-#pragma unroll
-        for (int t = 0; t < G; ++t) {
-            const double Bta = bv(I::B + t * G + a), Btb = bv(I::B + t * G + b);
-            const double Sta = bv(I::S + t * G + a);
-            double n3 = -p * (Bsa * Btb - Bsb * Bta);
-            double n4 = Ssa * Btb - Sta * Bsb - muH * bv(I::M + symi(s, t, G)) - rc.mu * Bta * Rsb;
-            C[1 + s][1 + t] = Jw * (n3 + rc.th0 * n4);
-        }
-    }
+            C[1 + s][1 + t] = Pa[s] * Bb[t] - Pa[t] * Bb[s] - Hab * bv(I::MJ + symi(s, t, G)) - Ba[t] * Rb[s];
 }
 
 // vectors of the small blocks: psi_a x delta p (test gradient slots), gamma x delta v_b and
@@ -303,11 +306,16 @@ template <int G, class BV>
 TFSI_HD void fluid_c_gamma_dd(BV bv, int b, double (&c)[G]) {
     typedef FluidBase<G> I;
     const double Jw = bv(I::JW);
-    double trH = 0;
+    double trH = 0, Hb[G];
 #pragma unroll
-    for (int e = 0; e < G; ++e) trH += bv(I::H + e * G + e);
+    for (int e = 0; e < G; ++e) { trH += bv(I::H + e * G + e); Hb[e] = bv(I::H + e * G + b); }
 #pragma unroll
-    for (int t = 0; t < G; ++t) c[t] = Jw * (bv(I::B + t * G + b) * trH - bv(I::R + t * G + b));
+    for (int t = 0; t < G; ++t) {
+        double r = 0;                                     // (B H)_tb
+#pragma unroll
+        for (int e = 0; e < G; ++e) r += bv(I::B + t * G + e) * Hb[e];
+        c[t] = Jw * (bv(I::B + t * G + b) * trH - r);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -424,39 +432,103 @@ TFSI_HD void solid_C_psi_dd(BV bv, const RegionConst& rc, int a, int b, double (
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sum-factorised block updates.  MODE bits: 1 = C[0][0] present, 2 = C[0][t] present,
-// 4 = C[s][t] present (C[s][0] is structurally zero in every form of this path).
-template <int G, int J0, int NJ, int MODE, class Tab>
+// Sum-factorised block updates, exploiting the SPARSITY of the P2 reference gradients:
+//   vertex function v :  ghat = (4 lam_v - 1) dlam_v            dlam_0 = -(1,..,1), dlam_k = e_k
+//   edge function (a,b): ghat = 4 lam_a dlam_b + 4 lam_b dlam_a
+// so a vertex column/row costs 2 FMAs per slot pair instead of G+1, an edge 3.  The columns of
+// one block are split into two halves of equal cost (a thread owns N2 x N2/2 accumulators).
+// MODE bits: 1 = C[0][0] present, 2 = C[0][t] present, 4 = C[s][t] present (C[s][0] is
+// structurally zero in every form of this path).
+template <int G> struct P2Edges;
+template <> struct P2Edges<2> {
+    TFSI_HD static constexpr int a(int e) { return e == 0 ? 1 : 0; }
+    TFSI_HD static constexpr int b(int e) { return e == 2 ? 1 : 2; }
+};
+template <> struct P2Edges<3> {
+    TFSI_HD static constexpr int a(int e) { return e == 0 ? 2 : (e <= 2 ? 1 : 0); }
+    TFSI_HD static constexpr int b(int e) { return e == 0 ? 3 : (e == 1 ? 3 : (e == 2 ? 2 : (e == 3 ? 3 : (e == 4 ? 2 : 1)))); }
+};
+// column lists of the two halves (2 vertices + 3 edges each in 3-D)
+template <int G, int HALF> struct HalfCols;
+template <int HALF> struct HalfCols<3, HALF> {
+    static constexpr int NJ = 5;
+    TFSI_HD static constexpr int col(int jj) { return HALF == 0 ? (jj < 2 ? jj : jj + 2) : (jj < 2 ? jj + 2 : jj + 5); }
+};
+template <int HALF> struct HalfCols<2, HALF> {
+    static constexpr int NJ = 3;
+    TFSI_HD static constexpr int col(int jj) { return HALF == 0 ? (jj == 0 ? 0 : jj + 2) : (jj < 2 ? jj + 1 : 5); }
+};
+
+template <int G, int HALF, int MODE, class Tab>
 TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
-                        double (&Z)[Dim<G>::N2][NJ])
+                        double (&Z)[Dim<G>::N2][HalfCols<G, HALF>::NJ])
 {
     constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = HalfCols<G, HALF>::NJ;
+    typedef P2Edges<G> E;
+    // row sums over the gradient slots (used by every function touching vertex 0)
+    double Cs[G + 1];
+#pragma unroll
+    for (int s = 0; s <= G; ++s) {
+        double x = 0.0;
+        if ((s == 0 && (MODE & 2)) || (s > 0 && (MODE & 4))) {
+#pragma unroll
+            for (int t = 1; t <= G; ++t) x += C[s][t];
+        }
+        Cs[s] = x;
+    }
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
-        const int j = J0 + jj;
+        const int j = HalfCols<G, HALF>::col(jj);
         double W[G + 1];
-        W[0] = 0.0;
-        if (MODE & 1) W[0] = C[0][0] * tab.phi2[q][j];
-        if (MODE & 2) {
+        // ---- stage 1: W_s = sum_t C'_st U_jt
+        if (j == 0) {
+            const double D = tab.d4[q][0];
+            W[0] = 0.0;
+            if (MODE & 1) W[0] = C[0][0] * tab.phi2[q][0];
+            if (MODE & 2) W[0] -= D * Cs[0];
 #pragma unroll
-            for (int t = 0; t < G; ++t) W[0] += C[0][1 + t] * tab.dphi2[q][j][t];
-        }
+            for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? -D * Cs[s] : 0.0;
+        } else if (j <= G) {
+            const double D = tab.d4[q][j];
+            W[0] = 0.0;
+            if (MODE & 1) W[0] = C[0][0] * tab.phi2[q][j];
+            if (MODE & 2) W[0] += D * C[0][j];
 #pragma unroll
-        for (int s = 0; s < G; ++s) {
-            double x = 0.0;
-            if (MODE & 4) {
+            for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? D * C[s][j] : 0.0;
+        } else {
+            const int ea = E::a(j - G - 1), eb = E::b(j - G - 1);
+            const double La = tab.l4[q][ea], Lb = tab.l4[q][eb];
+            W[0] = 0.0;
+            if (MODE & 1) W[0] = C[0][0] * tab.phi2[q][j];
+            if (ea == 0) {
+                if (MODE & 2) W[0] += La * C[0][eb] - Lb * Cs[0];
 #pragma unroll
-                for (int t = 0; t < G; ++t) x += C[1 + s][1 + t] * tab.dphi2[q][j][t];
+                for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? La * C[s][eb] - Lb * Cs[s] : 0.0;
+            } else {
+                if (MODE & 2) W[0] += La * C[0][eb] + Lb * C[0][ea];
+#pragma unroll
+                for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? La * C[s][eb] + Lb * C[s][ea] : 0.0;
             }
-            W[1 + s] = x;
+        }
+        // ---- stage 2: Z_ij += sum_s T_is W_s
+        double Wsum = 0.0;
+        if (MODE & 4) {
+#pragma unroll
+            for (int s = 1; s <= G; ++s) Wsum += W[s];
         }
 #pragma unroll
         for (int i = 0; i < N2; ++i) {
             double z = Z[i][jj];
             if (MODE & 3) z += tab.phi2[q][i] * W[0];
             if (MODE & 4) {
-#pragma unroll
-                for (int s = 0; s < G; ++s) z += tab.dphi2[q][i][s] * W[1 + s];
+                if (i == 0) z -= tab.d4[q][0] * Wsum;
+                else if (i <= G) z += tab.d4[q][i] * W[i];
+                else {
+                    const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
+                    if (ea == 0) z += tab.l4[q][0] * W[eb] - tab.l4[q][eb] * Wsum;
+                    else z += tab.l4[q][ea] * W[eb] + tab.l4[q][eb] * W[ea];
+                }
             }
             Z[i][jj] = z;
         }
@@ -729,6 +801,8 @@ inline int tabulate(int g, int nq, const double* pts, const double* wts, QuadTab
         tab.w[q] = wts[q];
         for (int i = 0; i <= g; ++i) {
             tab.phi1[q][i] = lam[i];
+            tab.d4[q][i] = 4.0 * lam[i] - 1.0;
+            tab.l4[q][i] = 4.0 * lam[i];
             tab.phi2[q][i] = lam[i] * (2.0 * lam[i] - 1.0);
             for (int c = 0; c < g; ++c) tab.dphi2[q][i][c] = (4.0 * lam[i] - 1.0) * dl[i][c];
         }
