@@ -144,6 +144,22 @@ int tfsi_halo_pack(tfsi_handle* h, const double* x, const int32_t* send_idx, int
 int tfsi_halo_unpack(tfsi_handle* h, double* x, const int32_t* recv_idx, int64_t n,
                      const double* recv_buf, void* stream);
 
+/* Set-up utility (DOLFIN's SparsityPatternBuilder stand-in, used when the pattern is not given by
+ * the host): expands the CSR adjacency of the P2 mesh nodes into the dof-level column array of a
+ * node-interleaved numbering (dofs of node I = node_base[I] .. + node_ncomp[I]).  All pointers
+ * DEVICE.  node_cum = exclusive prefix sum of node_ncomp[node_col] (length nnz_node + 1);
+ * rowptr [N+1] must already hold the dof-level row starts; colidx [nnz] is written. */
+int tfsi_expand_node_pattern(int64_t num_nodes, int64_t nnz_node, const int64_t* node_rowptr,
+                             const int32_t* node_col, const int64_t* node_cum, const int64_t* node_base,
+                             const int32_t* node_ncomp, const int64_t* rowptr, int32_t* colidx, void* stream);
+
+/* Per-kernel device timing for bench.py's roofline: with profiling on, every launch of the
+ * Jacobian (kind 0 fluid cells, 1 solid cells) and residual (kind 2) kernels is bracketed by CUDA
+ * events on its own stream; tfsi_kernel_time returns their summed duration and the launch count
+ * since profiling was switched on. */
+int tfsi_set_profiling(tfsi_handle* h, int32_t on);
+int tfsi_kernel_time(tfsi_handle* h, int32_t kind, double* total_ms, int64_t* count);
+
 /* kernels launched since creation (for bench.py's gpu_launches) */
 int64_t tfsi_launch_count(const tfsi_handle* h);
 

@@ -99,3 +99,43 @@ def test_ident_zeros_and_bcs(tube_params):
     assert abs(nrm - np.linalg.norm(bref)) <= 1e-13 * np.linalg.norm(bref)
     asm.apply_bc_vec(xd, gd)
     assert np.array_equal(xd.cpu().numpy()[bc], g)
+
+
+def test_device_pattern_builder_matches_host():
+    import torch
+    from turtlefsi_b200.mesh import tube_mesh
+    from turtlefsi_b200.space import MixedSpace, pattern_device
+    from tests.helpers import square_mesh
+    for mesh, bih in ((tube_mesh(5), False), (tube_mesh(3), True), (square_mesh(7), False)):
+        sp = MixedSpace(mesh, biharmonic=bih)
+        rp, ci = sp.pattern()
+        rpd, cid = pattern_device(sp, torch.device("cuda"))
+        assert np.array_equal(rpd.cpu().numpy(), rp)
+        assert np.array_equal(cid.cpu().numpy(), ci)
+
+
+def test_host_entry_matches_device_calls(tube_params):
+    """tfsi_newton_assemble_host (host buffers, the e2e call) == the sequence of device calls."""
+    import torch
+    from turtlefsi_b200.assembler import FSIAssembler
+    common, regions = tube_params
+    mesh, space, x, x1 = _setup(3, False, 3)
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"])
+    rng = np.random.default_rng(3)
+    bc = rng.choice(space.num_dofs, size=100, replace=False).astype(np.int32)
+    g = rng.uniform(-1, 1, size=100)
+    asm.set_bc_dofs(bc)
+    xd, x1d, gd = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda(), torch.as_tensor(g).cuda()
+    A_pre = asm.assemble_A_pre(xd, x1d)
+    A = asm.assemble_jacobian(xd, x1d, A_pre)
+    asm.ident_zeros(A)
+    asm.apply_bc_matrix(A)
+    b = asm.assemble_residual(xd, x1d)
+    asm.apply_bc_rhs(b, xd, gd)
+    A2 = asm.new_matrix()
+    bh = np.zeros(space.num_dofs)
+    ss = asm.newton_assemble_host(x, x1, g, A_pre, A2, bh, recompute=True)
+    scale = np.abs(A.cpu().numpy()).max()
+    assert np.abs(A2.cpu().numpy() - A.cpu().numpy()).max() < 1e-12 * scale     # atomic order only
+    assert np.abs(bh - b.cpu().numpy()).max() < 1e-12 * np.abs(bh).max()
+    assert abs(ss - float((bh ** 2).sum())) < 1e-10 * ss

@@ -56,7 +56,8 @@ class FSIAssembler:
         self.qJ = default_rule(g, quad_degree_jacobian)
         self.qR = default_rule(g, quad_degree_residual)
         if pattern is None:
-            pattern = space.pattern()
+            from .space import pattern_device
+            pattern = pattern_device(space, self.device) if space.numbering == "interleaved" else space.pattern()
         rowptr, colidx = pattern
         dev = self.device
 
@@ -128,6 +129,15 @@ class FSIAssembler:
 
     def new_matrix(self):
         return torch.zeros(self.nnz, dtype=torch.float64, device=self.device)
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.tfsi_set_profiling(self.h, int(bool(on))))
+
+    def kernel_time(self, kind):
+        """(total ms, launches) of kernel kind 0 = Jacobian/fluid, 1 = Jacobian/solid, 2 = residual."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self.lib.tfsi_kernel_time(self.h, int(kind), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self):
         return int(self.lib.tfsi_launch_count(self.h))

@@ -43,6 +43,8 @@ struct tfsi_handle {
     int fluid_on, solid_on, ext, ext_sub;
     int64_t launches;
     int sm_count;
+    int profiling;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
 };
@@ -93,6 +95,14 @@ CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* 
     return a;
 }
 
+struct KernelTimer {
+    tfsi_handle* h; int kind; cudaStream_t st; cudaEvent_t e0, e1; bool on;
+    KernelTimer(tfsi_handle* h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_), on(h_->profiling != 0) {
+        if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    }
+    ~KernelTimer() { if (on) { cudaEventRecord(e1, st); h->ev[kind].push_back({e0, e1}); } }
+};
+
 int grid_for(int64_t n, int block, int sm) {
     int64_t g = (n + block - 1) / block;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm * 16));
@@ -106,6 +116,7 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A
         const int grid = (int)((r.ncells + 31) / 32);
         if (r.rc.kind == TFSI_KIND_FLUID) {
             if (!r.rc.fluid_on) continue;
+            KernelTimer kt(h, 0, st);
             size_t smem = FluidJac<G>::SM::bytes(a.nq);
             if (smem > 227 * 1024)
                 return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
@@ -119,6 +130,7 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A
             }
         } else {
             if (!r.rc.solid_on) continue;
+            KernelTimer kt(h, 1, st);
             size_t smem = SolidJac<G>::SM::bytes(a.nq);
             if (G == 3 && a.nq == 14) {
                 CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -184,6 +196,7 @@ int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double*
         if (rc.kind == TFSI_KIND_FLUID && !rc.fluid_on && rc.ext == 0) continue;
         if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
+        KernelTimer kt(h, 2, st);
         residual_kernel<G, BIH><<<(unsigned)((r.ncells + 31) / 32), RES_THREADS, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
@@ -233,7 +246,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->coords = nullptr; h->cell_vertices = h->cell_dofs = h->colidx = h->bc_dofs = nullptr;
     h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
     h->hx = h->hx1 = h->hb = h->hg = nullptr;
-    h->nbc = 0; h->launches = 0;
+    h->nbc = 0; h->launches = 0; h->profiling = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     int dev = 0;
@@ -441,6 +454,42 @@ int tfsi_halo_unpack(tfsi_handle* h, double* x, const int32_t* idx, int64_t n, c
     scatter_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, idx, n, buf);
     h->launches++;
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+int tfsi_set_profiling(tfsi_handle* h, int32_t on) {
+    if (!h) return TFSI_ERR_ARG;
+    h->profiling = on;
+    for (auto& v : h->ev) { for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } v.clear(); }
+    return 0;
+}
+
+int tfsi_kernel_time(tfsi_handle* h, int32_t kind, double* total_ms, int64_t* count) {
+    if (!h || kind < 0 || kind > 2) return fail(h, TFSI_ERR_ARG, "bad argument");
+    double tot = 0;
+    for (auto& p : h->ev[kind]) {
+        CK(h, cudaEventSynchronize(p.second));
+        float ms = 0;
+        CK(h, cudaEventElapsedTime(&ms, p.first, p.second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = (int64_t)h->ev[kind].size();
+    return 0;
+}
+
+int tfsi_expand_node_pattern(int64_t num_nodes, int64_t nnz_node, const int64_t* node_rowptr, const int32_t* node_col,
+                             const int64_t* node_cum, const int64_t* node_base, const int32_t* node_ncomp,
+                             const int64_t* rowptr, int32_t* colidx, void* stream) {
+    if (!node_rowptr || !node_col || !node_cum || !node_base || !node_ncomp || !rowptr || !colidx)
+        return fail(nullptr, TFSI_ERR_ARG, "null argument");
+    int dev = 0, sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, TFSI_ERR_CUDA, "no CUDA device");
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    expand_node_pattern_kernel<<<grid_for(nnz_node, 256, sm), 256, 0, (cudaStream_t)stream>>>(
+        num_nodes, node_rowptr, node_col, node_cum, node_base, node_ncomp, rowptr, colidx, nnz_node);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, TFSI_ERR_CUDA, "expand_node_pattern: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -26,7 +26,7 @@ __constant__ QuadTab<MAXQ_R> c_tabR;
 
 constexpr int CELLS_PER_CTA = 32;
 #ifndef TFSI_JAC_WARPS
-#define TFSI_JAC_WARPS 8
+#define TFSI_JAC_WARPS 12
 #endif
 // registers are allocated per 4 warps: 8 warps -> 255 regs/thread, 12 warps -> 168 (9..11 gain nothing)
 constexpr int JAC_WARPS = TFSI_JAC_WARPS;
@@ -654,6 +654,28 @@ __global__ void scatter_kernel(double* x, const int32_t* idx, int64_t n, const d
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[idx[i]] = buf[i];
+}
+
+// dof-level CSR columns from the P2-node adjacency (node-interleaved numbering): one thread per
+// node-adjacency entry (I, J); writes the ncomp[I] x ncomp[J] block of column indices.
+__global__ void expand_node_pattern_kernel(int64_t num_nodes, const int64_t* nrowptr, const int32_t* ncol,
+                                           const int64_t* ncum, const int64_t* nbase, const int32_t* ncomp,
+                                           const int64_t* rowptr, int32_t* colidx, int64_t nnz_node)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz_node; k += (int64_t)gridDim.x * blockDim.x) {
+        // owning node row: binary search in nrowptr
+        int64_t lo = 0, hi = num_nodes;
+        while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (nrowptr[mid] <= k) lo = mid; else hi = mid - 1; }
+        const int64_t I = lo;
+        const int32_t J = ncol[k];
+        const int64_t off = ncum[k] - ncum[nrowptr[I]];
+        const int64_t bI = nbase[I], bJ = nbase[J];
+        const int cI = ncomp[I], cJ = ncomp[J];
+        for (int r = 0; r < cI; ++r) {
+            int32_t* dst = colidx + rowptr[bI + r] + off;
+            for (int c = 0; c < cJ; ++c) dst[c] = (int32_t)(bJ + c);
+        }
+    }
 }
 
 // FP64 peak probe: 8 independent DFMA chains per thread, register resident

@@ -171,6 +171,51 @@ class MixedSpace:
         return rowptr, colidx
 
 
+def pattern_device(space, device):
+    """(rowptr, colidx) as torch tensors on `device`, built there: node adjacency by a device
+    sort/unique (torch = plumbing), dof-level expansion by the library's CUDA kernel. Needs the
+    "interleaved" numbering. Same result as MixedSpace.pattern() (tests/test_gpu_parity.py)."""
+    import ctypes as C
+
+    import torch
+
+    from . import lib as _lib
+    assert space.numbering == "interleaved"
+    L = _lib.load()
+    nn = space.num_nodes
+    cn = torch.as_tensor(space.cell_nodes.astype(np.int64)).to(device)
+    keys = []
+    step = max(1, 50_000_000 // (space.n2 * space.n2))
+    for s in range(0, space.num_cells, step):
+        blk = cn[s:s + step]
+        keys.append(torch.unique((blk[:, :, None] * nn + blk[:, None, :]).reshape(-1)))
+    ukey = torch.unique(torch.cat(keys))
+    del keys, cn
+    rows = ukey // nn
+    ncol = (ukey % nn).to(torch.int32)
+    del ukey
+    nrowptr = torch.zeros(nn + 1, dtype=torch.int64, device=device)
+    nrowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=nn), 0)
+    del rows
+    ncomp = torch.as_tensor(space.node_ncomp.astype(np.int32)).to(device)
+    nbase = torch.as_tensor(space.node_base.astype(np.int64)).to(device)
+    ncum = torch.zeros(ncol.numel() + 1, dtype=torch.int64, device=device)
+    ncum[1:] = torch.cumsum(ncomp[ncol.long()].long(), 0)
+    rowlen_node = ncum[nrowptr[1:]] - ncum[nrowptr[:-1]]
+    rowptr = torch.zeros(space.num_dofs + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.repeat_interleave(rowlen_node, ncomp.long()), 0)
+    nnz = int(rowptr[-1].item())
+    colidx = torch.empty(nnz, dtype=torch.int32, device=device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(device):
+        rc = L.tfsi_expand_node_pattern(nn, ncol.numel(), p(nrowptr), p(ncol), p(ncum), p(nbase), p(ncomp),
+                                        p(rowptr), p(colidx), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError("tfsi_expand_node_pattern: %s" % L.tfsi_last_error(None).decode())
+        torch.cuda.synchronize(device)
+    return rowptr, colidx
+
+
 def pattern_from_cell_dofs(cell_dofs, num_dofs):
     """generic (any numbering) pattern: union of dense cell blocks, columns ascending."""
     cd = cell_dofs.astype(np.int64)
