@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +26,17 @@ struct Region {
     int32_t* cell_list;   // device
 };
 
+// One kernel launch of the Jacobian assembly: a slice of one region's cell list. `init_end` is
+// the end (in CSR entries) of the rows that may be touched by this and all earlier segments; A is
+// initialised (A := A_pre or 0) up to there on the copy stream before the segment starts, so the
+// HBM-bound initialisation overlaps with the FP64-bound kernels of earlier segments.
+struct Segment {
+    int region;
+    int64_t first, count;
+    int64_t init_end;
+};
+constexpr int JAC_CHUNKS = 8;
+
 }  // namespace
 
 struct tfsi_handle {
@@ -38,6 +50,10 @@ struct tfsi_handle {
     double *hx, *hx1, *hb, *hg;   // device staging for the _host entry
     int64_t nbc;
     std::vector<Region> regions;
+    std::vector<Segment> segments;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_begin, ev_seg[2 * JAC_CHUNKS * 8];
+    int n_ev;
     QuadTab<MAXQ_J> tabJ;
     QuadTab<MAXQ_R> tabR;
     int fluid_on, solid_on, ext, ext_sub;
@@ -109,40 +125,70 @@ int grid_for(int64_t n, int block, int sm) {
 }
 
 template <int G>
-int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, double* A, cudaStream_t st) {
-    for (const Region& r : h->regions) {
-        if (r.ncells == 0) continue;
-        CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
-        const int grid = (int)((r.ncells + 31) / 32);
-        if (r.rc.kind == TFSI_KIND_FLUID) {
-            if (!r.rc.fluid_on) continue;
-            KernelTimer kt(h, 0, st);
-            size_t smem = FluidJac<G>::SM::bytes(a.nq);
-            if (smem > 227 * 1024)
-                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
-            // compile-time quadrature size for the rule of the headline config (Keast 14-point)
-            if (G == 3 && a.nq == 14) {
-                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_fluid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
-            } else {
-                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_fluid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
-            }
+int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, const double* x1, double* A, cudaStream_t st) {
+    const Region& r = h->regions[sg.region];
+    CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
+    a.cell_list = r.cell_list + sg.first;
+    a.ncell_region = sg.count;
+    const int grid = (int)((sg.count + 31) / 32);
+    if (r.rc.kind == TFSI_KIND_FLUID) {
+        KernelTimer kt(h, 0, st);
+        size_t smem = FluidJac<G>::SM::bytes(a.nq);
+        if (smem > 227 * 1024)
+            return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
+        // compile-time quadrature size for the rule of the headline config (Keast 14-point)
+        if (G == 3 && a.nq == 14) {
+            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_fluid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
         } else {
-            if (!r.rc.solid_on) continue;
-            KernelTimer kt(h, 1, st);
-            size_t smem = SolidJac<G>::SM::bytes(a.nq);
-            if (G == 3 && a.nq == 14) {
-                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_solid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
-            } else {
-                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_solid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
-            }
+            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_fluid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
         }
-        h->launches++;
-        CK(h, cudaGetLastError());
+    } else {
+        KernelTimer kt(h, 1, st);
+        size_t smem = SolidJac<G>::SM::bytes(a.nq);
+        if (G == 3 && a.nq == 14) {
+            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_solid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
+        } else {
+            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_solid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
+        }
     }
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// A := (A_pre | 0) + J_nl, initialisation pipelined with the segment kernels (see Segment)
+int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st) {
+    CK(h, cudaEventRecord(h->ev_begin, st));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_begin, 0));
+    auto init = [&](int64_t lo, int64_t hi) -> int {
+        if (hi <= lo) return 0;
+        if (Apre) CK(h, cudaMemcpyAsync(A + lo, Apre + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, h->copy_stream));
+        else CK(h, cudaMemsetAsync(A + lo, 0, (size_t)(hi - lo) * sizeof(double), h->copy_stream));
+        h->launches++;
+        return 0;
+    };
+    int64_t done = 0;
+    int ev = 0;
+    for (const Segment& sg : h->segments) {
+        if (sg.init_end > done) {
+            if (int rc = init(done, sg.init_end)) return rc;
+            done = sg.init_end;
+            CK(h, cudaEventRecord(h->ev_seg[ev], h->copy_stream));
+            CK(h, cudaStreamWaitEvent(st, h->ev_seg[ev], 0));
+            ev++;
+        }
+        const Region& r = h->regions[sg.region];
+        if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
+        int rc = h->gdim == 3 ? launch_jacobian_segment<3>(h, sg, x, x1, A, st) : launch_jacobian_segment<2>(h, sg, x, x1, A, st);
+        if (rc) return rc;
+    }
+    if (int rc = init(done, h->nnz)) return rc;
+    CK(h, cudaEventRecord(h->ev_seg[ev], h->copy_stream));
+    CK(h, cudaStreamWaitEvent(st, h->ev_seg[ev], 0));
     return 0;
 }
 
@@ -224,6 +270,9 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
     for (Region& r : h->regions) cudaFree(r.cell_list);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+    for (int i = 0; i < h->n_ev; ++i) cudaEventDestroy(h->ev_seg[i]);
     if (g_tab_owner == h->id) g_tab_owner = 0;
     delete h;
 }
@@ -247,6 +296,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
     h->hx = h->hx1 = h->hb = h->hg = nullptr;
     h->nbc = 0; h->launches = 0; h->profiling = 0;
+    h->copy_stream = nullptr; h->ev_begin = nullptr; h->n_ev = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     int dev = 0;
@@ -298,6 +348,44 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             h->regions.push_back(r);
         }
     }
+    // launch segments + initialisation frontier (host pass over the dof map)
+    {
+        std::vector<int32_t> cd((size_t)h->nc * h->ndof);
+        std::vector<int64_t> rp((size_t)h->N + 1);
+        cudaError_t e = cudaMemcpy(cd.data(), h->cell_dofs, cd.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(rp.data(), h->rowptr, rp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "segment planning: %s", cudaGetErrorString(e)); }
+        std::vector<std::vector<int32_t>> lists(h->regions.size());
+        {
+            std::vector<int32_t> marker((size_t)h->nc);
+            cudaMemcpy(marker.data(), p->cell_marker, (size_t)h->nc * sizeof(int32_t), cudaMemcpyDefault);
+            for (int64_t c = 0; c < h->nc; ++c)
+                for (size_t r = 0; r < h->regions.size(); ++r)
+                    if (marker[(size_t)c] == h->regions[r].marker) { lists[r].push_back((int32_t)c); break; }
+        }
+        // measured on B200 (DESIGN.md "what did not work"): overlapping the copy with the cell kernels
+        // slows the kernels by the same amount (their REDs share L2/HBM with the copy), so one
+        // segment per region is used; the pipelined path is kept for finer experiments.
+        const int nch = (getenv("TFSI_JAC_CHUNKS") ? atoi(getenv("TFSI_JAC_CHUNKS")) : 1);
+        int64_t frontier = -1;
+        for (int c = 0; c < nch; ++c)
+            for (size_t r = 0; r < h->regions.size(); ++r) {
+                const int64_t n = (int64_t)lists[r].size();
+                int64_t lo = (n * c / nch) / 32 * 32, hi = (c == nch - 1) ? n : (n * (c + 1) / nch) / 32 * 32;
+                if (hi <= lo) continue;
+                for (int64_t k = lo; k < hi; ++k) {
+                    const int32_t* d = cd.data() + (size_t)lists[r][(size_t)k] * h->ndof;
+                    for (int j = 0; j < h->ndof; ++j) if (d[j] > frontier) frontier = d[j];
+                }
+                Segment sg; sg.region = (int)r; sg.first = lo; sg.count = hi - lo; sg.init_end = rp[(size_t)frontier + 1];
+                h->segments.push_back(sg);
+            }
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming);
+        h->n_ev = (int)h->segments.size() + 1;
+        if (h->n_ev > 2 * JAC_CHUNKS * 8) { h->n_ev = 0; tfsi_destroy(h); return fail(nullptr, TFSI_ERR_UNSUPPORTED, "too many regions"); }
+        for (int i = 0; i < h->n_ev; ++i) cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming);
+    }
     // scatter maps
     {
         int* derr = reinterpret_cast<int*>(h->scratch + 1);
@@ -345,9 +433,7 @@ int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, co
     if (!h || !x || !x1 || !A) return fail(h, TFSI_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
-    if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    else CK(h, cudaMemsetAsync(A, 0, (size_t)h->nnz * sizeof(double), st));
-    return h->gdim == 3 ? launch_jacobian<3>(h, x, x1, A, st) : launch_jacobian<2>(h, x, x1, A, st);
+    return launch_jacobian(h, x, x1, Apre, A, st);
 }
 
 int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b, void* stream) {
