@@ -1,0 +1,96 @@
+"""ORACLE (test infrastructure only): numpy assembler with the interface that
+turtlefsi_b200/modules/newtonsolver.py drives — the CPU restatement of the whole Newton hot path
+(forms: oracle/forms.py; assembly + BC + ident_zeros: oracle/assembly.py). Used by the tests to
+run the reference's Newton loop on the CPU and compare the CUDA path against it."""
+import numpy as np
+
+from . import assembly as oa
+
+
+class OracleAssembler:
+    def __init__(self, mesh, space, regions, common, quad_degree_jacobian, quad_degree_residual, pattern=None,
+                 use_c_port=False):
+        """use_c_port: assemble with the plain-C restatement (oracle/c, laplace/constant only; it is
+        checked against the numpy complex-step forms in tests/test_oracle_forms.py) — 100x faster."""
+        self.use_c = use_c_port
+        self.mesh, self.space, self.regions, self.common = mesh, space, regions, dict(common)
+        self.common.setdefault("hmin", mesh.hmin())
+        self.degJ, self.degR = quad_degree_jacobian, quad_degree_residual
+        self.pattern = pattern if pattern is not None else space.pattern()
+        self.rowptr, self.colidx = self.pattern
+        self.num_dofs, self.nnz = space.num_dofs, len(self.colidx)
+        self.bc_dofs = np.zeros(0, dtype=np.int32)
+
+    def new_vector(self):
+        return np.zeros(self.num_dofs)
+
+    def new_matrix(self):
+        return np.zeros(self.nnz)
+
+    def to_device(self, a):
+        return np.array(a, dtype=np.float64)
+
+    def to_host(self, a):
+        return np.asarray(a)
+
+    def copy(self, dst, src):
+        dst[:] = src
+
+    def axpy(self, x, alpha, y):
+        x += alpha * y
+
+    def _c_matrix(self, x, x1, part):
+        from . import cport, fem_tables as ft
+        v = np.zeros(self.nnz)
+        cport.assemble_jacobian(self.mesh, self.space, self.regions, self.common["dt"], self.common["theta"],
+                                np.ascontiguousarray(x), np.ascontiguousarray(x1),
+                                ft.quadrature(self.mesh.gdim, self.degJ), self.pattern, v, part=part)
+        return v
+
+    def assemble_A_pre(self, x, x1, out=None):
+        v = self._c_matrix(x, x1, "lin") if self.use_c else oa.assemble_matrix(self.mesh, self.space, self.regions, self.common, x, x1, "lin", self.degJ, self.pattern)
+        if out is not None:
+            out[:] = v
+            return out
+        return v
+
+    def assemble_jacobian(self, x, x1, A_pre=None, out=None):
+        v = self._c_matrix(x, x1, "nl") if self.use_c else oa.assemble_matrix(self.mesh, self.space, self.regions, self.common, x, x1, "nl", self.degJ, self.pattern)
+        if A_pre is not None:
+            v = v + A_pre
+        if out is not None:
+            out[:] = v
+            return out
+        return v
+
+    def assemble_residual(self, x, x1, out=None):
+        if self.use_c:
+            from . import cport, fem_tables as ft
+            b = np.zeros(self.num_dofs)
+            cport.assemble_residual(self.mesh, self.space, self.regions, self.common["dt"], self.common["theta"],
+                                    np.ascontiguousarray(x), np.ascontiguousarray(x1),
+                                    ft.quadrature(self.mesh.gdim, self.degR), b)
+        else:
+            b = oa.assemble_vector(self.mesh, self.space, self.regions, self.common, x, x1, self.degR)
+        if out is not None:
+            out[:] = b
+            return out
+        return b
+
+    def ident_zeros(self, A):
+        oa.ident_zeros(A, self.pattern)
+
+    def set_bc_dofs(self, dofs):
+        self.bc_dofs = np.asarray(dofs, dtype=np.int64)
+
+    def apply_bc_matrix(self, A):
+        oa.apply_bc_matrix(A, self.pattern, self.bc_dofs)
+
+    def apply_bc_rhs(self, b, x, g):
+        oa.apply_bc_rhs(b, x, self.bc_dofs, g)
+
+    def apply_bc_vec(self, x, g):
+        oa.apply_bc_vec(x, self.bc_dofs, g)
+
+    def norm(self, v):
+        return float(np.linalg.norm(v))

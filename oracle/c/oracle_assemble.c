@@ -106,8 +106,9 @@ static void eval_vec(const tab_t* t, int q, const double* c, double G[10][3], do
 }
 
 /* element tensor of J_nonlinear for one cell: Ae[ndof*ndof] (row-major), zeroed by the caller */
+/* part: 0 = J_nonlinear, 1 = J_linear (A_pre: fluid.py:33, laplace.py:45 alfa = 1, solid.py:41-43), 2 = both */
 static void jac_cell(const tab_t* t, const oracle_region* rg, double dt, double theta, const double* coords,
-                     const int32_t* cv, const double* u, const double* u1, int ndof, double* Ae)
+                     const int32_t* cv, const double* u, const double* u1, int ndof, double* Ae, int part)
 {
     const int g = t->g, n1 = t->n1, n2 = t->n2;
     const int ov = g * n2, op = 2 * g * n2;
@@ -130,6 +131,28 @@ static void jac_cell(const tab_t* t, const oracle_region* rg, double dt, double 
         double F[3][3], Fi[3][3];
         for (int a = 0; a < g; ++a) for (int b = 0; b < g; ++b) F[a][b] = (a == b) + Gd[a][b];
         const double jw = t->w[q] * adet;
+        if (part >= 1) {
+            const double th1 = 1 - theta, delta = 1.0e7;
+            double F1[3][3], F1i[3][3];
+            for (int a = 0; a < g; ++a) for (int b = 0; b < g; ++b) F1[a][b] = (a == b) + Gd1[a][b];
+            const double J1 = rg->kind == 0 ? inv_g(g, F1, F1i) : 1.0;
+            for (int a = 0; a < g; ++a)
+                for (int i = 0; i < n2; ++i)
+                    for (int j = 0; j < n2; ++j) {
+                        const double mm = jw * t->phi2[q][i] * t->phi2[q][j];
+                        double kk = 0;
+                        for (int c = 0; c < g; ++c) kk += G[i][c] * G[j][c];
+                        if (rg->kind == 0) {
+                            Ae[(size_t)(ov + a * n2 + i) * ndof + ov + a * n2 + j] += rho / k * th1 * J1 * mm;
+                            Ae[(size_t)(a * n2 + i) * ndof + a * n2 + j] += jw * kk;
+                        } else {
+                            Ae[(size_t)(ov + a * n2 + i) * ndof + ov + a * n2 + j] += rho / k * mm;
+                            Ae[(size_t)(a * n2 + i) * ndof + a * n2 + j] += delta * rho / k * mm;
+                            Ae[(size_t)(a * n2 + i) * ndof + ov + a * n2 + j] -= delta * rho * th0 * mm;
+                        }
+                    }
+        }
+        if (part == 1) continue;
         if (rg->kind == 0) {
             const double J = inv_g(g, F, Fi), Jw = J * jw;
             double p = 0;
@@ -329,7 +352,7 @@ int tfsi_oracle_assemble_jacobian(int g, int nq, const double* pts, const double
                                   const double* coords, const int32_t* cells, const int32_t* cell_dofs,
                                   const int32_t* marker, int ndof, int nreg, const oracle_region* regs, double dt,
                                   double theta, const double* x, const double* x1, const int64_t* rowptr,
-                                  const int32_t* colidx, double* A_vals, int nthreads)
+                                  const int32_t* colidx, double* A_vals, int nthreads, int part)
 {
     tab_t tab;
     if (nq > MAXQ) return -1;
@@ -350,7 +373,7 @@ int tfsi_oracle_assemble_jacobian(int g, int nq, const double* pts, const double
             const int32_t* dofs = cell_dofs + c * ndof;
             for (int i = 0; i < nloc; ++i) { u[i] = x[dofs[i]]; u1[i] = x1[dofs[i]]; }
             memset(Ae, 0, sizeof(double) * ndof * ndof);
-            jac_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, ndof, Ae);
+            jac_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, ndof, Ae, part);
             for (int i = 0; i < ndof; ++i) {
                 const int64_t lo = rowptr[dofs[i]], hi = rowptr[dofs[i] + 1];
                 for (int j = 0; j < ndof; ++j) {

@@ -42,7 +42,8 @@ def max_threads():
     return int(load().tfsi_oracle_max_threads())
 
 
-def assemble_jacobian(mesh, space, regions, dt, theta, x, x1, rule, pattern, A_vals, c0=0, c1=None, nthreads=0):
+def assemble_jacobian(mesh, space, regions, dt, theta, x, x1, rule, pattern, A_vals, c0=0, c1=None, nthreads=0,
+                      part="nl"):
     lib = load()
     pts, wts = rule
     c1 = mesh.num_cells if c1 is None else c1
@@ -55,7 +56,8 @@ def assemble_jacobian(mesh, space, regions, dt, theta, x, x1, rule, pattern, A_v
     rc = lib.tfsi_oracle_assemble_jacobian(
         C.c_int(mesh.gdim), C.c_int(len(wts)), _p(pts), _p(wts), C.c_int64(c0), C.c_int64(c1),
         _p(mesh.coords), _p(cells), _p(cd), _p(mk), C.c_int(space.ndof_cell), C.c_int(len(regions)), regs,
-        C.c_double(dt), C.c_double(theta), _p(x), _p(x1), _p(rowptr), _p(colidx), _p(A_vals), C.c_int(nthreads))
+        C.c_double(dt), C.c_double(theta), _p(x), _p(x1), _p(rowptr), _p(colidx), _p(A_vals), C.c_int(nthreads),
+        C.c_int({"nl": 0, "lin": 1, "all": 2}[part]))
     if rc != 0:
         raise RuntimeError("oracle C assembly failed (%d)" % rc)
     return A_vals

@@ -82,15 +82,16 @@ class CellForms:
         g, n2 = sp.g, sp.n2
         out = np.zeros((R.shape[0], g, n2), dtype=R.dtype)
         if fval is not None:
-            out = out + np.einsum('cq,cqa,qi->cai', wdet, fval, self.phi2)
+            out = out + np.einsum('cqa,qi->cai', wdet[:, :, None] * fval, self.phi2)
         if fgrad is not None:
-            gphys = np.einsum('qik,ckb->cqib', self.dphi2, K)              # d phi_i / d x_b
-            out = out + np.einsum('cq,cqab,cqib->cai', wdet, fgrad, gphys)
+            # d phi_i / d x_b = K^T ghat_i ; contract the flux with K first (cheap), then with ghat
+            fref = np.einsum('cqab,ckb->cqak', wdet[:, :, None, None] * fgrad, K)
+            out = out + np.einsum('cqak,qik->cai', fref, self.dphi2)
         R[:, off:off + g * n2] += out.reshape(R.shape[0], g * n2)
 
     def _test_p(self, R, wdet, f):
         sp = self.sp
-        R[:, sp.off_p:sp.off_p + sp.n1] += np.einsum('cq,cq,qi->ci', wdet, f, self.phi1)
+        R[:, sp.off_p:sp.off_p + sp.n1] += np.einsum('cq,qi->ci', wdet * f, self.phi1)
 
     # ---- the forms ---------------------------------------------------------------------
     def residual(self, kind, X, u, u1, prm):

@@ -130,6 +130,19 @@ class FSIAssembler:
     def new_matrix(self):
         return torch.zeros(self.nnz, dtype=torch.float64, device=self.device)
 
+    # vector plumbing used by modules/newtonsolver.py (torch = device memory only)
+    def to_device(self, a):
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+
+    def to_host(self, t):
+        return t.detach().cpu().numpy()
+
+    def copy(self, dst, src):
+        dst.copy_(src)
+
+    def axpy(self, x, alpha, y):
+        x.add_(y, alpha=float(alpha))
+
     def set_profiling(self, on=True):
         self._check(self.lib.tfsi_set_profiling(self.h, int(bool(on))))
 

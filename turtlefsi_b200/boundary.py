@@ -1,0 +1,197 @@
+"""Host-side boundary logic of the drop-in: facet markers, Dirichlet dof sets, surface
+functionals and point evaluation (2-D and 3-D simplices, numpy).
+
+Replaces what the problem files obtain from DOLFIN [dep]:
+  AutoSubDomain(...).mark(boundaries, id), DomainBoundary()   turtleFSI/problems/TF_fsi.py:70-95
+  DirichletBC(DVP.sub(i)[.sub(j)], value, boundaries, id)      TF_fsi.py:143-185 (topological)
+  assemble((sigma(v,p,d,mu_f)*n)[k]*ds(id)), ... ("+")*dS(id)  TF_fsi.py:229-233
+  Function.__call__(point) / peval                              TF_fsi.py:208-219
+Marking rule of SubDomain.mark: a facet is marked when all its vertices AND its midpoint satisfy
+inside(x, on_boundary). "+" side of an interior facet = its lowest-numbered incident cell.
+"""
+import itertools
+
+import numpy as np
+
+from .element import tabulate
+
+
+class Facets:
+    """codimension-1 entities with their incident cells."""
+
+    def __init__(self, mesh):
+        g = mesh.gdim
+        self.mesh = mesh
+        cells = mesh.cells.astype(np.int64)
+        nc, nv = cells.shape[0], mesh.num_vertices
+        # local facet k is opposite to local vertex k (UFC)
+        loc = [tuple(v for v in range(g + 1) if v != k) for k in range(g + 1)]
+        fv = np.stack([cells[:, l] for l in loc], axis=1)            # [nc, g+1, g] ascending already
+        key = np.zeros((nc, g + 1), dtype=np.int64)
+        for c in range(g):
+            key = key * nv + fv[:, :, c]
+        ukey, inv = np.unique(key.ravel(), return_inverse=True)
+        self.num = len(ukey)
+        verts = np.zeros((self.num, g), dtype=np.int64)
+        rem = ukey.copy()
+        for c in range(g - 1, -1, -1):
+            verts[:, c] = rem % nv
+            rem //= nv
+        self.vertices = verts                                        # [nf, g]
+        self.cell_facets = inv.reshape(nc, g + 1)
+        # incident cells, ascending cell index
+        order = np.argsort(inv, kind="stable")
+        fsorted = inv[order]
+        cell_of = order // (g + 1)
+        localf = order % (g + 1)
+        start = np.searchsorted(fsorted, np.arange(self.num))
+        cnt = np.diff(np.append(start, len(fsorted)))
+        self.cell0 = cell_of[start]
+        self.local0 = localf[start]
+        self.cell1 = np.where(cnt > 1, cell_of[np.minimum(start + 1, len(order) - 1)], -1)
+        self.local1 = np.where(cnt > 1, localf[np.minimum(start + 1, len(order) - 1)], -1)
+        self.on_boundary = cnt == 1
+        X = mesh.coords
+        self.midpoints = X[verts].mean(axis=1)
+        self.markers = np.zeros(self.num, dtype=np.int64)
+
+    def mark(self, inside, value):
+        """inside(x [n, g], on_boundary [n]) -> bool [n]; DOLFIN SubDomain.mark semantics."""
+        X = self.mesh.coords
+        ok = inside(self.midpoints, self.on_boundary)
+        for c in range(self.vertices.shape[1]):
+            ok &= inside(X[self.vertices[:, c]], self.on_boundary)
+        self.markers[ok] = value
+
+
+def mark_cells(mesh, inside, value):
+    X = mesh.coords
+    ok = inside(X[mesh.cells].mean(axis=1))
+    for c in range(mesh.cells.shape[1]):
+        ok &= inside(X[mesh.cells[:, c]])
+    mesh.markers[ok] = value
+
+
+class DirichletBC:
+    """DirichletBC(DVP.sub(field)[.sub(comp)], value, boundaries, marker), topological method.
+    value: scalar, tuple (one entry per component) or callable(x [n, g]) -> [n, ncomp]."""
+
+    def __init__(self, space, mesh, facets, field, value, marker, comp=None):
+        self.field, self.comp, self.value = field, comp, value
+        g = mesh.gdim
+        fsel = np.nonzero(facets.markers == marker)[0]
+        verts = np.unique(facets.vertices[fsel])
+        if field == 2:
+            self.dofs = [np.asarray(space.vertex_dof_p())[verts]]
+            self.coords = mesh.coords[verts]
+            self.comps = [0]
+            return
+        nodes = [space.vertex_node[verts]]
+        if len(fsel):
+            # edge midpoints lying on the marked facets
+            fv = facets.vertices[fsel]
+            pairs = set()
+            for a, b in itertools.combinations(range(g), 2):
+                for lo, hi in zip(np.minimum(fv[:, a], fv[:, b]), np.maximum(fv[:, a], fv[:, b])):
+                    pairs.add((int(lo), int(hi)))
+            ek = {(int(a), int(b)): i for i, (a, b) in enumerate(space.edge_vertices)} if not hasattr(space, "_edge_lookup") else space._edge_lookup
+            space._edge_lookup = ek
+            eids = np.array(sorted(ek[p] for p in pairs), dtype=np.int64)
+            nodes.append(space.edge_node[eids])
+        nodes = np.concatenate(nodes)
+        self.comps = list(range(g)) if comp is None else [comp]
+        self.dofs = [space.node_dof(field, a)[nodes] for a in self.comps]
+        self.coords = space.node_coords(mesh)[nodes]
+
+    def values(self):
+        n = len(self.coords)
+        if callable(self.value):
+            val = np.asarray(self.value(self.coords)).reshape(n, -1)
+            return [val[:, a] for a in (self.comps if val.shape[1] > 1 else [0] * len(self.comps))]
+        v = np.atleast_1d(np.asarray(self.value, dtype=float))
+        if self.field == 2 or self.comp is not None:
+            return [np.full(n, v[0])]
+        return [np.full(n, v[a]) for a in self.comps]
+
+
+def flatten_bcs(bcs):
+    """(dofs int32 [n], values [n]) in list order, later BCs win on shared dofs (DOLFIN applies
+    the list sequentially: newtonsolver.py:82,91,98)."""
+    table = {}
+    for bc in bcs:
+        for d, v in zip(bc.dofs, bc.values()):
+            for i, x in zip(d, v):
+                table[int(i)] = float(x)
+    dofs = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
+    vals = np.fromiter(table.values(), dtype=np.float64, count=len(table))
+    order = np.argsort(dofs)
+    return dofs[order].astype(np.int32), vals[order]
+
+
+def _gauss_legendre_01(n):
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def surface_traction(mesh, space, facets, x, mu_f, facet_ids, npts=6):
+    """sum over the given facets of  int sigma(v, p, d, mu_f) * n  dS  (vector [g]), evaluated on
+    the "+" cell (cell0) with its outward normal; sigma = mu (grad v F^-1 + F^-T grad v^T) - p I
+    (turtleFSI/modules/common.py:63-81). 2-D only needs a 1-D rule; 3-D uses a triangle rule."""
+    g = mesh.gdim
+    if g != 2:
+        raise NotImplementedError("surface functionals are implemented for 2-D benchmarks")
+    s, w = _gauss_legendre_01(npts)
+    total = np.zeros(g)
+    ref_vertices = np.vstack([np.zeros(g), np.eye(g)])
+    for f in facet_ids:
+        c = facets.cell0[f]
+        k = facets.local0[f]
+        vloc = [v for v in range(g + 1) if v != k]
+        cv = mesh.cells[c]
+        X = mesh.coords[cv]
+        Jg = (X[1:] - X[0]).T
+        K = np.linalg.inv(Jg)
+        a, b = X[vloc[0]], X[vloc[1]]
+        length = np.linalg.norm(b - a)
+        t = (b - a) / length
+        nrm = np.array([t[1], -t[0]])
+        if np.dot(nrm, X[k] - a) > 0:
+            nrm = -nrm
+        ra, rb = ref_vertices[vloc[0]], ref_vertices[vloc[1]]
+        pts = ra[None, :] + s[:, None] * (rb - ra)[None, :]
+        phi2, dphi2, phi1 = tabulate(g, pts)
+        dofs = space.cell_dofs[c]
+        n2 = space.n2
+        u = x[dofs]
+        dco = u[:g * n2].reshape(g, n2)
+        vco = u[g * n2:2 * g * n2].reshape(g, n2)
+        pco = u[2 * g * n2:2 * g * n2 + g + 1]
+        gphys = np.einsum('qik,kb->qib', dphi2, K)
+        Gd = np.einsum('ai,qib->qab', dco, gphys)
+        Gv = np.einsum('ai,qib->qab', vco, gphys)
+        p = phi1 @ pco
+        F = np.eye(g) + Gd
+        Fi = np.linalg.inv(F)
+        H = Gv @ Fi
+        sig = mu_f * (H + np.swapaxes(H, 1, 2)) - p[:, None, None] * np.eye(g)
+        total += np.einsum('q,qab,b->a', w * length, sig, nrm)
+    return total
+
+
+def point_eval(mesh, space, x, point, field=0):
+    """value of P2 vector field `field` at a point (first containing cell, as DOLFIN's bounding-box
+    tree returns one of the colliding cells; the field is continuous)."""
+    g = mesh.gdim
+    X = mesh.coords[mesh.cells]
+    Jg = np.swapaxes(X[:, 1:] - X[:, :1], 1, 2)
+    xi = np.linalg.solve(Jg, (np.asarray(point)[None, :] - X[:, 0])[:, :, None])[:, :, 0]
+    lam = np.concatenate([1 - xi.sum(axis=1, keepdims=True), xi], axis=1)
+    inside = np.nonzero((lam > -1e-10).all(axis=1))[0]
+    if len(inside) == 0:
+        raise RuntimeError("point outside the mesh")
+    c = inside[0]
+    phi2, _, _ = tabulate(g, xi[c][None, :])
+    n2 = space.n2
+    off = {0: 0, 1: g * n2, 3: 2 * g * n2 + g + 1}[field]
+    co = x[space.cell_dofs[c]][off:off + g * n2].reshape(g, n2)
+    return co @ phi2[0]

@@ -1,0 +1,105 @@
+"""turtleFSI/modules/newtonsolver.py counterpart — same functions, same control flow, same
+returned keys; the four DOLFIN calls that carry the cost are replaced by C-ABI calls into the
+sm_100a kernels (through an assembler object: turtlefsi_b200.assembler.FSIAssembler on the GPU).
+
+  reference line (modules/newtonsolver.py)                 here
+  :26-27  A_pre = assemble(J_linear, keep_diagonal=True)   asm.assemble_A_pre(x, x1)
+  :28     A = Matrix(A_pre)                                asm.new_matrix() (same fixed pattern)
+  :75-79  assemble(J_nonlinear, tensor=A); A.axpy(A_pre)   asm.assemble_jacobian(x, x1, A_pre, A)
+  :81     A.ident_zeros()                                  asm.ident_zeros(A)
+  :82     [bc.apply(A) for bc in bcs]                      asm.apply_bc_matrix(A)
+  :88     assemble(-F, tensor=b)                           asm.assemble_residual(x, x1, b)
+  :91     [bc.apply(b, x) ...]                             asm.apply_bc_rhs(b, x, g)
+  :93     up_sol.solve(dvp_res.vector(), b)                up_sol.solve(b)   (not optimised here)
+  :95,98  x.axpy(lmbda, dx); [bc.apply(x) ...]             asm.axpy / asm.apply_bc_vec(x, g)
+  :105-106 b.norm('l2'), norm(dvp_res, 'l2')               asm.norm
+"""
+from math import isnan
+
+from ..boundary import flatten_bcs
+
+
+def solver_setup(assembler, dvp_, up_sol, bcs, **namespace):
+    """Pre-assemble the linear part of the Jacobian (frozen at the state present now, as in the
+    reference: SURVEY 8a "frozen-A_pre")."""
+    bc_dofs, bc_vals = flatten_bcs(bcs)
+    assembler.set_bc_dofs(bc_dofs)
+    A_pre = assembler.assemble_A_pre(dvp_["n"], dvp_["n-1"])
+    A = assembler.new_matrix()
+    assembler.copy(A, A_pre)                  # A = Matrix(A_pre)
+    b = None
+    F = "F_lin + F_nonlin"                    # descriptor; the forms live in the kernels
+    return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n)", A_pre=A_pre, A=A, b=b, up_sol=up_sol)
+
+
+def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_tstep, compiler_parameters,
+                 dvp_, up_sol, dvp_res, rtol, atol, max_it, counter, first_step_num, verbose, assembler,
+                 residual_history=None, **namespace):
+    """Newton scheme with the reference's Jacobian-reuse predicates (newtonsolver.py:44-113)."""
+    # Initial values
+    iter = 0
+    residual = 10**8
+    rel_res = 10**8
+
+    # Capture if residual increases from last iteration
+    last_rel_res = residual
+    last_residual = rel_res
+    x, x1 = dvp_["n"], dvp_["n-1"]
+    bc_dofs, bc_vals = flatten_bcs(bcs)         # dof set is fixed; values may be time dependent
+    g = assembler.to_device(bc_vals)
+    up_sol_dirty = False
+    while rel_res > rtol and residual > atol and iter < max_it:
+        # Check if recompute Jacobian from 'recompute_tstep' (time step)
+        recompute_for_timestep = iter == 0 and (counter % recompute_tstep == 0)
+
+        # Check if recompute Jacobian from 'recompute' (iteration)
+        recompute_frequency = iter > 0 and iter % recompute == 0
+
+        # Recompute Jacobian due to increased residual
+        recompute_residual = iter > 0 and last_residual < residual
+
+        # Recompute Jacobian on first step of simulation (important if restart is used)
+        recompute_initialize = iter == 0 and counter == first_step_num
+
+        if recompute_for_timestep or recompute_frequency or recompute_residual or recompute_initialize:
+            if verbose:
+                print("Compute Jacobian matrix")
+            assembler.assemble_jacobian(x, x1, A_pre, A)      # J_nonlinear + A_pre
+            assembler.ident_zeros(A)
+            assembler.apply_bc_matrix(A)
+            up_sol.set_operator(A)                            # new values -> re-factorise
+            up_sol_dirty = True
+
+        # Assemble right hand side vector
+        if b is None:
+            b = assembler.assemble_residual(x, x1)
+        else:
+            assembler.assemble_residual(x, x1, b)
+
+        # Apply boundary conditions before solve
+        assembler.apply_bc_rhs(b, x, g)
+        # Solve the linear system A * x = b
+        dx = up_sol.solve(b)
+        assembler.copy(dvp_res, dx)
+        # Update solution using the Newton increment, then re-apply the boundary conditions
+        assembler.axpy(x, lmbda, dvp_res)
+        assembler.apply_bc_vec(x, g)
+
+        # Reset residuals
+        last_residual = residual
+        last_rel_res = rel_res
+
+        # Check residual
+        residual = assembler.norm(b)
+        rel_res = assembler.norm(dvp_res)
+        if rel_res > 1E20 or residual > 1E20 or isnan(rel_res) or isnan(residual):
+            raise RuntimeError("Error: The simulation has diverged during the Newton solve with residual = %.3e and relative residual = %.3e" % (residual, rel_res))
+
+        if verbose:
+            print("Newton iteration %d: r (atol) = %.3e (tol = %.3e), r (rel) = %.3e (tol = %.3e) "
+                  % (iter, residual, atol, rel_res, rtol))
+        if residual_history is not None:
+            residual_history.append((counter, iter, residual, rel_res))
+        iter += 1
+
+    return dict(up_sol=up_sol, A=A, b=b)

@@ -1,0 +1,7 @@
+"""turtleFSI/modules/no_solid.py counterpart: selects the solid terms assembled by the CUDA kernels
+(solid.py:41-43, 62-68 St.Venant-Kirchhoff; zero forms of no_solid.py:14-15)."""
+
+
+def solid_setup(**namespace):
+    term = dict(solid="no_solid")
+    return dict(F_solid_linear=term, F_solid_nonlinear=term)

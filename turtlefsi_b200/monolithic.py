@@ -1,0 +1,93 @@
+"""turtleFSI/monolithic.py counterpart: the driver of a problem file, with the reference's order
+of operations (monolithic.py:20-230): parameters -> mesh -> mixed space -> domain properties ->
+physics modules (selected BY NAME with the same --fluid/--solid/--extrapolation/--solver values)
+-> initiate -> create_bcs -> solver_setup -> time loop (pre_solve, newtonsolver, state rotation,
+post_solve) -> finished. Every hook is called as f(**namespace) and its returned dict is merged
+back, as the reference does with vars().update(...)."""
+import copy
+import importlib
+
+from .problems import default_variables as _defaults
+from .space import MixedSpace
+
+
+def assign_domain_properties(dx_f_id, rho_f, mu_f, fluid_properties, dx_s_id, material_model, rho_s, mu_s,
+                             lambda_s, solid_properties, **namespace):
+    """turtleFSI/modules/domain.py:16-121: scalar-or-list inputs -> per-region property lists."""
+    as_list = lambda v: v if isinstance(v, list) else [v]
+    dx_f_id_list, dx_s_id_list = as_list(dx_f_id), as_list(dx_s_id)
+    if len(fluid_properties) == 0:
+        fluid_properties = [{"dx_f_id": i, "rho_f": as_list(rho_f)[k] if isinstance(rho_f, list) else rho_f,
+                             "mu_f": as_list(mu_f)[k] if isinstance(mu_f, list) else mu_f}
+                            for k, i in enumerate(dx_f_id_list)]
+    elif isinstance(fluid_properties, dict):
+        fluid_properties = [fluid_properties]
+    if len(solid_properties) == 0:
+        pick = lambda v, k: v[k] if isinstance(v, list) else v
+        solid_properties = [{"dx_s_id": i, "material_model": pick(material_model, k), "rho_s": pick(rho_s, k),
+                             "mu_s": pick(mu_s, k), "lambda_s": pick(lambda_s, k)} for k, i in enumerate(dx_s_id_list)]
+    elif isinstance(solid_properties, dict):
+        solid_properties = [solid_properties]
+    for sp in solid_properties:
+        if sp["material_model"] != "StVenantKirchoff":
+            raise RuntimeError("material model '%s' is not available on the B200 path" % sp["material_model"])
+    regions = [dict(marker=fp["dx_f_id"], kind="fluid", rho=fp["rho_f"], mu=fp["mu_f"]) for fp in fluid_properties]
+    regions += [dict(marker=sp["dx_s_id"], kind="solid", rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"])
+                for sp in solid_properties]
+    return dict(dx_f_id_list=dx_f_id_list, dx_s_id_list=dx_s_id_list, fluid_properties=fluid_properties,
+                solid_properties=solid_properties, regions=regions)
+
+
+def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
+    """problem: module name under turtlefsi_b200.problems (or a module object).
+    make_assembler(mesh, space, regions, ns) -> assembler; make_solver(assembler) -> up_sol.
+    Returns the final namespace (what the reference keeps in its module globals)."""
+    mod = importlib.import_module("turtlefsi_b200.problems." + problem) if isinstance(problem, str) else problem
+    ns = {}
+    default_variables = copy.deepcopy(_defaults)
+    default_variables.update(mod.set_problem_parameters(default_variables=default_variables) or {})   # monolithic.py:35
+    default_variables.update(overrides or {})                                                        # CLI: :38-43
+    ns.update(default_variables)
+    ns["default_variables"] = default_variables
+    ns.setdefault("results_folder", None)
+    mesh, domains, boundaries = mod.get_mesh_domain_and_boundaries(**ns)                              # :63
+    ns.update(mesh=mesh, domains=domains, boundaries=boundaries)
+    DVP = MixedSpace(mesh, biharmonic=(ns["extrapolation"] == "biharmonic"))                          # :77-92
+    ns["DVP"] = DVP
+    ns.update(assign_domain_properties(**ns))                                                         # :124-125
+    for key, fn in (("fluid", "fluid_setup"), ("solid", "solid_setup"), ("extrapolation", "extrapolate_setup")):
+        m = importlib.import_module("turtlefsi_b200.modules." + ns[key])                              # :139-144
+        ns.update(getattr(m, fn)(**ns))
+    assembler = make_assembler(mesh, DVP, ns["regions"], ns)
+    ns["assembler"] = assembler
+    dvp_ = {k: assembler.new_vector() for k in ("n-2", "n-1", "n")}                                   # :95-111
+    ns["dvp_"] = dvp_
+    ns["up_sol"] = make_solver(assembler)                                                             # :136
+    ns.update(mod.initiate(**ns) or {})                                                               # :147
+    ns.update(mod.create_bcs(**ns) or {})                                                             # :150
+    solver = importlib.import_module("turtlefsi_b200.modules." + ns["solver"])                        # :153
+    ns.update(solver.solver_setup(**ns))
+    ns["dvp_res"] = assembler.new_vector()                                                            # :157
+    ns.setdefault("residual_history", [])
+    t, T, dt = ns["t"], ns["T"], ns["dt"]
+    counter = ns["counter"]
+    ns["first_step_num"] = counter                                                                    # :168
+    stop = False
+    while t <= T + dt / 10 and not stop:                                                              # :169
+        t += dt
+        ns.update(t=t, counter=counter)
+        tmp = mod.pre_solve(**ns)
+        if tmp is not None:
+            ns.update(tmp)
+        ns.update(solver.newtonsolver(**ns))                                                          # :177
+        assembler.copy(dvp_["n-2"], dvp_["n-1"])                                                      # :179-182
+        assembler.copy(dvp_["n-1"], dvp_["n"])
+        tmp = mod.post_solve(**ns)
+        if tmp is not None:
+            ns.update(tmp)
+        counter += 1
+        if max_steps is not None and counter >= max_steps:
+            stop = True
+    ns.update(t=t, counter=counter)
+    mod.finished(**ns)
+    return ns

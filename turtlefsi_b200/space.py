@@ -47,6 +47,7 @@ class MixedSpace:
         self.num_edges = ne
         self.edge_vertices = np.stack([ukey // nv, ukey % nv], axis=1)
         cell_edges = inv.reshape(nc, -1)
+        self.cell_edges = cell_edges
 
         # ---- P2 nodes ordered by anchor vertex (vertex node, then its edges) -----------
         nn = nv + ne
