@@ -139,3 +139,53 @@ def test_host_entry_matches_device_calls(tube_params):
     assert np.abs(A2.cpu().numpy() - A.cpu().numpy()).max() < 1e-12 * scale     # atomic order only
     assert np.abs(bh - b.cpu().numpy()).max() < 1e-12 * np.abs(bh).max()
     assert abs(ss - float((bh ** 2).sum())) < 1e-10 * ss
+
+
+def test_partitioned_assembly_owned_rows_equal_global(tube_params):
+    """multi-GPU path emulated on one GPU: each rank's local assembly (own cells + ghost layer) gives,
+    on the rows it owns, exactly the rows of the single-domain assembly (no reduction needed)."""
+    import scipy.sparse as sp
+    import torch
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.partition import LocalSpaceGlobalKeys, SlabMesh, synthetic_state_global
+    from turtlefsi_b200.space import MixedSpace
+    common, regions = tube_params
+    n, world = 3, 2
+
+    def local(r, w, nz=None):
+        slab = SlabMesh(n, r, w, nz=nz)
+        space = MixedSpace(slab.mesh)
+        gk = LocalSpaceGlobalKeys(slab, space)
+        asm = FSIAssembler(slab.mesh, space, regions, common["dt"], common["theta"])
+        x = synthetic_state_global(slab, space, gk, 2024, 0.3)
+        x1 = synthetic_state_global(slab, space, gk, 2025, 0.3)
+        xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+        A = asm.assemble_jacobian(xd, x1d, asm.assemble_A_pre(xd, x1d))
+        b = asm.assemble_residual(xd, x1d)
+        torch.cuda.synchronize()
+        M = sp.csr_matrix((A.cpu().numpy(), asm.colidx.cpu().numpy(), asm.rowptr.cpu().numpy()),
+                          shape=(space.num_dofs, space.num_dofs))
+        # (global node key, component) of every local dof
+        node = np.repeat(np.arange(space.num_nodes), space.node_ncomp)
+        comp = np.arange(space.num_dofs) - space.node_base[node]
+        return slab, space, gk, M, b.cpu().numpy(), gk.key[node], comp
+
+    gslab, gspace, ggk, GM, gb, gkey, gcomp = local(0, 1, nz=n * world)
+    lookup = {(int(k), int(c)): i for i, (k, c) in enumerate(zip(gkey, gcomp))}
+    covered = 0
+    for r in range(world):
+        slab, space, gk, M, b, key, comp = local(r, world)
+        to_global = np.array([lookup[(int(k), int(c))] for k, c in zip(key, comp)])
+        owned = np.repeat(gk.owned, space.node_ncomp)
+        Mo = M[owned].tocoo()
+        rows_g = to_global[np.nonzero(owned)[0][Mo.row]]
+        cols_g = to_global[Mo.col]
+        L = sp.csr_matrix((Mo.data, (rows_g, cols_g)), shape=GM.shape)
+        sel = np.zeros(GM.shape[0], dtype=bool)
+        sel[to_global[owned]] = True
+        D = (L - sp.diags(sel.astype(float)) @ GM).tocoo()
+        scale = abs(GM).max()
+        assert abs(D.data).max() < 1e-12 * scale
+        assert np.abs(b[owned] - gb[to_global[owned]]).max() < 1e-12 * np.abs(gb).max()
+        covered += int(sel.sum())
+    assert covered == GM.shape[0]

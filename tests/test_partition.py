@@ -1,0 +1,120 @@
+"""Host logic of the multi-GPU path (CPU): slab partition, node ownership, halo index lists, and a
+world_size-2 gloo run of the halo exchange protocol."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from turtlefsi_b200.partition import (LocalSpaceGlobalKeys, SlabMesh, halo_lists, synthetic_state_global)
+from turtlefsi_b200.space import MixedSpace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _local(n, r, w, nz=None):
+    slab = SlabMesh(n, r, w, nz=nz)
+    sp = MixedSpace(slab.mesh)
+    return slab, sp, LocalSpaceGlobalKeys(slab, sp)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_covers_global_mesh_and_owners_are_unique(world):
+    n = 3
+    glob = _local(n, 0, 1, nz=n * world)
+    parts = [_local(n, r, world) for r in range(world)]
+    assert sum(int(p[0].cell_owned.sum()) for p in parts) == glob[0].mesh.num_cells
+    # every global node is owned by exactly one rank, and ranks agree on the owner
+    owners = {}
+    for r, (slab, sp, gk) in enumerate(parts):
+        for k, o in zip(gk.key, gk.owner):
+            assert owners.setdefault(int(k), int(o)) == int(o)
+    assert set(owners) == set(int(k) for k in glob[2].key)
+    for r, (slab, sp, gk) in enumerate(parts):
+        mine = set(int(k) for k in gk.key[gk.owned])
+        assert mine == {k for k, o in owners.items() if o == r}
+        # every cell touching an owned node is present locally (owned rows complete without reduction)
+        cells_here = {tuple(sorted(slab.global_vertex[c])) for c in slab.mesh.cells}
+        gslab, gsp, ggk = glob
+        touch = np.isin(ggk.key[gsp.cell_nodes], list(mine)).any(axis=1)
+        for c in gslab.mesh.cells[touch]:
+            assert tuple(sorted(gslab.global_vertex[c])) in cells_here
+
+
+def test_halo_lists_pair_up_and_states_agree():
+    world, n = 3, 3
+    parts = [_local(n, r, world) for r in range(world)]
+    lists = [halo_lists(*p) for p in parts]
+    states = [synthetic_state_global(p[0], p[1], p[2], 2024, 0.3) for p in parts]
+
+    def keys(p, dofs):          # (global node key, component) of local dofs
+        slab, sp, gk = p
+        node = np.searchsorted(sp.node_base, dofs, side="right") - 1
+        return np.stack([gk.key[node], dofs - sp.node_base[node]], axis=1)
+    for r in range(world - 1):
+        up, below = lists[r]["send_up"], lists[r + 1]["recv_below"]
+        down, above = lists[r + 1]["send_down"], lists[r]["recv_above"]
+        assert np.array_equal(keys(parts[r], up), keys(parts[r + 1], below))
+        assert np.array_equal(keys(parts[r + 1], down), keys(parts[r], above))
+        # the synthetic state is a function of global keys: ghosts already agree with their owners
+        assert np.array_equal(states[r][up], states[r + 1][below])
+        assert np.array_equal(states[r + 1][down], states[r][above])
+    # ghosts = exactly the non-owned dofs
+    for r, p in enumerate(parts):
+        slab, sp, gk = p
+        ghost = np.concatenate([l for k, l in lists[r].items() if k.startswith("recv") and l is not None])
+        node = np.searchsorted(sp.node_base, ghost, side="right") - 1
+        assert set(node) == set(np.nonzero(~gk.owned)[0])
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from turtlefsi_b200.partition import LocalSpaceGlobalKeys, SlabMesh, halo_lists, synthetic_state_global
+from turtlefsi_b200.space import MixedSpace
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+slab = SlabMesh(3, rank, world); sp = MixedSpace(slab.mesh); gk = LocalSpaceGlobalKeys(slab, sp)
+lists = halo_lists(slab, sp, gk)
+truth = synthetic_state_global(slab, sp, gk, 7, 0.3)
+x = torch.as_tensor(truth.copy())
+ghost = np.concatenate([l for k, l in lists.items() if k.startswith("recv") and l is not None])
+x[torch.as_tensor(ghost.astype(np.int64))] = -1.0          # poison the ghosts
+ops, bufs = [], {}
+for key, peer in (("send_up", rank + 1), ("send_down", rank - 1)):
+    if lists[key] is not None:
+        bufs[key] = x[torch.as_tensor(lists[key].astype(np.int64))].contiguous()
+        ops.append(dist.P2POp(dist.isend, bufs[key], peer))
+for key, peer in (("recv_below", rank - 1), ("recv_above", rank + 1)):
+    if lists[key] is not None:
+        bufs[key] = torch.empty(len(lists[key]), dtype=torch.float64)
+        ops.append(dist.P2POp(dist.irecv, bufs[key], peer))
+for req in dist.batch_isend_irecv(ops):
+    req.wait()
+for key in ("recv_below", "recv_above"):
+    if lists[key] is not None:
+        x[torch.as_tensor(lists[key].astype(np.int64))] = bufs[key]
+assert np.array_equal(x.numpy(), truth), "halo exchange did not restore the ghost values"
+# distributed norm: owned dofs only + all-reduce == the norm of the global vector
+owned_dofs = np.repeat(gk.owned, sp.node_ncomp)
+ss = torch.tensor([float((truth[owned_dofs] ** 2).sum())], dtype=torch.float64)
+dist.all_reduce(ss)
+if rank == 0:
+    g = SlabMesh(3, 0, 1, nz=3 * world); gsp = MixedSpace(g.mesh); ggk = LocalSpaceGlobalKeys(g, gsp)
+    ref = float((synthetic_state_global(g, gsp, ggk, 7, 0.3) ** 2).sum())
+    assert abs(ss.item() - ref) < 1e-12 * ref, (ss.item(), ref)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_halo_exchange_gloo_world2(tmp_path):
+    import subprocess
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
