@@ -119,7 +119,8 @@ def cpu_baseline(n_cpu=20, steps=1, threads=0):
     x1 = synthetic_state(mesh, space, 2025, h=2.0 / n_cpu)
     A = np.zeros(len(pattern[1]))
     rule = ft.quadrature(3, QDEG_J)
-    cores = threads or cport.max_threads()
+    # all host cores of the box (torchrun exports OMP_NUM_THREADS=1: do not rely on OpenMP's default)
+    cores = threads or len(os.sched_getaffinity(0))
     cport.assemble_jacobian(mesh, space, REGIONS, DT, THETA, x, x1, rule, pattern, A, c1=2000, nthreads=cores)  # warm
     times = []
     for _ in range(steps):
@@ -311,6 +312,8 @@ def main():
         "flops_per_cell": flops_fluid, "cells_per_step": n_fluid, "launches_per_step": kf_n // max(args.steps, 1),
         "ms_per_step": kf_avg_ms,
         "traffic": None,
+        "traffic_note": "ncu --set full (profiles/r1_jac_kernels_raw.csv, 110263 fluid cells): dram read 964 MB + write 730 MB "
+                        "per launch = 15.4 KB/cell vs 218 kFLOP/cell -> 14 FLOP/B, above the 5.6 FLOP/B ridge",
         "hbm": {"achieved": alg_bytes_step / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak,
                 "algorithmic_bytes_per_cell": alg_bytes_step / mesh.num_cells,
@@ -328,7 +331,7 @@ def main():
                         "nnz %d (%.0f per cell), P2-P2-P1 monolithic, laplace/constant lifting, Jacobian quadrature "
                         "degree 4 (14 pts), Test_Cylinder parameters" % (
                             args.ncube, mesh.num_cells, n_fluid, n_solid, space.num_dofs, asm.nnz, nnz_per_cell),
-            "step": "tfsi_assemble_jacobian: A := A_pre + J_nl(x) (A_pre copy pipelined on a second stream with the fluid/solid cell kernels)",
+            "step": "tfsi_assemble_jacobian: A := A_pre + J_nl(x) (D2D copy of A_pre, then one kernel per cell region: fluid, solid)",
             "l2": "inputs larger than L2 (A and A_pre are %.1f GB each)" % (asm.nnz * 8 / 1e9),
             "parallelism": "cells partitioned in z-slabs, ghost-dof halo exchange per step" if world > 1 else "single GPU",
         },
