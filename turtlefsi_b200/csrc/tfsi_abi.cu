@@ -130,7 +130,7 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
     CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
     a.cell_list = r.cell_list + sg.first;
     a.ncell_region = sg.count;
-    const int grid = (int)((sg.count + 31) / 32);
+    const int grid = (int)((sg.count + LB<G>::NC - 1) / LB<G>::NC);
     if (r.rc.kind == TFSI_KIND_FLUID) {
         KernelTimer kt(h, 0, st);
         size_t smem = FluidJac<G>::SM::bytes(a.nq);

@@ -64,55 +64,97 @@ __device__ __forceinline__ double load_geometry(const CellArgs& a, int64_t cell,
     return cell_geometry<G>(X, K);
 }
 
-// shared-memory carve-up of the Jacobian kernels (byte offsets).
-//   base   [NBASE][nq][32] f64      per-point tensors, live for the whole CTA
-//   U      coef/coef1 [NCOEF][32] f64 during stage + phase 0; afterwards re-used (with TAIL) for
-//          srank [N2][NCOLS][32] u16 = scatter ranks of the 32 cells
-//   rowst  [NROWS][32] i64          CSR row starts of the rows this kernel scatters into
+// -------------------------------------------------------------------------------------------
+// Jacobian kernels, thread mapping "lane = (cell, trial component b)":
+//   a warp covers CPW = 32/G cells x G trial components (30 of 32 lanes in 3-D); a CTA owns
+//   NC = NGRP * CPW cells (30 in 3-D, 32 in 2-D). Because the dofs of one mesh node are consecutive in
+//   a node-interleaved numbering, the G lanes of a cell hit ADJACENT CSR entries in every scatter
+//   instruction (one or two 32-byte sectors per cell instead of one per lane), and all per-point items
+//   that do not depend on b are shared-memory broadcasts.
+template <int G> struct LB {
+    static constexpr int CPW = 32 / G;                 // cells per warp: 10 (3-D), 16 (2-D)
+    static constexpr int NGRP = (G == 3) ? 3 : 2;      // cell groups per CTA
+    static constexpr int NC = CPW * NGRP;              // cells per CTA
+    static constexpr int RKS = 33;                     // row stride (u16) of the staged ranks: conflict-free
+};
+// item stride of the per-point base: >= n and == G (mod 16) so that lanes (cell, b) reading items
+// (X + b) of cells c fall into distinct 8-byte banks
+constexpr int base_stride(int n, int g) { return n + ((g - n % 16) + 16) % 16; }
+
+// shared-memory carve-up (byte offsets)
+//   base   [nq][NC][STRIDE] f64     per-point tensors, live for the whole CTA
+//   U      coef/coef1 [NCOEF][NC] f64 during stage + phase 0; afterwards re-used for
+//          srank [N2][NCOLS][RKS] u16 = scatter ranks of the CTA's cells
+//   rowst  [NROWS][NC] i64          CSR row starts of the rows this kernel scatters into
+//   geo    [G*G+1][NC] f64          K = J_geo^-1 and |det J_geo|
+//   scell  [NC] i32, counter
 template <int G, int NBASE, int NCOEF, int NCOLS, int NROWS>
 struct JacSmem {
-    static constexpr size_t U_BYTES = 2 * (size_t)NCOEF * 32 * sizeof(double);
-    static constexpr size_t RANK_BYTES = (size_t)Dim<G>::N2 * NCOLS * 32 * sizeof(uint16_t);
+    static constexpr int NC = LB<G>::NC;
+    static constexpr int STRIDE = base_stride(NBASE, G);
+    static constexpr size_t U_BYTES = 2 * (size_t)NCOEF * NC * sizeof(double);
+    static constexpr size_t RANK_BYTES = (((size_t)Dim<G>::N2 * NCOLS * LB<G>::RKS * sizeof(uint16_t)) + 15) / 16 * 16;
     static constexpr size_t UR_BYTES = (U_BYTES > RANK_BYTES ? U_BYTES : RANK_BYTES);
-    static __host__ __device__ size_t off_u(int nq) { return sizeof(double) * (size_t)NBASE * nq * 32; }
+    static __host__ __device__ size_t off_u(int nq) { return sizeof(double) * (size_t)nq * NC * STRIDE; }
     static __host__ __device__ size_t off_rowst(int nq) { return off_u(nq) + UR_BYTES; }
-    static __host__ __device__ size_t off_counter(int nq) { return off_rowst(nq) + (size_t)NROWS * 32 * sizeof(int64_t); }
+    static __host__ __device__ size_t off_geo(int nq) { return off_rowst(nq) + (size_t)NROWS * NC * sizeof(int64_t); }
+    static __host__ __device__ size_t off_cell(int nq) { return off_geo(nq) + (size_t)(G * G + 1) * NC * sizeof(double); }
+    static __host__ __device__ size_t off_counter(int nq) { return off_cell(nq) + (size_t)NC * sizeof(int32_t); }
     static __host__ __device__ size_t bytes(int nq) { return off_counter(nq) + 16; }
 };
 
-// copy the rank rows of the CTA's cells into shared memory, transposed to [i][col][lane]
-// (16-byte global loads: rows are padded to a multiple of 8 entries)
-template <int G, int NCOLS>
-__device__ __forceinline__ void stage_rank(const CellArgs& a, int64_t cell, int lane, int warp, int nwarps,
-                                           uint16_t* srank)
+// cell ids + geometry of the CTA's cells
+template <int G>
+__device__ __forceinline__ void stage_cells(const CellArgs& a, int32_t* scell, double* sgeo)
 {
-    constexpr int N2 = Dim<G>::N2;
+    constexpr int NC = LB<G>::NC;
+    const int c = threadIdx.x;
+    if (c < NC) {
+        const int64_t idx = (int64_t)blockIdx.x * NC + c;
+        const int32_t cell = a.cell_list[idx < a.ncell_region ? idx : a.ncell_region - 1];
+        scell[c] = cell;
+        double K[G][G];
+        const double adet = load_geometry<G>(a, cell, K);
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+#pragma unroll
+            for (int t = 0; t < G; ++t) sgeo[(s * G + t) * NC + c] = K[s][t];
+        sgeo[G * G * NC + c] = adet;
+    }
+}
+
+// rank rows -> shared memory [i][col][cell] (row stride RKS); 16-byte global loads
+template <int G, int NCOLS>
+__device__ __forceinline__ void stage_rank(const CellArgs& a, const int32_t* scell, uint16_t* srank)
+{
+    constexpr int N2 = Dim<G>::N2, NC = LB<G>::NC, RKS = LB<G>::RKS;
     constexpr int NCH = (NCOLS + 7) / 8;
-    for (int idx = warp; idx < N2 * NCH; idx += nwarps) {
-        const int i = idx / NCH, c0 = (idx % NCH) * 8;
-        const uint4 v = *reinterpret_cast<const uint4*>(a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + c0);
+    for (int idx = threadIdx.x; idx < N2 * NCH * NC; idx += JAC_THREADS) {
+        const int c = idx % NC, r = idx / NC;
+        const int i = r / NCH, c0 = (r % NCH) * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(a.rank + ((size_t)scell[c] * N2 + i) * a.ndof_pad + c0);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t)
             if (c0 + t < NCOLS)
-                srank[((i * NCOLS) + c0 + t) * 32 + lane] = (uint16_t)(w[t >> 1] >> ((t & 1) * 16));
+                srank[((i * NCOLS) + c0 + t) * RKS + c] = (uint16_t)(w[t >> 1] >> ((t & 1) * 16));
     }
 }
 
-// scatter one P2xP2 half block: rows (row_loc + i) of the staged row starts, cols col_off + HalfCols
+// scatter one P2xP2 half block of cell slot c: rows (row_loc + i), cols (col_off + HalfCols)
 template <int G, int NCOLS, int HALF>
 __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* rowst, const uint16_t* srank,
-                                             int lane, int row_loc, int col_off,
+                                             int c, int row_loc, int col_off,
                                              const double (&Z)[Dim<G>::N2][HalfCols<G, HALF>::NJ])
 {
-    constexpr int N2 = Dim<G>::N2;
+    constexpr int N2 = Dim<G>::N2, NC = LB<G>::NC, RKS = LB<G>::RKS;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
-        double* dst = a.out + rowst[(row_loc + i) * 32 + lane];
-        const uint16_t* rk = srank + ((i * NCOLS) + col_off) * 32 + lane;
+        double* dst = a.out + rowst[(row_loc + i) * NC + c];
+        const uint16_t* rk = srank + ((i * NCOLS) + col_off) * RKS + c;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * 32], Z[i][jj]);
+        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * RKS], Z[i][jj]);
     }
 }
 
@@ -126,11 +168,12 @@ template <int G> struct FluidJac {
 };
 
 template <int G, int NQ, int FLD, int HALF>
-__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
-                                               const uint16_t* srank, int lane, bool valid, int ca, int cb)
+__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
+                                               const uint16_t* srank, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
+    constexpr int QSTR = LB<G>::NC * FluidJac<G>::SM::STRIDE;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -139,119 +182,139 @@ __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* 
     const int nq = NQ ? NQ : a.nq;
 #pragma unroll 1
     for (int q = 0; q < nq; ++q) {
-        auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+        auto bv = [&](int item) { return basec[q * QSTR + item]; };
         double C[G + 1][G + 1];
         if (FLD == 0) fluid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 7>(c_tabJ, q, C, Z);
     }
     if (valid)
-        scatter_p2p2<G, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, lane, ca * N2, FLD * G * N2 + cb * N2, Z);
+        scatter_p2p2<G, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, FLD * G * N2 + cb * N2, Z);
 }
 
 template <int G, int NQ>
 __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
-    typedef FluidBase<G> FB;
     typedef typename FluidJac<G>::SM SM;
-    constexpr int NCOEF = FluidJac<G>::NCOEF, NROWS = FluidJac<G>::NROWS;
+    constexpr int NCOEF = FluidJac<G>::NCOEF;
+    constexpr int NC = LB<G>::NC, CPW = LB<G>::CPW, NGRP = LB<G>::NGRP, RKS = LB<G>::RKS, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
-    double* coef1 = coef + NCOEF * 32;
+    double* coef1 = coef + NCOEF * NC;
     uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
     int64_t* rowst = reinterpret_cast<int64_t*>(smem_raw + SM::off_rowst(nq));
+    double* sgeo = reinterpret_cast<double*>(smem_raw + SM::off_geo(nq));
+    int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + SM::off_cell(nq));
     int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
-    const bool valid = idx < a.ncell_region;
-    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
-
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) *counter = 0;
-    for (int k = warp; k < NCOEF; k += JAC_WARPS) {
-        const int dof = a.cell_dofs[cell * a.ndof + k];
-        coef[k * 32 + lane] = a.x[dof];
-        coef1[k * 32 + lane] = a.x1[dof];
-        if (k >= G * N2) rowst[(k - G * N2) * 32 + lane] = a.rowptr[dof];   // psi rows, gamma rows
+    stage_cells<G>(a, scell, sgeo);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NCOEF * NC; idx += JAC_THREADS) {
+        const int c = idx % NC, k = idx / NC;
+        const int dof = a.cell_dofs[(int64_t)scell[c] * a.ndof + k];
+        coef[k * NC + c] = a.x[dof];
+        coef1[k * NC + c] = a.x1[dof];
+        if (k >= G * N2) rowst[(k - G * N2) * NC + c] = a.rowptr[dof];   // psi rows, gamma rows
     }
     __syncthreads();
-    {   // phase 0
+    for (int t = threadIdx.x; t < nq * NC; t += JAC_THREADS) {   // phase 0: one (cell, q) per thread
+        const int c = t % NC, q = t / NC;
         double K[G][G];
-        const double adet = load_geometry<G>(a, cell, K);
-        auto cf = [&](int k) { return coef[k * 32 + lane]; };
-        auto cf1 = [&](int k) { return coef1[k * 32 + lane]; };
-        for (int q = warp; q < nq; q += JAC_WARPS) {
-            auto out = [&](int item, double v) { base[(item * nq + q) * 32 + lane] = v; };
-            fluid_base<G>(c_tabJ, q, K, adet, a.rc, cf, cf1, out);
-        }
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+#pragma unroll
+            for (int u = 0; u < G; ++u) K[s][u] = sgeo[(s * G + u) * NC + c];
+        const double adet = sgeo[G * G * NC + c];
+        auto cf = [&](int k) { return coef[k * NC + c]; };
+        auto cf1 = [&](int k) { return coef1[k * NC + c]; };
+        double* dstb = base + ((size_t)q * NC + c) * STRIDE;
+        auto out = [&](int item, double v) { dstb[item] = v; };
+        fluid_base<G>(c_tabJ, q, K, adet, a.rc, cf, cf1, out);
     }
     __syncthreads();
-    stage_rank<G, NCOEF>(a, cell, lane, warp, JAC_WARPS, srank);     // overwrites coef/coef1
+    stage_rank<G, NCOEF>(a, scell, srank);              // overwrites coef/coef1
     __syncthreads();
-    constexpr int NBIG = 4 * G * G;                 // (field d|v) x a x b x half
-    constexpr int NTASK = NBIG + 3 * G;
+
+    // lane -> (cell within the warp's group, component)
+    const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
+    const int lcomp = lane % G;
+    const bool lane_on = lane < CPW * G;
+    constexpr int NBIG = NGRP * 4 * G;                  // group x (field d|v) x a x half ; b = lane
+    constexpr int NTASK = NBIG + NGRP * 3;              // + psi x dp, gamma x dd, gamma x dv per group
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= NTASK) break;
         if (t < NBIG) {
-            const int fld = t / (2 * G * G), r = t % (2 * G * G);
-            const int ca = r / (2 * G), cb = (r >> 1) % G, half = r & 1;
+            const int grp = t % NGRP, r = t / NGRP;
+            const int fld = r / (2 * G), ca = (r >> 1) % G, half = r & 1;
+            const int c = grp * CPW + cw;
+            const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
+            const double* basec = base + (size_t)c * STRIDE;
             if (fld == 0) {
-                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-                else fluid_big_task<G, NQ, 0, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
+                else fluid_big_task<G, NQ, 0, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
             } else {
-                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-                else fluid_big_task<G, NQ, 1, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
+                else fluid_big_task<G, NQ, 1, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
             }
-        } else if (t < NBIG + G) {                  // psi_a x delta p
-            const int ca = t - NBIG;
-            double Z[N2][N1];
+        } else {
+            const int r = t - NBIG;
+            const int grp = r % NGRP, kind = r / NGRP;  // 0: psi x dp (lane comp = a), 1: gamma x dd, 2: gamma x dv
+            const int c = grp * CPW + cw;
+            const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
+            const double* basec = base + (size_t)c * STRIDE;
+            constexpr int QSTR = NC * STRIDE;
+            if (kind == 0) {
+                const int ca = lcomp;
+                double Z[N2][N1];
 #pragma unroll
-            for (int i = 0; i < N2; ++i)
+                for (int i = 0; i < N2; ++i)
 #pragma unroll
-                for (int m = 0; m < N1; ++m) Z[i][m] = 0.0;
-            for (int q = 0; q < nq; ++q) {
-                auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
-                double c[G];
-                fluid_c_psi_dp<G>(bv, ca, c);
-                block_gradp2_p1<G>(c_tabJ, q, c, Z);
-            }
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < N2; ++i) {
-                    double* dst = a.out + rowst[(ca * N2 + i) * 32 + lane];
-                    const uint16_t* rk = srank + ((i * NCOEF) + 2 * G * N2) * 32 + lane;
-#pragma unroll
-                    for (int m = 0; m < N1; ++m) atomicAdd(dst + rk[m * 32], Z[i][m]);
+                    for (int m = 0; m < N1; ++m) Z[i][m] = 0.0;
+                for (int q = 0; q < nq; ++q) {
+                    auto bv = [&](int item) { return basec[q * QSTR + item]; };
+                    double cc[G];
+                    fluid_c_psi_dp<G>(bv, ca, cc);
+                    block_gradp2_p1<G>(c_tabJ, q, cc, Z);
                 }
-            }
-        } else {                                    // gamma x delta d_b | delta v_b
-            const int r = t - NBIG - G;
-            const int fld = r / G, cb = r % G;
-            double Z[N1][N2];
+                if (valid) {
 #pragma unroll
-            for (int m = 0; m < N1; ++m)
+                    for (int i = 0; i < N2; ++i) {
+                        double* dst = a.out + rowst[(ca * N2 + i) * NC + c];
+                        const uint16_t* rk = srank + ((i * NCOEF) + 2 * G * N2) * RKS + c;
 #pragma unroll
-                for (int j = 0; j < N2; ++j) Z[m][j] = 0.0;
-            for (int q = 0; q < nq; ++q) {
-                auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
-                double c[G];
-                if (fld == 0) fluid_c_gamma_dd<G>(bv, cb, c);
-                else fluid_c_gamma_dv<G>(bv, cb, c);
-                block_p1_gradp2<G>(c_tabJ, q, c, Z);
-            }
-            if (valid) {
+                        for (int m = 0; m < N1; ++m) atomicAdd(dst + rk[m * RKS], Z[i][m]);
+                    }
+                }
+            } else {
+                const int fld = kind - 1, cb = lcomp;
+                double Z[N1][N2];
 #pragma unroll
-                for (int m = 0; m < N1; ++m) {
-                    double* dst = a.out + rowst[(G * N2 + m) * 32 + lane];
-                    const uint16_t* rk = srank + ((m * NCOEF) + fld * G * N2 + cb * N2) * 32 + lane;
+                for (int m = 0; m < N1; ++m)
 #pragma unroll
-                    for (int j = 0; j < N2; ++j) atomicAdd(dst + rk[j * 32], Z[m][j]);
+                    for (int j = 0; j < N2; ++j) Z[m][j] = 0.0;
+                for (int q = 0; q < nq; ++q) {
+                    auto bv = [&](int item) { return basec[q * QSTR + item]; };
+                    double cc[G];
+                    if (fld == 0) fluid_c_gamma_dd<G>(bv, cb, cc);
+                    else fluid_c_gamma_dv<G>(bv, cb, cc);
+                    block_p1_gradp2<G>(c_tabJ, q, cc, Z);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int m = 0; m < N1; ++m) {
+                        double* dst = a.out + rowst[(G * N2 + m) * NC + c];
+                        const uint16_t* rk = srank + ((m * NCOEF) + fld * G * N2 + cb * N2) * RKS + c;
+#pragma unroll
+                        for (int j = 0; j < N2; ++j) atomicAdd(dst + rk[j * RKS], Z[m][j]);
+                    }
                 }
             }
         }
@@ -268,11 +331,12 @@ template <int G> struct SolidJac {
 };
 
 template <int G, int NQ, int HALF>
-__device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* base, const int64_t* rowst,
-                                               const uint16_t* srank, int lane, bool valid, int ca, int cb)
+__device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
+                                               const uint16_t* srank, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
+    constexpr int QSTR = LB<G>::NC * SolidJac<G>::SM::STRIDE;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -281,62 +345,74 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
     const int nq = NQ ? NQ : a.nq;
 #pragma unroll 1
     for (int q = 0; q < nq; ++q) {
-        auto bv = [&](int item) { return base[(item * nq + q) * 32 + lane]; };
+        auto bv = [&](int item) { return basec[q * QSTR + item]; };
         double C[G + 1][G + 1];
         solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 4>(c_tabJ, q, C, Z);
     }
-    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, lane, ca * N2, cb * N2, Z);
+    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
 }
 
 template <int G, int NQ>
 __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
-    typedef SolidBase<G> SB;
     typedef typename SolidJac<G>::SM SM;
     constexpr int NCOEF = SolidJac<G>::NCOEF;
+    constexpr int NC = LB<G>::NC, CPW = LB<G>::CPW, NGRP = LB<G>::NGRP, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
     int64_t* rowst = reinterpret_cast<int64_t*>(smem_raw + SM::off_rowst(nq));
+    double* sgeo = reinterpret_cast<double*>(smem_raw + SM::off_geo(nq));
+    int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + SM::off_cell(nq));
     int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
-    const bool valid = idx < a.ncell_region;
-    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
-
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) *counter = 0;
-    for (int k = warp; k < 2 * G * N2; k += JAC_WARPS) {
-        const int dof = a.cell_dofs[cell * a.ndof + k];
-        if (k < G * N2) coef[k * 32 + lane] = a.x[dof];
-        else rowst[(k - G * N2) * 32 + lane] = a.rowptr[dof];
+    stage_cells<G>(a, scell, sgeo);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * G * N2 * NC; idx += JAC_THREADS) {
+        const int c = idx % NC, k = idx / NC;
+        const int dof = a.cell_dofs[(int64_t)scell[c] * a.ndof + k];
+        if (k < G * N2) coef[k * NC + c] = a.x[dof];
+        else rowst[(k - G * N2) * NC + c] = a.rowptr[dof];
     }
     __syncthreads();
-    {
+    for (int t = threadIdx.x; t < nq * NC; t += JAC_THREADS) {
+        const int c = t % NC, q = t / NC;
         double K[G][G];
-        const double adet = load_geometry<G>(a, cell, K);
-        auto cf = [&](int k) { return coef[k * 32 + lane]; };
-        for (int q = warp; q < nq; q += JAC_WARPS) {
-            auto out = [&](int item, double v) { base[(item * nq + q) * 32 + lane] = v; };
-            solid_base<G>(c_tabJ, q, K, adet, a.rc, cf, out);
-        }
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+#pragma unroll
+            for (int u = 0; u < G; ++u) K[s][u] = sgeo[(s * G + u) * NC + c];
+        const double adet = sgeo[G * G * NC + c];
+        auto cf = [&](int k) { return coef[k * NC + c]; };
+        double* dstb = base + ((size_t)q * NC + c) * STRIDE;
+        auto out = [&](int item, double v) { dstb[item] = v; };
+        solid_base<G>(c_tabJ, q, K, adet, a.rc, cf, out);
     }
     __syncthreads();
-    stage_rank<G, NCOEF>(a, cell, lane, warp, JAC_WARPS, srank);
+    stage_rank<G, NCOEF>(a, scell, srank);
     __syncthreads();
-    constexpr int NTASK = 2 * G * G;
+    const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
+    const int lcomp = lane % G;
+    const bool lane_on = lane < CPW * G;
+    constexpr int NTASK = NGRP * 2 * G;                 // group x a x half ; b = lane
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= NTASK) break;
-        const int ca = t / (2 * G), cb = (t >> 1) % G, half = t & 1;
-        if (half == 0) solid_big_task<G, NQ, 0>(a, base, rowst, srank, lane, valid, ca, cb);
-        else solid_big_task<G, NQ, 1>(a, base, rowst, srank, lane, valid, ca, cb);
+        const int grp = t % NGRP, r = t / NGRP;
+        const int ca = r >> 1, half = r & 1;
+        const int c = grp * CPW + cw;
+        const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
+        const double* basec = base + (size_t)c * STRIDE;
+        if (half == 0) solid_big_task<G, NQ, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
+        else solid_big_task<G, NQ, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
     }
 }
 
