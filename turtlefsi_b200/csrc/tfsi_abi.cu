@@ -24,6 +24,9 @@ struct Region {
     int32_t marker;
     int64_t ncells;
     int32_t* cell_list;   // device
+    uint16_t* rank_blk;   // device, per CTA batch (Jacobian kernels)
+    int32_t* dofs_blk;    // device, per CTA batch
+    size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
 };
 
 // One kernel launch of the Jacobian assembly: a slice of one region's cell list. `init_end` is
@@ -106,7 +109,7 @@ int bind_tables(tfsi_handle* h, cudaStream_t st) {
 CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* x, const double* x1, double* out) {
     CellArgs a;
     a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
-    a.rank = h->rank; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.cell_alfa = nullptr;
+    a.rank = h->rank; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.rank_blk = r.rank_blk; a.dofs_blk = r.dofs_blk;
     a.ncell_region = r.ncells; a.ndof = h->ndof; a.ndof_pad = h->ndof_pad; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
     return a;
 }
@@ -130,6 +133,8 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
     CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
     a.cell_list = r.cell_list + sg.first;
     a.ncell_region = sg.count;
+    a.rank_blk = r.rank_blk + (size_t)(sg.first / LB<G>::NC) * r.rank_blk_elems;
+    a.dofs_blk = r.dofs_blk + (size_t)(sg.first / LB<G>::NC) * r.dofs_blk_elems;
     const int grid = (int)((sg.count + LB<G>::NC - 1) / LB<G>::NC);
     if (r.rc.kind == TFSI_KIND_FLUID) {
         KernelTimer kt(h, 0, st);
@@ -269,7 +274,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs); cudaFree(h->colidx);
     cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
-    for (Region& r : h->regions) cudaFree(r.cell_list);
+    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     for (int i = 0; i < h->n_ev; ++i) cudaEventDestroy(h->ev_seg[i]);
@@ -343,7 +348,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
             r.ncells = (int64_t)list.size();
-            r.cell_list = nullptr;
+            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
             CKC(upload(h, &r.cell_list, list.data(), list.size()));
             h->regions.push_back(r);
         }
@@ -371,7 +376,8 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         for (int c = 0; c < nch; ++c)
             for (size_t r = 0; r < h->regions.size(); ++r) {
                 const int64_t n = (int64_t)lists[r].size();
-                int64_t lo = (n * c / nch) / 32 * 32, hi = (c == nch - 1) ? n : (n * (c + 1) / nch) / 32 * 32;
+                const int ncta = (h->gdim == 3) ? LB<3>::NC : LB<2>::NC;   // segment boundaries on CTA batches
+                int64_t lo = (n * c / nch) / ncta * ncta, hi = (c == nch - 1) ? n : (n * (c + 1) / nch) / ncta * ncta;
                 if (hi <= lo) continue;
                 for (int64_t k = lo; k < hi; ++k) {
                     const int32_t* d = cd.data() + (size_t)lists[r][(size_t)k] * h->ndof;
@@ -415,6 +421,28 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "verify kernel: %s", cudaGetErrorString(e)); }
             if (herr) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_PATTERN, "CSR pattern is not a union of dense cell blocks with node-uniform column sets (%d mismatches)", herr); }
         }
+    }
+    // per-CTA-batch blocked copies for the Jacobian kernels (bulk-copy / coalesced staging)
+    for (Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        const int g3 = (g == 3);
+        const int ncta = g3 ? LB<3>::NC : LB<2>::NC, rks = g3 ? LB<3>::RKS : LB<2>::RKS;
+        const bool fl = r.rc.kind == TFSI_KIND_FLUID;
+        const int ncols = fl ? (2 * g * h->n2 + h->n1) : g * h->n2;
+        const int ncoef = fl ? (2 * g * h->n2 + h->n1) : 2 * g * h->n2;
+        size_t rbytes = ((size_t)h->n2 * ncols * rks * sizeof(uint16_t) + 15) / 16 * 16;
+        r.rank_blk_elems = rbytes / sizeof(uint16_t);
+        r.dofs_blk_elems = (size_t)ncoef * ncta;
+        const int64_t nb = (r.ncells + ncta - 1) / ncta;
+        auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
+        CKC(cka(cudaMalloc((void**)&r.rank_blk, (size_t)nb * rbytes)));
+        CKC(cka(cudaMemset(r.rank_blk, 0, (size_t)nb * rbytes)));
+        CKC(cka(cudaMalloc((void**)&r.dofs_blk, (size_t)nb * r.dofs_blk_elems * sizeof(int32_t))));
+        build_rank_blocked_kernel<<<grid_for(nb * h->n2 * ncols * ncta, 256, h->sm_count), 256>>>(
+            h->rank, r.cell_list, r.ncells, h->n2, h->ndof_pad, ncols, ncta, rks, r.rank_blk_elems, r.rank_blk);
+        build_dofs_blocked_kernel<<<grid_for(nb * ncoef * ncta, 256, h->sm_count), 256>>>(
+            h->cell_dofs, r.cell_list, r.ncells, h->ndof, ncoef, ncta, r.dofs_blk);
+        CKC(cka(cudaDeviceSynchronize()));
     }
 #undef CKC
     *out = h;

@@ -41,7 +41,8 @@ struct CellArgs {
     const uint16_t* rank;          // [nc][N2][ndof_pad]
     const int64_t* rowptr;         // [N+1]
     const int32_t* cell_list;      // cells of this region
-    const float* cell_alfa;        // unused (alfa computed in-kernel)
+    const uint16_t* rank_blk;      // per CTA batch: [N2][NCOLS][RKS] ranks in the shared-memory layout
+    const int32_t* dofs_blk;       // per CTA batch: [NCOEF][NC] dofs
     int64_t ncell_region;
     int32_t ndof;                  // dofs per cell (27/39/64/94)
     int32_t ndof_pad;              // row stride of the rank map (multiple of 8 -> 16-byte rows)
@@ -62,6 +63,27 @@ __device__ __forceinline__ double load_geometry(const CellArgs& a, int64_t cell,
         for (int c = 0; c < G; ++c) X[v][c] = a.coords[(int64_t)vid * G + c];
     }
     return cell_geometry<G>(X, K);
+}
+
+
+// ---- TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP) --------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -99,8 +121,10 @@ struct JacSmem {
     static __host__ __device__ size_t off_rowst(int nq) { return off_u(nq) + UR_BYTES; }
     static __host__ __device__ size_t off_geo(int nq) { return off_rowst(nq) + (size_t)NROWS * NC * sizeof(int64_t); }
     static __host__ __device__ size_t off_cell(int nq) { return off_geo(nq) + (size_t)(G * G + 1) * NC * sizeof(double); }
-    static __host__ __device__ size_t off_counter(int nq) { return off_cell(nq) + (size_t)NC * sizeof(int32_t); }
-    static __host__ __device__ size_t bytes(int nq) { return off_counter(nq) + 16; }
+    static __host__ __device__ size_t off_counter(int nq) { return (off_cell(nq) + (size_t)NC * sizeof(int32_t) + 15) / 16 * 16; }
+    static __host__ __device__ size_t off_mbar(int nq) { return off_counter(nq) + 16; }
+    static __host__ __device__ size_t bytes(int nq) { return off_mbar(nq) + 16; }
+    static constexpr size_t DOFS_BLK = (size_t)NCOEF * NC;   // int32 per CTA batch in dofs_blk
 };
 
 // cell ids + geometry of the CTA's cells
@@ -123,21 +147,39 @@ __device__ __forceinline__ void stage_cells(const CellArgs& a, int32_t* scell, d
     }
 }
 
-// rank rows -> shared memory [i][col][cell] (row stride RKS); 16-byte global loads
-template <int G, int NCOLS>
-__device__ __forceinline__ void stage_rank(const CellArgs& a, const int32_t* scell, uint16_t* srank)
+// set-up kernels: per-CTA-batch copies of the scatter ranks (already in the shared-memory layout, so
+// that staging is ONE bulk copy) and of the cell dofs (so that the gather of the batch is coalesced)
+__global__ void build_rank_blocked_kernel(const uint16_t* rank, const int32_t* cell_list, int64_t ncells,
+                                          int n2, int ndof_pad, int ncols, int nc_cta, int rks, size_t blk_elems,
+                                          uint16_t* out)
 {
-    constexpr int N2 = Dim<G>::N2, NC = LB<G>::NC, RKS = LB<G>::RKS;
-    constexpr int NCH = (NCOLS + 7) / 8;
-    for (int idx = threadIdx.x; idx < N2 * NCH * NC; idx += JAC_THREADS) {
-        const int c = idx % NC, r = idx / NC;
-        const int i = r / NCH, c0 = (r % NCH) * 8;
-        const uint4 v = *reinterpret_cast<const uint4*>(a.rank + ((size_t)scell[c] * N2 + i) * a.ndof_pad + c0);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-            if (c0 + t < NCOLS)
-                srank[((i * NCOLS) + c0 + t) * RKS + c] = (uint16_t)(w[t >> 1] >> ((t & 1) * 16));
+    const int64_t nb = (ncells + nc_cta - 1) / nc_cta;
+    const int64_t total = nb * n2 * ncols * nc_cta;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % nc_cta);
+        int64_t r = t / nc_cta;
+        const int col = (int)(r % ncols); r /= ncols;
+        const int i = (int)(r % n2);
+        const int64_t b = r / n2;
+        int64_t idx = b * nc_cta + c;
+        if (idx >= ncells) idx = ncells - 1;
+        const int64_t cell = cell_list[idx];
+        out[(size_t)b * blk_elems + ((size_t)i * ncols + col) * rks + c] = rank[((size_t)cell * n2 + i) * ndof_pad + col];
+    }
+}
+__global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells,
+                                          int ndof, int ncoef, int nc_cta, int32_t* out)
+{
+    const int64_t nb = (ncells + nc_cta - 1) / nc_cta;
+    const int64_t total = nb * ncoef * nc_cta;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % nc_cta);
+        int64_t r = t / nc_cta;
+        const int k = (int)(r % ncoef);
+        const int64_t b = r / ncoef;
+        int64_t idx = b * nc_cta + c;
+        if (idx >= ncells) idx = ncells - 1;
+        out[t] = cell_dofs[(int64_t)cell_list[idx] * ndof + k];
     }
 }
 
@@ -169,7 +211,7 @@ template <int G> struct FluidJac {
 
 template <int G, int NQ, int FLD, int HALF>
 __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
-                                               const uint16_t* srank, int c, bool valid, int ca, int cb)
+                                               const uint16_t* srank, uint64_t* mbar, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
@@ -188,6 +230,7 @@ __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* 
         else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 7>(c_tabJ, q, C, Z);
     }
+    mbar_wait(mbar, 0);                       // ranks have landed (immediately true after the first task)
     if (valid)
         scatter_p2p2<G, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, FLD * G * N2 + cb * N2, Z);
 }
@@ -209,17 +252,20 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
     double* sgeo = reinterpret_cast<double*>(smem_raw + SM::off_geo(nq));
     int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + SM::off_cell(nq));
     int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::off_mbar(nq));
 
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
     stage_cells<G>(a, scell, sgeo);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < NCOEF * NC; idx += JAC_THREADS) {
-        const int c = idx % NC, k = idx / NC;
-        const int dof = a.cell_dofs[(int64_t)scell[c] * a.ndof + k];
-        coef[k * NC + c] = a.x[dof];
-        coef1[k * NC + c] = a.x1[dof];
-        if (k >= G * N2) rowst[(k - G * N2) * NC + c] = a.rowptr[dof];   // psi rows, gamma rows
+    {   // gather of the batch: dofs are pre-blocked [k][cell] (coalesced), the state gathers hit L2
+        const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * SM::DOFS_BLK;
+        for (int idx = threadIdx.x; idx < NCOEF * NC; idx += JAC_THREADS) {
+            const int k = idx / NC;
+            const int dof = dblk[idx];
+            coef[idx] = a.x[dof];
+            coef1[idx] = a.x1[dof];
+            if (k >= G * N2) rowst[idx - G * N2 * NC] = a.rowptr[dof];   // psi rows, gamma rows
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nq * NC; t += JAC_THREADS) {   // phase 0: one (cell, q) per thread
@@ -237,8 +283,11 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
         fluid_base<G>(c_tabJ, q, K, adet, a.rc, cf, cf1, out);
     }
     __syncthreads();
-    stage_rank<G, NCOEF>(a, scell, srank);              // overwrites coef/coef1
-    __syncthreads();
+    if (threadIdx.x == 0) {   // scatter ranks of the batch: one TMA bulk copy into the (now dead) coefficient region;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // it lands while the first tasks compute
+        mbar_expect_tx(mbar, (uint32_t)SM::RANK_BYTES);
+        bulk_g2s(srank, a.rank_blk + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
+    }
 
     // lane -> (cell within the warp's group, component)
     const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
@@ -258,11 +307,11 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
             const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
             const double* basec = base + (size_t)c * STRIDE;
             if (fld == 0) {
-                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
-                else fluid_big_task<G, NQ, 0, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
+                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+                else fluid_big_task<G, NQ, 0, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
             } else {
-                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
-                else fluid_big_task<G, NQ, 1, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
+                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+                else fluid_big_task<G, NQ, 1, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
             }
         } else {
             const int r = t - NBIG;
@@ -284,6 +333,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
                     fluid_c_psi_dp<G>(bv, ca, cc);
                     block_gradp2_p1<G>(c_tabJ, q, cc, Z);
                 }
+                mbar_wait(mbar, 0);
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < N2; ++i) {
@@ -307,6 +357,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
                     else fluid_c_gamma_dv<G>(bv, cb, cc);
                     block_p1_gradp2<G>(c_tabJ, q, cc, Z);
                 }
+                mbar_wait(mbar, 0);
                 if (valid) {
 #pragma unroll
                     for (int m = 0; m < N1; ++m) {
@@ -332,7 +383,7 @@ template <int G> struct SolidJac {
 
 template <int G, int NQ, int HALF>
 __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
-                                               const uint16_t* srank, int c, bool valid, int ca, int cb)
+                                               const uint16_t* srank, uint64_t* mbar, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
@@ -350,6 +401,7 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
         solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 4>(c_tabJ, q, C, Z);
     }
+    mbar_wait(mbar, 0);
     if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
 }
 
@@ -369,16 +421,18 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
     double* sgeo = reinterpret_cast<double*>(smem_raw + SM::off_geo(nq));
     int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + SM::off_cell(nq));
     int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::off_mbar(nq));
 
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
     stage_cells<G>(a, scell, sgeo);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * G * N2 * NC; idx += JAC_THREADS) {
-        const int c = idx % NC, k = idx / NC;
-        const int dof = a.cell_dofs[(int64_t)scell[c] * a.ndof + k];
-        if (k < G * N2) coef[k * NC + c] = a.x[dof];
-        else rowst[(k - G * N2) * NC + c] = a.rowptr[dof];
+    {   // dofs_blk of a solid region: [2*G*N2][NC] = d dofs (trial columns) then v dofs (psi rows)
+        const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * (2 * G * N2 * NC);
+        for (int idx = threadIdx.x; idx < 2 * G * N2 * NC; idx += JAC_THREADS) {
+            const int dof = dblk[idx];
+            if (idx < G * N2 * NC) coef[idx] = a.x[dof];
+            else rowst[idx - G * N2 * NC] = a.rowptr[dof];
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nq * NC; t += JAC_THREADS) {
@@ -395,8 +449,11 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
         solid_base<G>(c_tabJ, q, K, adet, a.rc, cf, out);
     }
     __syncthreads();
-    stage_rank<G, NCOEF>(a, scell, srank);
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, (uint32_t)SM::RANK_BYTES);
+        bulk_g2s(srank, a.rank_blk + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
+    }
     const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
     const int lcomp = lane % G;
     const bool lane_on = lane < CPW * G;
@@ -411,8 +468,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
         const int c = grp * CPW + cw;
         const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
         const double* basec = base + (size_t)c * STRIDE;
-        if (half == 0) solid_big_task<G, NQ, 0>(a, basec, rowst, srank, c, valid, ca, lcomp);
-        else solid_big_task<G, NQ, 1>(a, basec, rowst, srank, c, valid, ca, lcomp);
+        if (half == 0) solid_big_task<G, NQ, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+        else solid_big_task<G, NQ, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
     }
 }
 
