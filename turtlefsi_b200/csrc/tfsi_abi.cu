@@ -133,9 +133,14 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
     CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
     a.cell_list = r.cell_list + sg.first;
     a.ncell_region = sg.count;
-    a.rank_blk = r.rank_blk + (size_t)(sg.first / LB<G>::NC) * r.rank_blk_elems;
-    a.dofs_blk = r.dofs_blk + (size_t)(sg.first / LB<G>::NC) * r.dofs_blk_elems;
-    const int grid = (int)((sg.count + LB<G>::NC - 1) / LB<G>::NC);
+    {
+        const int nc_ = (r.rc.kind == TFSI_KIND_FLUID) ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
+        a.rank_blk = r.rank_blk + (size_t)(sg.first / nc_) * r.rank_blk_elems;
+        a.dofs_blk = r.dofs_blk + (size_t)(sg.first / nc_) * r.dofs_blk_elems;
+    }
+    const bool is_fluid = r.rc.kind == TFSI_KIND_FLUID;
+    const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
+    const int grid = (int)((sg.count + ncta - 1) / ncta);
     if (r.rc.kind == TFSI_KIND_FLUID) {
         KernelTimer kt(h, 0, st);
         size_t smem = FluidJac<G>::SM::bytes(a.nq);
@@ -144,20 +149,20 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
         // compile-time quadrature size for the rule of the headline config (Keast 14-point)
         if (G == 3 && a.nq == 14) {
             CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_fluid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
+            jac_fluid_kernel<G, 14><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
         } else {
             CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_fluid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
+            jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
         }
     } else {
         KernelTimer kt(h, 1, st);
         size_t smem = SolidJac<G>::SM::bytes(a.nq);
         if (G == 3 && a.nq == 14) {
             CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G, 14><<<grid, JAC_THREADS, smem, st>>>(a);
+            jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
         } else {
             CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G, 0><<<grid, JAC_THREADS, smem, st>>>(a);
+            jac_solid_kernel<G, 0><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
         }
     }
     h->launches++;
@@ -376,7 +381,9 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         for (int c = 0; c < nch; ++c)
             for (size_t r = 0; r < h->regions.size(); ++r) {
                 const int64_t n = (int64_t)lists[r].size();
-                const int ncta = (h->gdim == 3) ? LB<3>::NC : LB<2>::NC;   // segment boundaries on CTA batches
+                const bool flr = h->regions[r].rc.kind == TFSI_KIND_FLUID;
+                const int ncta = (h->gdim == 3) ? (flr ? FluidCfg<3>::L::NC : SolidCfg<3>::L::NC)
+                                                : (flr ? FluidCfg<2>::L::NC : SolidCfg<2>::L::NC);   // boundaries on CTA batches
                 int64_t lo = (n * c / nch) / ncta * ncta, hi = (c == nch - 1) ? n : (n * (c + 1) / nch) / ncta * ncta;
                 if (hi <= lo) continue;
                 for (int64_t k = lo; k < hi; ++k) {
@@ -426,8 +433,9 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     for (Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const int g3 = (g == 3);
-        const int ncta = g3 ? LB<3>::NC : LB<2>::NC, rks = g3 ? LB<3>::RKS : LB<2>::RKS;
         const bool fl = r.rc.kind == TFSI_KIND_FLUID;
+        const int ncta = g3 ? (fl ? FluidCfg<3>::L::NC : SolidCfg<3>::L::NC) : (fl ? FluidCfg<2>::L::NC : SolidCfg<2>::L::NC);
+        const int rks = ncta + 1;
         const int ncols = fl ? (2 * g * h->n2 + h->n1) : g * h->n2;
         const int ncoef = fl ? (2 * g * h->n2 + h->n1) : 2 * g * h->n2;
         size_t rbytes = ((size_t)h->n2 * ncols * rks * sizeof(uint16_t) + 15) / 16 * 16;

@@ -28,6 +28,12 @@ constexpr int CELLS_PER_CTA = 32;
 #ifndef TFSI_JAC_WARPS
 #define TFSI_JAC_WARPS 12
 #endif
+#ifndef TFSI_JAC_NGRP
+#define TFSI_JAC_NGRP 3
+#endif
+#ifndef TFSI_JAC_CTAS
+#define TFSI_JAC_CTAS 1
+#endif
 // registers are allocated per 4 warps: 8 warps -> 255 regs/thread, 12 warps -> 168 (9..11 gain nothing)
 constexpr int JAC_WARPS = TFSI_JAC_WARPS;
 constexpr int JAC_THREADS = JAC_WARPS * 32;
@@ -93,12 +99,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 //   a node-interleaved numbering, the G lanes of a cell hit ADJACENT CSR entries in every scatter
 //   instruction (one or two 32-byte sectors per cell instead of one per lane), and all per-point items
 //   that do not depend on b are shared-memory broadcasts.
-template <int G> struct LB {
+template <int G, int NGRP_> struct LB {
     static constexpr int CPW = 32 / G;                 // cells per warp: 10 (3-D), 16 (2-D)
-    static constexpr int NGRP = (G == 3) ? 3 : 2;      // cell groups per CTA
+    static constexpr int NGRP = NGRP_;                 // cell groups (= warps' worth of cells) per CTA
     static constexpr int NC = CPW * NGRP;              // cells per CTA
-    static constexpr int RKS = 33;                     // row stride (u16) of the staged ranks: conflict-free
+    static constexpr int RKS = NC + 1;                 // row stride (u16) of the staged ranks (odd: conflict-free)
 };
+// CTA shapes (measured on B200): the fluid kernel is best with ONE big CTA per SM (30 cells,
+// 12 warps: its per-point base fills the shared memory); the solid kernel's base is half as big and
+// it runs best as THREE small CTAs per SM (10 cells, 4 warps each) whose phases overlap.
+template <int G> struct FluidCfg { static constexpr int NGRP = TFSI_JAC_NGRP, WARPS = TFSI_JAC_WARPS, CTAS = TFSI_JAC_CTAS; typedef LB<G, NGRP> L; };
+template <int G> struct SolidCfg { static constexpr int NGRP = 1, WARPS = 4, CTAS = 3; typedef LB<G, NGRP> L; };
+
 // item stride of the per-point base: >= n and == G (mod 16) so that lanes (cell, b) reading items
 // (X + b) of cells c fall into distinct 8-byte banks
 constexpr int base_stride(int n, int g) { return n + ((g - n % 16) + 16) % 16; }
@@ -110,12 +122,12 @@ constexpr int base_stride(int n, int g) { return n + ((g - n % 16) + 16) % 16; }
 //   rowst  [NROWS][NC] i64          CSR row starts of the rows this kernel scatters into
 //   geo    [G*G+1][NC] f64          K = J_geo^-1 and |det J_geo|
 //   scell  [NC] i32, counter
-template <int G, int NBASE, int NCOEF, int NCOLS, int NROWS>
+template <int G, class L, int NBASE, int NCOEF, int NCOLS, int NROWS>
 struct JacSmem {
-    static constexpr int NC = LB<G>::NC;
+    static constexpr int NC = L::NC;
     static constexpr int STRIDE = base_stride(NBASE, G);
     static constexpr size_t U_BYTES = 2 * (size_t)NCOEF * NC * sizeof(double);
-    static constexpr size_t RANK_BYTES = (((size_t)Dim<G>::N2 * NCOLS * LB<G>::RKS * sizeof(uint16_t)) + 15) / 16 * 16;
+    static constexpr size_t RANK_BYTES = (((size_t)Dim<G>::N2 * NCOLS * L::RKS * sizeof(uint16_t)) + 15) / 16 * 16;
     static constexpr size_t UR_BYTES = (U_BYTES > RANK_BYTES ? U_BYTES : RANK_BYTES);
     static __host__ __device__ size_t off_u(int nq) { return sizeof(double) * (size_t)nq * NC * STRIDE; }
     static __host__ __device__ size_t off_rowst(int nq) { return off_u(nq) + UR_BYTES; }
@@ -128,10 +140,10 @@ struct JacSmem {
 };
 
 // cell ids + geometry of the CTA's cells
-template <int G>
+template <int G, class L>
 __device__ __forceinline__ void stage_cells(const CellArgs& a, int32_t* scell, double* sgeo)
 {
-    constexpr int NC = LB<G>::NC;
+    constexpr int NC = L::NC;
     const int c = threadIdx.x;
     if (c < NC) {
         const int64_t idx = (int64_t)blockIdx.x * NC + c;
@@ -184,12 +196,12 @@ __global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_
 }
 
 // scatter one P2xP2 half block of cell slot c: rows (row_loc + i), cols (col_off + HalfCols)
-template <int G, int NCOLS, int HALF>
+template <int G, class L, int NCOLS, int HALF>
 __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* rowst, const uint16_t* srank,
                                              int c, int row_loc, int col_off,
                                              const double (&Z)[Dim<G>::N2][HalfCols<G, HALF>::NJ])
 {
-    constexpr int N2 = Dim<G>::N2, NC = LB<G>::NC, RKS = LB<G>::RKS;
+    constexpr int N2 = Dim<G>::N2, NC = L::NC, RKS = L::RKS;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
@@ -206,7 +218,9 @@ template <int G> struct FluidJac {
     static constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     static constexpr int NCOEF = 2 * G * N2 + N1;     // local dofs d, v, p = trial columns
     static constexpr int NROWS = G * N2 + N1;          // psi rows then gamma rows
-    typedef JacSmem<G, FluidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
+    typedef typename FluidCfg<G>::L L;
+    static constexpr int THREADS = FluidCfg<G>::WARPS * 32;
+    typedef JacSmem<G, L, FluidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
 };
 
 template <int G, int NQ, int FLD, int HALF>
@@ -215,7 +229,7 @@ __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* 
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
-    constexpr int QSTR = LB<G>::NC * FluidJac<G>::SM::STRIDE;
+    constexpr int QSTR = FluidJac<G>::L::NC * FluidJac<G>::SM::STRIDE;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -232,16 +246,18 @@ __device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* 
     }
     mbar_wait(mbar, 0);                       // ranks have landed (immediately true after the first task)
     if (valid)
-        scatter_p2p2<G, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, FLD * G * N2 + cb * N2, Z);
+        scatter_p2p2<G, typename FluidJac<G>::L, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, FLD * G * N2 + cb * N2, Z);
 }
 
 template <int G, int NQ>
-__global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
+__global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     typedef typename FluidJac<G>::SM SM;
     constexpr int NCOEF = FluidJac<G>::NCOEF;
-    constexpr int NC = LB<G>::NC, CPW = LB<G>::CPW, NGRP = LB<G>::NGRP, RKS = LB<G>::RKS, STRIDE = SM::STRIDE;
+    typedef typename FluidJac<G>::L L;
+    constexpr int JAC_THREADS = FluidJac<G>::THREADS;
+    constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, RKS = L::RKS, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_fluid_kernel(CellArgs a)
 
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
-    stage_cells<G>(a, scell, sgeo);
+    stage_cells<G, L>(a, scell, sgeo);
     {   // gather of the batch: dofs are pre-blocked [k][cell] (coalesced), the state gathers hit L2
         const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * SM::DOFS_BLK;
         for (int idx = threadIdx.x; idx < NCOEF * NC; idx += JAC_THREADS) {
@@ -378,7 +394,9 @@ template <int G> struct SolidJac {
     static constexpr int N2 = Dim<G>::N2;
     static constexpr int NCOEF = G * N2;               // d dofs = trial columns
     static constexpr int NROWS = G * N2;               // psi rows
-    typedef JacSmem<G, SolidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
+    typedef typename SolidCfg<G>::L L;
+    static constexpr int THREADS = SolidCfg<G>::WARPS * 32;
+    typedef JacSmem<G, L, SolidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
 };
 
 template <int G, int NQ, int HALF>
@@ -387,7 +405,7 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
-    constexpr int QSTR = LB<G>::NC * SolidJac<G>::SM::STRIDE;
+    constexpr int QSTR = SolidJac<G>::L::NC * SolidJac<G>::SM::STRIDE;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -402,16 +420,18 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
         block_p2p2<G, HALF, 4>(c_tabJ, q, C, Z);
     }
     mbar_wait(mbar, 0);
-    if (valid) scatter_p2p2<G, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
+    if (valid) scatter_p2p2<G, typename SolidJac<G>::L, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
 }
 
 template <int G, int NQ>
-__global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
+__global__ void __launch_bounds__(SolidCfg<G>::WARPS * 32, SolidCfg<G>::CTAS) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
     typedef typename SolidJac<G>::SM SM;
     constexpr int NCOEF = SolidJac<G>::NCOEF;
-    constexpr int NC = LB<G>::NC, CPW = LB<G>::CPW, NGRP = LB<G>::NGRP, STRIDE = SM::STRIDE;
+    typedef typename SolidJac<G>::L L;
+    constexpr int JAC_THREADS = SolidJac<G>::THREADS;
+    constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = NQ ? NQ : a.nq;
     double* base = reinterpret_cast<double*>(smem_raw);
@@ -425,7 +445,7 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jac_solid_kernel(CellArgs a)
 
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
-    stage_cells<G>(a, scell, sgeo);
+    stage_cells<G, L>(a, scell, sgeo);
     {   // dofs_blk of a solid region: [2*G*N2][NC] = d dofs (trial columns) then v dofs (psi rows)
         const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * (2 * G * N2 * NC);
         for (int idx = threadIdx.x; idx < 2 * G * N2 * NC; idx += JAC_THREADS) {
