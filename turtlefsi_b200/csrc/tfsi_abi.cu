@@ -241,11 +241,11 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
     return 0;
 }
 
-template <int G, bool BIH>
-int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
-    constexpr int NDOF = (BIH ? 3 : 2) * G * Dim<G>::N2 + Dim<G>::N1;
-    const size_t smem = (size_t)NDOF * 32 * (2 * sizeof(double) + sizeof(int32_t));
-    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int G, bool BIH, int NC>
+int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    typedef ResCfg<G, BIH> R;
+    const size_t smem = R::bytes(h->tabR.nq, NC);
+    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const RegionConst& rc = r.rc;
@@ -253,11 +253,20 @@ int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double*
         if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
         KernelTimer kt(h, 2, st);
-        residual_kernel<G, BIH><<<(unsigned)((r.ncells + 31) / 32), RES_THREADS, smem, st>>>(a);
+        residual_kernel<G, BIH, NC><<<(unsigned)((r.ncells + NC - 1) / NC), RES_THREADS, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
     }
     return 0;
+}
+
+template <int G, bool BIH>
+int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    typedef ResCfg<G, BIH> R;
+    // cells per CTA: as many as the per-point flux table allows in shared memory
+    if (R::bytes(h->tabR.nq, 32) <= 220 * 1024) return launch_residual_nc<G, BIH, 32>(h, x, x1, b, st);
+    if (R::bytes(h->tabR.nq, 16) <= 220 * 1024) return launch_residual_nc<G, BIH, 16>(h, x, x1, b, st);
+    return fail(h, TFSI_ERR_UNSUPPORTED, "residual rule with %d points does not fit in shared memory", h->tabR.nq);
 }
 
 int launch_residual(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {

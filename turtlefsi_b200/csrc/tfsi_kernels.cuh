@@ -594,89 +594,112 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
 }
 
 // -------------------------------------------------------------------------------------------
-// RESIDUAL b = -F.  lane = cell; warp w takes quadrature points w, w+8, ...; each thread keeps a
-// private partial cell vector in registers and reduces it into b with RED.ADD.F64.
-template <int G, bool BIH>
+// RESIDUAL b = -F.  lane = cell (NC cells per CTA).
+//   phase 0: thread (cell, q) evaluates the per-point fluxes of F = F_lin + F_nonlin (residual_point)
+//            into shared memory [q][cell][item];
+//   phase 1: a warp takes one (test field, component) row group — 10 rows of every cell — and
+//            accumulates them over ALL quadrature points in registers (sparse P2 test functions),
+//            then ONE reduction per row into b (64 REDs per tet).
+template <int G, bool BIH> struct ResCfg {
+    static constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
+    static constexpr int NDOF = (BIH ? 3 : 2) * G * N2 + N1;
+    static constexpr int NGROUPS = (BIH ? 3 : 2) * G;            // P2 row groups (field, comp): phi, psi (, beta)
+    static constexpr int FS = NGROUPS * (G + 1) + 1;             // flux items per point (+ gamma); odd in all cases
+    static __host__ __device__ size_t off_coef(int nq, int nc) { return sizeof(double) * (size_t)nq * nc * FS; }
+    static __host__ __device__ size_t off_dofs(int nq, int nc) { return off_coef(nq, nc) + 2 * sizeof(double) * (size_t)NDOF * nc; }
+    static __host__ __device__ size_t bytes(int nq, int nc) { return off_dofs(nq, nc) + sizeof(int32_t) * (size_t)NDOF * nc; }
+};
+
+template <int G, bool BIH, int NC>
 __global__ void __launch_bounds__(RES_THREADS, 1) residual_kernel(CellArgs a)
 {
-    constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
-    constexpr int NDOF = (BIH ? 3 : 2) * G * N2 + N1;
-    extern __shared__ double smem[];
-    double* coef = smem;
-    double* coef1 = coef + NDOF * 32;
-    int32_t* sdofs = reinterpret_cast<int32_t*>(coef1 + NDOF * 32);
+    typedef ResCfg<G, BIH> R;
+    constexpr int N2 = R::N2, N1 = R::N1, NDOF = R::NDOF, FS = R::FS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nq = a.nq;
+    double* flux = reinterpret_cast<double*>(smem_raw);
+    double* coef = reinterpret_cast<double*>(smem_raw + R::off_coef(nq, NC));
+    double* coef1 = coef + NDOF * NC;
+    int32_t* sdofs = reinterpret_cast<int32_t*>(smem_raw + R::off_dofs(nq, NC));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
-    const bool valid = idx < a.ncell_region;
-    const int64_t cell = a.cell_list[valid ? idx : a.ncell_region - 1];
-    for (int k = warp; k < NDOF; k += RES_WARPS) {
-        int dof = a.cell_dofs[cell * a.ndof + k];
-        sdofs[k * 32 + lane] = dof;
-        coef[k * 32 + lane] = a.x[dof];
-        coef1[k * 32 + lane] = a.x1[dof];
+    for (int idx = threadIdx.x; idx < NDOF * NC; idx += RES_THREADS) {
+        const int c = idx % NC, k = idx / NC;
+        const int64_t ci = (int64_t)blockIdx.x * NC + c;
+        const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
+        const int dof = a.cell_dofs[cell * a.ndof + k];
+        sdofs[idx] = dof;
+        coef[idx] = a.x[dof];
+        coef1[idx] = a.x1[dof];
     }
     __syncthreads();
-    double K[G][G];
-    const double adet = load_geometry<G>(a, cell, K);
-    double alfa_cell = a.rc.alfa;
-    if (a.rc.ext == 1 && a.rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
-    auto cf = [&](int k) { return coef[k * 32 + lane]; };
-    auto cf1 = [&](int k) { return coef1[k * 32 + lane]; };
-
-    double acc_psi[G][N2], acc_phi[G][N2], acc_gam[N1];
-    double acc_beta[BIH ? G : 1][N2];
+    for (int t = threadIdx.x; t < nq * NC; t += RES_THREADS) {       // phase 0
+        const int c = t % NC, q = t / NC;
+        const int64_t ci = (int64_t)blockIdx.x * NC + c;
+        const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
+        double K[G][G];
+        const double adet = load_geometry<G>(a, cell, K);
+        double alfa_cell = a.rc.alfa;
+        if (a.rc.ext == 1 && a.rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
+        auto cf = [&](int k) { return coef[k * NC + c]; };
+        auto cf1 = [&](int k) { return coef1[k * NC + c]; };
+        PointFlux<G> f;
+        residual_point<G>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
+        double* dst = flux + ((size_t)q * NC + c) * FS;
 #pragma unroll
-    for (int c = 0; c < G; ++c)
+        for (int cc = 0; cc < G; ++cc) {
+            dst[(0 * G + cc) * (G + 1)] = f.phi_val[cc];
+            dst[(1 * G + cc) * (G + 1)] = f.psi_val[cc];
+            if (BIH) dst[(2 * G + cc) * (G + 1)] = f.beta_val[cc];
 #pragma unroll
-        for (int i = 0; i < N2; ++i) { acc_psi[c][i] = 0; acc_phi[c][i] = 0; if (BIH) acc_beta[c][i] = 0; }
-#pragma unroll
-    for (int m = 0; m < N1; ++m) acc_gam[m] = 0;
-
+            for (int s = 0; s < G; ++s) {
+                dst[(0 * G + cc) * (G + 1) + 1 + s] = f.phi_grad[cc][s];
+                dst[(1 * G + cc) * (G + 1) + 1 + s] = f.psi_grad[cc][s];
+                if (BIH) dst[(2 * G + cc) * (G + 1) + 1 + s] = f.beta_grad[cc][s];
+            }
+        }
+        dst[FS - 1] = f.gamma;
+    }
+    __syncthreads();
     const bool fluid = a.rc.kind == 0;
     const bool has_phi = fluid ? (a.rc.ext != 0) : (a.rc.solid_on != 0);
     const bool has_psi = fluid ? (a.rc.fluid_on != 0) : (a.rc.solid_on != 0);
-    for (int q = warp; q < a.nq; q += RES_WARPS) {
-        PointFlux<G> f;
-        residual_point<G>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
+    const bool has_beta = BIH && fluid && a.rc.ext == 2;
+    const int c = lane % NC;                                          // NC is 32 or 16 (half-warps duplicate)
+    const bool valid = (lane < NC) && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
+    for (int t = warp; t <= R::NGROUPS; t += RES_WARPS) {             // phase 1: row groups, last = gamma
+        if (t < R::NGROUPS) {
+            const int fieldg = t / G, cc = t % G;                     // 0 phi (d rows), 1 psi (v rows), 2 beta (w rows)
+            if ((fieldg == 0 && !has_phi) || (fieldg == 1 && !has_psi) || (fieldg == 2 && !has_beta)) continue;
+            double Z[N2];
 #pragma unroll
-        for (int i = 0; i < N2; ++i) {
-            const double ph = c_tabR.phi2[q][i];
+            for (int i = 0; i < N2; ++i) Z[i] = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                const double* src = flux + ((size_t)q * NC + c) * FS + t * (G + 1);
+                double W[G + 1];
 #pragma unroll
-            for (int c = 0; c < G; ++c) {
-                double zp = acc_psi[c][i] + ph * f.psi_val[c];
-                double zd = acc_phi[c][i] + ph * f.phi_val[c];
+                for (int s = 0; s <= G; ++s) W[s] = src[s];
+                test_p2_sparse<G>(c_tabR, q, W, Z);
+            }
+            if (valid) {
+                const int row0 = (fieldg == 0 ? 0 : (fieldg == 1 ? G * N2 : 2 * G * N2 + N1)) + cc * N2;
 #pragma unroll
-                for (int s = 0; s < G; ++s) {
-                    const double g = c_tabR.dphi2[q][i][s];
-                    zp += g * f.psi_grad[c][s];
-                    zd += g * f.phi_grad[c][s];
-                }
-                acc_psi[c][i] = zp; acc_phi[c][i] = zd;
-                if (BIH) {
-                    double zb = acc_beta[c][i] + ph * f.beta_val[c];
+                for (int i = 0; i < N2; ++i) atomicAdd(a.out + sdofs[(row0 + i) * NC + c], -Z[i]);
+            }
+        } else if (fluid && a.rc.fluid_on) {
+            double Zg[N1];
 #pragma unroll
-                    for (int s = 0; s < G; ++s) zb += c_tabR.dphi2[q][i][s] * f.beta_grad[c][s];
-                    acc_beta[c][i] = zb;
-                }
+            for (int m = 0; m < N1; ++m) Zg[m] = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                const double gm = flux[((size_t)q * NC + c) * FS + FS - 1];
+#pragma unroll
+                for (int m = 0; m < N1; ++m) Zg[m] += c_tabR.phi1[q][m] * gm;
+            }
+            if (valid) {
+#pragma unroll
+                for (int m = 0; m < N1; ++m) atomicAdd(a.out + sdofs[(2 * G * N2 + m) * NC + c], -Zg[m]);
             }
         }
-#pragma unroll
-        for (int m = 0; m < N1; ++m) acc_gam[m] += c_tabR.phi1[q][m] * f.gamma;
-    }
-    if (!valid || warp >= a.nq) return;
-#pragma unroll
-    for (int c = 0; c < G; ++c)
-#pragma unroll
-        for (int i = 0; i < N2; ++i) {
-            if (has_phi) atomicAdd(a.out + sdofs[(c * N2 + i) * 32 + lane], -acc_phi[c][i]);
-            if (has_psi) atomicAdd(a.out + sdofs[(G * N2 + c * N2 + i) * 32 + lane], -acc_psi[c][i]);
-            if (BIH && fluid && a.rc.ext == 2)
-                atomicAdd(a.out + sdofs[(2 * G * N2 + N1 + c * N2 + i) * 32 + lane], -acc_beta[c][i]);
-        }
-    if (fluid && a.rc.fluid_on) {
-#pragma unroll
-        for (int m = 0; m < N1; ++m) atomicAdd(a.out + sdofs[(2 * G * N2 + m) * 32 + lane], -acc_gam[m]);
     }
 }
 

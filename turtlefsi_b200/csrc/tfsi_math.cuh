@@ -535,6 +535,29 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
     }
 }
 
+// z_i += phi_i W[0] + ghat_i . W[1..G]  for all P2 functions i (sparse reference gradients, as stage 2)
+template <int G, class Tab>
+TFSI_HD void test_p2_sparse(const Tab& tab, int q, const double (&W)[G + 1], double (&Z)[Dim<G>::N2])
+{
+    constexpr int N2 = Dim<G>::N2;
+    typedef P2Edges<G> E;
+    double Wsum = 0.0;
+#pragma unroll
+    for (int s = 1; s <= G; ++s) Wsum += W[s];
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        double z = Z[i] + tab.phi2[q][i] * W[0];
+        if (i == 0) z -= tab.d4[q][0] * Wsum;
+        else if (i <= G) z += tab.d4[q][i] * W[i];
+        else {
+            const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
+            if (ea == 0) z += tab.l4[q][0] * W[eb] - tab.l4[q][eb] * Wsum;
+            else z += tab.l4[q][ea] * W[eb] + tab.l4[q][eb] * W[ea];
+        }
+        Z[i] = z;
+    }
+}
+
 // P2 gradient-test x P1 value-trial :  Z[i][m] += (ghat_i . c) chi_m
 template <int G, class Tab>
 TFSI_HD void block_gradp2_p1(const Tab& tab, int q, const double (&c)[G],
