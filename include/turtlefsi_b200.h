@@ -106,6 +106,14 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
 int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1,
                            const double* Apre_vals, double* A_vals, void* stream);
 
+/* Optional: register a COMPRESSED copy of A_pre (only its non-zero entries; the linear forms fill
+ * ~15-20 % of the pattern). While `Apre_vals` passed to tfsi_assemble_jacobian is the pointer
+ * registered here, "A := A_pre" streams A once from a position bitmap + the packed non-zeros instead of
+ * reading the full A_pre. The
+ * caller must call it again (or tfsi_assemble_A_pre, which invalidates it) if it changes A_pre. */
+int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre_vals, void* stream);
+int64_t tfsi_compressed_nnz(const tfsi_handle* h);
+
 /* b = assemble(-F)                                          newtonsolver.py:86-88 */
 int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b,
                            void* stream);

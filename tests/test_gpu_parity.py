@@ -60,6 +60,12 @@ def test_assembly_matches_oracle(gdim, biharmonic, n, numbering, tube_params):
     assert _row_rel_err(Jnl.cpu().numpy(), ref_nl, rp) < TOL
     assert _row_rel_err(A.cpu().numpy(), ref_pre + ref_nl, rp) < TOL
     assert np.abs(b.cpu().numpy() - ref_b).max() / np.abs(ref_b).max() < TOL
+    # compressed A_pre path (zero-fill + sparse overwrite) gives the same matrix
+    nz = asm.compress_A_pre(A_pre)
+    assert nz == int((ref_pre != 0).sum()) or nz == int((A_pre != 0).sum().item())
+    A2 = asm.assemble_jacobian(xd, x1d, A_pre)
+    torch.cuda.synchronize()
+    assert _row_rel_err(A2.cpu().numpy(), ref_pre + ref_nl, rp) < TOL
     # CSR pattern / dof map are inputs and must come back untouched (bit-exact)
     assert np.array_equal(asm.rowptr.cpu().numpy(), pattern[0])
     assert np.array_equal(asm.colidx.cpu().numpy(), pattern[1])

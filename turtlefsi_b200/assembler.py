@@ -161,6 +161,11 @@ class FSIAssembler:
         self._check(self.lib.tfsi_assemble_A_pre(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
         return out
 
+    def compress_A_pre(self, A_pre):
+        """register the non-zeros of A_pre so that A := A_pre costs a zero-fill + sparse overwrite."""
+        self._check(self.lib.tfsi_compress_A_pre(self.h, _ptr(A_pre), self._stream()))
+        return int(self.lib.tfsi_compressed_nnz(self.h))
+
     def assemble_jacobian(self, x, x1, A_pre=None, out=None):
         out = self.new_matrix() if out is None else out
         self._check(self.lib.tfsi_assemble_jacobian(self.h, _ptr(x), _ptr(x1), _ptr(A_pre), _ptr(out), self._stream()))

@@ -1,6 +1,7 @@
 // C ABI of libturtlefsi_b200.so (declared in include/turtlefsi_b200.h). Host orchestration only:
 // uploads, scatter-map construction, kernel launches. No CPU compute path exists.
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -63,6 +64,9 @@ struct tfsi_handle {
     int64_t launches;
     int sm_count;
     int profiling;
+    // compressed copy of A_pre (tfsi_compress_A_pre)
+    const double* cpre_src;
+    uint32_t* cpre_bitmap; int64_t* cpre_base; double* cpre_val; int64_t cpre_nnz, cpre_words;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
@@ -174,6 +178,21 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
 int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st) {
     CK(h, cudaEventRecord(h->ev_begin, st));
     CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_begin, 0));
+    const bool use_compressed = Apre && Apre == h->cpre_src && h->segments.size() <= h->regions.size();
+    if (use_compressed) {
+        // A := A_pre as zero-fill + sparse overwrite (one kernel, whole matrix), then the cell kernels
+        bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
+            h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        for (const Segment& sg : h->segments) {
+            const Region& r = h->regions[sg.region];
+            if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
+            int rc = h->gdim == 3 ? launch_jacobian_segment<3>(h, sg, x, x1, A, st) : launch_jacobian_segment<2>(h, sg, x, x1, A, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     auto init = [&](int64_t lo, int64_t hi) -> int {
         if (hi <= lo) return 0;
         if (Apre) CK(h, cudaMemcpyAsync(A + lo, Apre + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, h->copy_stream));
@@ -288,6 +307,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs); cudaFree(h->colidx);
     cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
+    cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
@@ -316,6 +336,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->hx = h->hx1 = h->hb = h->hg = nullptr;
     h->nbc = 0; h->launches = 0; h->profiling = 0;
     h->copy_stream = nullptr; h->ev_begin = nullptr; h->n_ev = 0;
+    h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     int dev = 0;
@@ -468,6 +489,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
 
 int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, double* Apre, void* stream) {
     if (!h || !x || !x1 || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (Apre == h->cpre_src) h->cpre_src = nullptr;     // values change: compressed copy is stale
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(Apre, 0, (size_t)h->nnz * sizeof(double), st));
@@ -480,6 +502,41 @@ int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, co
     if (int rc = bind_tables(h, st)) return rc;
     return launch_jacobian(h, x, x1, Apre, A, st);
 }
+
+int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
+    if (!h || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    h->cpre_src = nullptr;
+    cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
+    h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr;
+    const int64_t nwords = (h->nnz + 31) / 32, ngroups = (nwords + 31) / 32;
+    if (ngroups + 1 > INT32_MAX) return fail(h, TFSI_ERR_UNSUPPORTED, "matrix too large for the bitmap scan");
+    h->cpre_words = nwords;
+    int64_t* cnt = nullptr;
+    CK(h, cudaMalloc((void**)&h->cpre_bitmap, std::max<size_t>((size_t)nwords, 1) * sizeof(uint32_t)));
+    CK(h, cudaMalloc((void**)&h->cpre_base, ((size_t)ngroups + 1) * sizeof(int64_t)));
+    CK(h, cudaMalloc((void**)&cnt, ((size_t)ngroups + 1) * sizeof(int64_t)));
+    CK(h, cudaMemsetAsync(cnt, 0, ((size_t)ngroups + 1) * sizeof(int64_t), st));
+    bitmap_build_kernel<<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(Apre, h->nnz, h->cpre_bitmap, nwords, cnt);
+    void* tmp = nullptr; size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, h->cpre_base, (int)(ngroups + 1), st);
+    CK(h, cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, h->cpre_base, (int)(ngroups + 1), st);
+    int64_t total = 0;
+    CK(h, cudaMemcpyAsync(&total, h->cpre_base + ngroups, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    cudaFree(tmp); cudaFree(cnt);
+    h->cpre_nnz = total;
+    CK(h, cudaMalloc((void**)&h->cpre_val, std::max<size_t>((size_t)total, 1) * sizeof(double)));
+    bitmap_stream_kernel<0><<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(
+        h->cpre_bitmap, nwords, h->cpre_base, h->nnz, Apre, h->cpre_val, nullptr);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(st));
+    h->cpre_src = Apre;
+    return 0;
+}
+
+int64_t tfsi_compressed_nnz(const tfsi_handle* h) { return h ? h->cpre_nnz : -1; }
 
 int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b, void* stream) {
     if (!h || !x || !x1 || !b) return fail(h, TFSI_ERR_ARG, "null argument");

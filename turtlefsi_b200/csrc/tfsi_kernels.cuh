@@ -832,6 +832,82 @@ __global__ void scatter_kernel(double* x, const int32_t* idx, int64_t n, const d
         x[idx[i]] = buf[i];
 }
 
+// ---- compressed A_pre: most entries of A_pre are explicit zeros (only the delta_ab blocks of the linear
+// forms are non-zero, ~19 % of the pattern), so "A := A_pre" streams A ONCE (coalesced) from a flat bitmap
+// of the non-zero positions (1 bit per entry) + the packed non-zero values: 8 B written + ~1.6 B read per
+// entry instead of 8 + 8.  One warp expands 1024 consecutive entries (32 bitmap words).
+__global__ void bitmap_build_kernel(const double* vals, int64_t nnz, uint32_t* bitmap, int64_t nwords, int64_t* group_cnt)
+{
+    // one warp per group of 32 words; lane l builds word l of the group
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t ngroups = (nwords + 31) / 32;
+    for (int64_t gidx = wid; gidx < ngroups; gidx += nw) {
+        uint32_t myword = 0;
+        for (int j = 0; j < 32; ++j) {
+            const int64_t k = (gidx * 32 + j) * 32 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, k < nnz && vals[k] != 0.0);
+            if (lane == j) myword = m;
+        }
+        const int64_t w = gidx * 32 + lane;
+        if (w < nwords) bitmap[w] = myword;
+        int c = __popc(myword);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) group_cnt[gidx] = c;
+    }
+}
+// MODE 0: pack the non-zero values (cval[idx] = vals[k]); MODE 1: expand (A[k] = bit ? cval[idx] : 0)
+template <int MODE>
+__global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, const int64_t* group_base, int64_t nnz,
+                                     const double* vals_in, double* cval, double* A)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t ngroups = (nwords + 31) / 32;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t gidx = wid; gidx < ngroups; gidx += nw) {
+        const int64_t w = gidx * 32 + lane;
+        const uint32_t myword = (w < nwords) ? bitmap[w] : 0u;
+        int pre = __popc(myword);                         // inclusive scan over lanes -> exclusive
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+        pre -= __popc(myword);
+        const int64_t base = group_base[gidx];
+        if (MODE == 0) {
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t m = __shfl_sync(0xffffffffu, myword, j);
+                const int start = __shfl_sync(0xffffffffu, pre, j);
+                const int64_t k = (gidx * 32 + j) * 32 + lane;
+                if (k >= nnz) break;
+                if ((m >> lane) & 1u) cval[base + start + __popc(m & lt)] = vals_in[k];
+            }
+        } else {
+            // expand: every lane writes two consecutive entries (16-byte stores, 512 B per warp instruction)
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t mlo = __shfl_sync(0xffffffffu, myword, 2 * j);
+                const uint32_t mhi = __shfl_sync(0xffffffffu, myword, 2 * j + 1);
+                const int start = __shfl_sync(0xffffffffu, pre, 2 * j);
+                const unsigned long long m = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+                const int pos = 2 * lane;
+                const int64_t k = (gidx * 32 + 2 * j) * 32 + pos;
+                if (k >= nnz) continue;
+                const int below = __popcll(m & ((1ull << pos) - 1ull));
+                const bool b0 = (m >> pos) & 1ull, b1 = (m >> (pos + 1)) & 1ull;
+                const int64_t idx = base + start + below;
+                const double v0 = b0 ? cval[idx] : 0.0;
+                const double v1 = b1 ? cval[idx + (b0 ? 1 : 0)] : 0.0;
+                if (k + 1 < nnz) *reinterpret_cast<double2*>(A + k) = make_double2(v0, v1);
+                else A[k] = v0;
+            }
+        }
+    }
+}
+
 // dof-level CSR columns from the P2-node adjacency (node-interleaved numbering): one thread per
 // node-adjacency entry (I, J); writes the ncomp[I] x ncomp[J] block of column indices.
 __global__ void expand_node_pattern_kernel(int64_t num_nodes, const int64_t* nrowptr, const int32_t* ncol,

@@ -25,6 +25,8 @@ def solver_setup(assembler, dvp_, up_sol, bcs, **namespace):
     bc_dofs, bc_vals = flatten_bcs(bcs)
     assembler.set_bc_dofs(bc_dofs)
     A_pre = assembler.assemble_A_pre(dvp_["n"], dvp_["n-1"])
+    if hasattr(assembler, "compress_A_pre"):
+        assembler.compress_A_pre(A_pre)           # A_pre is final here (problem files edit the forms before)
     A = assembler.new_matrix()
     assembler.copy(A, A_pre)                  # A = Matrix(A_pre)
     b = None
