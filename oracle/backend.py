@@ -13,6 +13,15 @@ class OracleAssembler:
         """use_c_port: assemble with the plain-C restatement (oracle/c, laplace/constant only; it is
         checked against the numpy complex-step forms in tests/test_oracle_forms.py) — 100x faster."""
         self.use_c = use_c_port
+        ext = common.get("extrapolation", "laplace")
+        sub = common.get("extrapolation_sub_type", "constant")
+        self._c_ext = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2}.get(ext, -1)
+        if use_c_port and (self._c_ext < 0 or (ext == "laplace" and sub != "constant")):
+            raise ValueError("the C port covers lifting none | laplace/constant | biharmonic only")
+        if use_c_port:
+            # no_fluid / no_solid: the C port has no switch; drop the region instead (same zero forms)
+            self.regions = [r for r in regions if not ((r["kind"] == "fluid" and common.get("fluid", "fluid") != "fluid" and self._c_ext == 0)
+                                                        or (r["kind"] == "solid" and common.get("solid", "solid") != "solid"))]
         self.mesh, self.space, self.regions, self.common = mesh, space, regions, dict(common)
         self.common.setdefault("hmin", mesh.hmin())
         self.degJ, self.degR = quad_degree_jacobian, quad_degree_residual
@@ -44,7 +53,7 @@ class OracleAssembler:
         v = np.zeros(self.nnz)
         cport.assemble_jacobian(self.mesh, self.space, self.regions, self.common["dt"], self.common["theta"],
                                 np.ascontiguousarray(x), np.ascontiguousarray(x1),
-                                ft.quadrature(self.mesh.gdim, self.degJ), self.pattern, v, part=part)
+                                ft.quadrature(self.mesh.gdim, self.degJ), self.pattern, v, part=part, ext=self._c_ext)
         return v
 
     def assemble_A_pre(self, x, x1, out=None):
@@ -69,7 +78,8 @@ class OracleAssembler:
             b = np.zeros(self.num_dofs)
             cport.assemble_residual(self.mesh, self.space, self.regions, self.common["dt"], self.common["theta"],
                                     np.ascontiguousarray(x), np.ascontiguousarray(x1),
-                                    ft.quadrature(self.mesh.gdim, self.degR), b)
+                                    ft.quadrature(self.mesh.gdim, self.degR), b, ext=self._c_ext,
+                                    gravity=float(self.common.get("gravity") or 0.0))
         else:
             b = oa.assemble_vector(self.mesh, self.space, self.regions, self.common, x, x1, self.degR)
         if out is not None:

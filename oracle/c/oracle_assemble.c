@@ -12,7 +12,7 @@
  * Third-party origin: FFC/DOLFIN/PETSc 2019.1 (un-vendored); validated against the numpy
  * complex-step oracle (oracle/forms.py) in tests/test_oracle_c.py.  PARITY vs DOLFIN: UNPINNED
  * at entry level (see oracle/fem_tables.py header).
- * Build: oracle/Makefile (gcc -O3 -march=x86-64-v3 -fopenmp). Laplace/constant lifting only.
+ * Build: oracle/Makefile (gcc -O3 -march=x86-64-v3 -fopenmp). Lifting: none | laplace/constant | biharmonic cell terms.
  */
 #include <math.h>
 #include <stdint.h>
@@ -108,10 +108,11 @@ static void eval_vec(const tab_t* t, int q, const double* c, double G[10][3], do
 /* element tensor of J_nonlinear for one cell: Ae[ndof*ndof] (row-major), zeroed by the caller */
 /* part: 0 = J_nonlinear, 1 = J_linear (A_pre: fluid.py:33, laplace.py:45 alfa = 1, solid.py:41-43), 2 = both */
 static void jac_cell(const tab_t* t, const oracle_region* rg, double dt, double theta, const double* coords,
-                     const int32_t* cv, const double* u, const double* u1, int ndof, double* Ae, int part)
+                     const int32_t* cv, const double* u, const double* u1, int ndof, double* Ae, int part, int ext)
 {
     const int g = t->g, n1 = t->n1, n2 = t->n2;
-    const int ov = g * n2, op = 2 * g * n2;
+    const int ov = g * n2, op = 2 * g * n2, ow = 2 * g * n2 + n1;
+    const double au = 0.01; /* biharmonic.py:31 */
     double K[3][3];
     const double adet = geometry(g, coords, cv, K);
     const double th0 = theta, k = dt, rho = rg->rho, mu = rg->mu, lam = rg->lambda;
@@ -144,7 +145,12 @@ static void jac_cell(const tab_t* t, const oracle_region* rg, double dt, double 
                         for (int c = 0; c < g; ++c) kk += G[i][c] * G[j][c];
                         if (rg->kind == 0) {
                             Ae[(size_t)(ov + a * n2 + i) * ndof + ov + a * n2 + j] += rho / k * th1 * J1 * mm;
-                            Ae[(size_t)(a * n2 + i) * ndof + a * n2 + j] += jw * kk;
+                            if (ext == 1) Ae[(size_t)(a * n2 + i) * ndof + a * n2 + j] += jw * kk;
+                            if (ext == 2) { /* biharmonic.py:35-36 */
+                                Ae[(size_t)(ow + a * n2 + i) * ndof + ow + a * n2 + j] += au * mm;
+                                Ae[(size_t)(ow + a * n2 + i) * ndof + a * n2 + j] -= au * jw * kk;
+                                Ae[(size_t)(a * n2 + i) * ndof + ow + a * n2 + j] += au * jw * kk;
+                            }
                         } else {
                             Ae[(size_t)(ov + a * n2 + i) * ndof + ov + a * n2 + j] += rho / k * mm;
                             Ae[(size_t)(a * n2 + i) * ndof + a * n2 + j] += delta * rho / k * mm;
@@ -253,10 +259,11 @@ static void jac_cell(const tab_t* t, const oracle_region* rg, double dt, double 
 
 /* element vector of F = F_lin + F_nonlin (laplace/constant lifting) */
 static void res_cell(const tab_t* t, const oracle_region* rg, double dt, double theta, const double* coords,
-                     const int32_t* cv, const double* u, const double* u1, double* Fe)
+                     const int32_t* cv, const double* u, const double* u1, double* Fe, int ext, double grav)
 {
     const int g = t->g, n1 = t->n1, n2 = t->n2;
-    const int ov = g * n2, op = 2 * g * n2;
+    const int ov = g * n2, op = 2 * g * n2, ow = 2 * g * n2 + n1;
+    const double au = 0.01;
     double K[3][3];
     const double adet = geometry(g, coords, cv, K);
     const double th0 = theta, th1 = 1 - theta, k = dt, rho = rg->rho, mu = rg->mu, lam = rg->lambda;
@@ -277,6 +284,7 @@ static void res_cell(const tab_t* t, const oracle_region* rg, double dt, double 
         for (int a = 0; a < g; ++a) for (int b = 0; b < g; ++b) { F[a][b] = (a == b) + Gd[a][b]; F1[a][b] = (a == b) + Gd1[a][b]; }
         const double jw = t->w[q] * adet;
         double fval[3] = {0, 0, 0}, flux[3][3] = {{0}}, dval[3] = {0, 0, 0}, dflux[3][3] = {{0}}, gam = 0;
+        double wval[3] = {0, 0, 0}, wflux[3][3] = {{0}};
         if (rg->kind == 0) {
             double Fi[3][3], Fi1[3][3];
             const double J = inv_g(g, F, Fi), J1 = inv_g(g, F1, Fi1);
@@ -301,7 +309,15 @@ static void res_cell(const tab_t* t, const oracle_region* rg, double dt, double 
                     flux[a][b] = s;
                 }
                 gam += J * H[a][a];
-                for (int b = 0; b < g; ++b) dflux[a][b] = Gd[a][b];   /* laplace.py:45, alfa = 1 */
+                if (ext == 1) for (int b = 0; b < g; ++b) dflux[a][b] = Gd[a][b];   /* laplace.py:45, alfa = 1 */
+            }
+            if (ext == 2) { /* biharmonic.py:35-36 */
+                double w[3], Gw[3][3];
+                eval_vec(t, q, u + ow, G, w, Gw);
+                for (int a = 0; a < g; ++a) {
+                    wval[a] = au * w[a];
+                    for (int b = 0; b < g; ++b) { wflux[a][b] = -au * Gd[a][b]; dflux[a][b] = au * Gw[a][b]; }
+                }
             }
         } else {
             for (int pass = 0; pass < 2; ++pass) {
@@ -326,7 +342,7 @@ static void res_cell(const tab_t* t, const oracle_region* rg, double dt, double 
             }
             const double delta = 1.0e7;
             for (int a = 0; a < g; ++a) {
-                fval[a] = rho / k * (v[a] - v1[a]);
+                fval[a] = rho / k * (v[a] - v1[a]) + (a == 1 ? grav * rho : 0.0);   /* solid.py:65-68 */
                 dval[a] = delta * rho / k * (d[a] - d1[a]) - delta * rho * (th0 * v[a] + th1 * v1[a]);
             }
         }
@@ -336,6 +352,11 @@ static void res_cell(const tab_t* t, const oracle_region* rg, double dt, double 
                 for (int b = 0; b < g; ++b) { s += flux[a][b] * G[i][b]; sd += dflux[a][b] * G[i][b]; }
                 Fe[ov + a * n2 + i] += jw * s;
                 Fe[a * n2 + i] += jw * sd;
+                if (ext == 2) {
+                    double sw = wval[a] * t->phi2[q][i];
+                    for (int b = 0; b < g; ++b) sw += wflux[a][b] * G[i][b];
+                    Fe[ow + a * n2 + i] += jw * sw;
+                }
             }
         for (int m = 0; m < n1; ++m) Fe[op + m] += jw * gam * t->phi1[q][m];
     }
@@ -352,12 +373,12 @@ int tfsi_oracle_assemble_jacobian(int g, int nq, const double* pts, const double
                                   const double* coords, const int32_t* cells, const int32_t* cell_dofs,
                                   const int32_t* marker, int ndof, int nreg, const oracle_region* regs, double dt,
                                   double theta, const double* x, const double* x1, const int64_t* rowptr,
-                                  const int32_t* colidx, double* A_vals, int nthreads, int part)
+                                  const int32_t* colidx, double* A_vals, int nthreads, int part, int ext)
 {
     tab_t tab;
     if (nq > MAXQ) return -1;
     tabulate(g, nq, pts, wts, &tab);
-    const int nloc = 2 * g * tab.n2 + tab.n1;
+    const int nloc = ndof;
     int bad = 0;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -373,7 +394,7 @@ int tfsi_oracle_assemble_jacobian(int g, int nq, const double* pts, const double
             const int32_t* dofs = cell_dofs + c * ndof;
             for (int i = 0; i < nloc; ++i) { u[i] = x[dofs[i]]; u1[i] = x1[dofs[i]]; }
             memset(Ae, 0, sizeof(double) * ndof * ndof);
-            jac_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, ndof, Ae, part);
+            jac_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, ndof, Ae, part, ext);
             for (int i = 0; i < ndof; ++i) {
                 const int64_t lo = rowptr[dofs[i]], hi = rowptr[dofs[i] + 1];
                 for (int j = 0; j < ndof; ++j) {
@@ -396,12 +417,12 @@ int tfsi_oracle_assemble_jacobian(int g, int nq, const double* pts, const double
 int tfsi_oracle_assemble_residual(int g, int nq, const double* pts, const double* wts, int64_t c0, int64_t c1,
                                   const double* coords, const int32_t* cells, const int32_t* cell_dofs,
                                   const int32_t* marker, int ndof, int nreg, const oracle_region* regs, double dt,
-                                  double theta, const double* x, const double* x1, double* b, int nthreads)
+                                  double theta, const double* x, const double* x1, double* b, int nthreads, int ext, double grav)
 {
     tab_t tab;
     if (nq > MAXQ) return -1;
     tabulate(g, nq, pts, wts, &tab);
-    const int nloc = 2 * g * tab.n2 + tab.n1;
+    const int nloc = ndof;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -415,7 +436,7 @@ int tfsi_oracle_assemble_residual(int g, int nq, const double* pts, const double
             const int32_t* dofs = cell_dofs + c * ndof;
             for (int i = 0; i < nloc; ++i) { u[i] = x[dofs[i]]; u1[i] = x1[dofs[i]]; }
             memset(Fe, 0, sizeof Fe);
-            res_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, Fe);
+            res_cell(&tab, rg, dt, theta, coords, cells + c * (g + 1), u, u1, Fe, ext, grav);
             for (int i = 0; i < nloc; ++i) {
 #pragma omp atomic
                 b[dofs[i]] -= Fe[i];

@@ -43,7 +43,7 @@ def max_threads():
 
 
 def assemble_jacobian(mesh, space, regions, dt, theta, x, x1, rule, pattern, A_vals, c0=0, c1=None, nthreads=0,
-                      part="nl"):
+                      part="nl", ext=1):
     lib = load()
     pts, wts = rule
     c1 = mesh.num_cells if c1 is None else c1
@@ -57,13 +57,14 @@ def assemble_jacobian(mesh, space, regions, dt, theta, x, x1, rule, pattern, A_v
         C.c_int(mesh.gdim), C.c_int(len(wts)), _p(pts), _p(wts), C.c_int64(c0), C.c_int64(c1),
         _p(mesh.coords), _p(cells), _p(cd), _p(mk), C.c_int(space.ndof_cell), C.c_int(len(regions)), regs,
         C.c_double(dt), C.c_double(theta), _p(x), _p(x1), _p(rowptr), _p(colidx), _p(A_vals), C.c_int(nthreads),
-        C.c_int({"nl": 0, "lin": 1, "all": 2}[part]))
+        C.c_int({"nl": 0, "lin": 1, "all": 2}[part]), C.c_int(ext))
     if rc != 0:
         raise RuntimeError("oracle C assembly failed (%d)" % rc)
     return A_vals
 
 
-def assemble_residual(mesh, space, regions, dt, theta, x, x1, rule, b, c0=0, c1=None, nthreads=0):
+def assemble_residual(mesh, space, regions, dt, theta, x, x1, rule, b, c0=0, c1=None, nthreads=0, ext=1,
+                      gravity=0.0):
     lib = load()
     pts, wts = rule
     c1 = mesh.num_cells if c1 is None else c1
@@ -74,7 +75,7 @@ def assemble_residual(mesh, space, regions, dt, theta, x, x1, rule, b, c0=0, c1=
     rc = lib.tfsi_oracle_assemble_residual(
         C.c_int(mesh.gdim), C.c_int(len(wts)), _p(pts), _p(wts), C.c_int64(c0), C.c_int64(c1),
         _p(mesh.coords), _p(cells), _p(cd), _p(mk), C.c_int(space.ndof_cell), C.c_int(len(regions)), regs,
-        C.c_double(dt), C.c_double(theta), _p(x), _p(x1), _p(b), C.c_int(nthreads))
+        C.c_double(dt), C.c_double(theta), _p(x), _p(x1), _p(b), C.c_int(nthreads), C.c_int(ext), C.c_double(gravity))
     if rc != 0:
         raise RuntimeError("oracle C residual failed (%d)" % rc)
     return b

@@ -23,6 +23,39 @@ GOLDENS = {
 }
 
 
+CASES = {
+    # name: (problem, overrides, golden key)  — the command lines of the reference's tests
+    "tf_fsi_laplace_constant": ("TF_fsi", dict(theta=0.51, extrapolation="laplace", extrapolation_sub_type="constant"), "TF_fsi"),
+    "tf_fsi_biharmonic_default": ("TF_fsi", dict(theta=0.51), "TF_fsi"),          # tests/test_turtleFSI.py:40-58
+    "tf_cfd": ("TF_cfd", dict(theta=0.5), "TF_cfd"),                              # :12-23
+    "tf_csm": ("TF_csm", dict(), "TF_csm"),                                       # :26-37
+}
+
+
+def run_oracle(problem, overrides):
+    from oracle.backend import OracleAssembler
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.linear_solver import HostLU
+
+    def make_asm(mesh, space, regions, ns):
+        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
+                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
+                      gravity=ns["gravity"])
+        return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"], 10,
+                               use_c_port=True)
+    ov = dict(T=0.05, dt=0.01, verbose=False)
+    ov.update(overrides)
+    ns = monolithic.run(problem, make_asm, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs), overrides=ov)
+    out = {"problem": problem, "overrides": {k: v for k, v in ov.items()},
+           "residual_history": [[int(c), int(i), float(r), float(rr)] for c, i, r, rr in ns["residual_history"]],
+           "num_dofs": int(ns["DVP"].num_dofs), "nnz": int(ns["assembler"].nnz)}
+    for key, name in (("drag", "drag_list"), ("lift", "lift_list"), ("dis_x", "displacement_x_list"),
+                      ("dis_y", "displacement_y_list")):
+        if name in ns:
+            out[key] = [float(v) for v in ns[name]]
+    return out
+
+
 def run_oracle_tf_fsi():
     from oracle.backend import OracleAssembler
     from turtlefsi_b200 import monolithic
@@ -49,4 +82,6 @@ def run_oracle_tf_fsi():
 if __name__ == "__main__":
     json.dump(GOLDENS, open(os.path.join(HERE, "turek_goldens.json"), "w"), indent=1)
     json.dump(run_oracle_tf_fsi(), open(os.path.join(HERE, "tf_fsi_oracle_history.json"), "w"), indent=1)
+    hist = {name: run_oracle(prob, ov) for name, (prob, ov, _) in CASES.items()}
+    json.dump(hist, open(os.path.join(HERE, "turek_oracle_histories.json"), "w"), indent=1)
     print("written")

@@ -1,14 +1,21 @@
-"""ORACLE PIN: the CPU restatement, driven by the re-hosted problem file and the reference's
-Newton loop, must reproduce the end-of-run scalars that the reference's OWN test-suite pins
-(tests/test_turtleFSI.py:61-80 `test_laplace[constant]`: TF_fsi, theta 0.51, dt 0.01, T 0.05,
-laplace/constant lifting) with the reference's own tolerances. This is the only golden the
-reference holds for the path; it exercises forms, element and quadrature conventions,
-dof map, BCs, ident_zeros, the Newton loop with Jacobian reuse predicates, and the drag/lift/
-point-evaluation post-processing ("+" side = lowest cell index)."""
+"""ORACLE PIN against the reference's OWN golden values (the only goldens it holds for this path:
+end-of-run scalars of tests/test_turtleFSI.py). The CPU restatement (oracle/), driven by
+the re-hosted problem files and the reference's Newton loop, reproduces
+
+  TF_fsi  file default (biharmonic, constrained_disp_vel)   tests/test_turtleFSI.py:40-58
+          drag to 2e-14, dis_x to 3e-13, lift to 1e-10, dis_y to 5e-10 RELATIVE
+  TF_cfd  (refined mesh, fluid only)                         :12-23   drag 1e-13, lift 2e-11
+  TF_csm  (refined mesh, solid only, gravity)                :26-37   dis_x 7e-7, dis_y 2e-7
+  TF_fsi  laplace/constant                                   :61-80   within the reference tolerances
+
+i.e. forms, P2/P1 and quadrature conventions, dof map, Dirichlet sets, ident_zeros, the Newton
+loop with its Jacobian-reuse predicates, Plaza refinement and the drag/lift/point-evaluation
+post-processing ("+" side = lowest cell index) all agree with DOLFIN's to round-off."""
 import json
 import os
 
 import numpy as np
+import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -17,7 +24,11 @@ def _goldens():
     return json.load(open(os.path.join(HERE, "golden", "turek_goldens.json")))
 
 
-def test_oracle_reproduces_reference_tf_fsi_goldens():
+def _histories():
+    return json.load(open(os.path.join(HERE, "golden", "turek_oracle_histories.json")))
+
+
+def _run_oracle(problem, overrides, made=None):
     from oracle.backend import OracleAssembler
     from turtlefsi_b200 import monolithic
     from turtlefsi_b200.linear_solver import HostLU
@@ -28,45 +39,74 @@ def test_oracle_reproduces_reference_tf_fsi_goldens():
                       gravity=ns["gravity"])
         return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"], 10,
                                use_c_port=True)
-    ns = monolithic.run("TF_fsi", make_asm, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs),
-                        overrides=dict(T=0.05, dt=0.01, theta=0.51, extrapolation="laplace",
-                                       extrapolation_sub_type="constant", verbose=False))
-    g = _goldens()["TF_fsi"]
-    # reference assertions, tests/test_turtleFSI.py:77-80
-    assert np.isclose(ns["displacement_x_list"][-1], g["dis_x"])
-    assert np.isclose(ns["displacement_y_list"][-1], g["dis_y"])
-    assert np.isclose(ns["drag_list"][-1], g["drag"])
-    assert np.isclose(ns["lift_list"][-1], g["lift"], rtol=1e-4)
-    # sharper than the reference asks: drag to 1e-7
-    assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-7
-    # 6 time steps (the reference's `while t <= T + dt / 10` takes one more than T/dt), 3 Newton its each
-    assert len(ns["drag_list"]) == 6
-    hist = json.load(open(os.path.join(HERE, "golden", "tf_fsi_oracle_history.json")))
-    assert np.allclose(ns["drag_list"], hist["drag"], rtol=1e-10)
-    # mesh sizes quoted in SURVEY 8a: 21 749 dofs, 1 120 795 non-zeros
-    assert ns["DVP"].num_dofs == 21749 and ns["assembler"].nnz == 1120795
-
-
-def test_newton_jacobian_reuse_predicates():
-    """newtonsolver.py:54-63 with recompute=5: the Jacobian is rebuilt at iteration 0 of a step and
-    when the residual increases, re-used otherwise (factorisation count < iteration count)."""
-    from oracle.backend import OracleAssembler
-    from turtlefsi_b200 import monolithic
-    from turtlefsi_b200.linear_solver import HostLU
-    made = {}
-
-    def make_asm(mesh, space, regions, ns):
-        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
-                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
-                      gravity=ns["gravity"])
-        return OracleAssembler(mesh, space, regions, common, 5, 10, use_c_port=True)
 
     def make_solver(a):
-        made["lu"] = HostLU(a.rowptr, a.colidx, a.num_dofs)
-        return made["lu"]
-    ns = monolithic.run("TF_fsi", make_asm, make_solver,
-                        overrides=dict(T=0.02, dt=0.01, theta=0.51, extrapolation="laplace",
-                                       extrapolation_sub_type="constant", verbose=False, recompute=5), max_steps=2)
+        lu = HostLU(a.rowptr, a.colidx, a.num_dofs)
+        if made is not None:
+            made["lu"] = lu
+        return lu
+    ov = dict(T=0.05, dt=0.01, verbose=False)
+    ov.update(overrides)
+    return monolithic.run(problem, make_asm, make_solver, overrides=ov)
+
+
+def test_oracle_reproduces_tf_fsi_file_default_golden():
+    ns = _run_oracle("TF_fsi", dict(theta=0.51))
+    g = _goldens()["TF_fsi"]
+    assert ns["extrapolation"] == "biharmonic" and ns["extrapolation_sub_type"] == "constrained_disp_vel"
+    assert ns["DVP"].num_dofs == 31965 and ns["assembler"].nnz == 2367247          # SURVEY 8a sizes
+    assert len(ns["drag_list"]) == 6          # `while t <= T + dt / 10` takes T/dt + 1 steps
+    # far sharper than the reference's np.isclose(rtol=1e-5): round-off level agreement
+    assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-11
+    assert abs(ns["displacement_x_list"][-1] / g["dis_x"] - 1) < 1e-10
+    assert abs(ns["lift_list"][-1] / g["lift"] - 1) < 1e-8
+    assert abs(ns["displacement_y_list"][-1] / g["dis_y"] - 1) < 1e-7
+
+
+def test_oracle_reproduces_tf_cfd_golden():
+    ns = _run_oracle("TF_cfd", dict(theta=0.5))
+    g = _goldens()["TF_cfd"]
+    assert ns["DVP"].num_dofs == 80938                                               # refined once (Plaza)
+    assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-11
+    assert abs(ns["lift_list"][-1] / g["lift"] - 1) < 1e-8
+
+
+def test_oracle_reproduces_tf_csm_golden_and_reuses_the_jacobian():
+    made = {}
+    ns = _run_oracle("TF_csm", dict(), made)
+    g = _goldens()["TF_csm"]
+    assert np.isclose(ns["displacement_x_list"][-1], g["dis_x"])                     # reference's assertion
+    assert np.isclose(ns["displacement_y_list"][-1], g["dis_y"])
+    assert abs(ns["displacement_y_list"][-1] / g["dis_y"] - 1) < 1e-6
+    # recompute=5 (default): newtonsolver.py:54-63 rebuild at iteration 0, every 5th iteration and
+    # when the residual increases — the factorisation is re-used in between
     iters = len(ns["residual_history"])
-    assert made["lu"].factorizations < iters          # factorisation re-used between iterations
-    assert made["lu"].factorizations >= 2             # but rebuilt at the start of every step
+    assert made["lu"].factorizations < iters and made["lu"].factorizations >= 6
+
+
+def test_stored_oracle_histories_match_reference_goldens():
+    """the committed fixtures (tests/golden/turek_oracle_histories.json, made by make_goldens.py) that
+    the GPU tests compare against are themselves within the reference's tolerances"""
+    h, g = _histories(), _goldens()
+    f = h["tf_fsi_laplace_constant"]
+    assert np.isclose(f["dis_x"][-1], g["TF_fsi"]["dis_x"]) and np.isclose(f["drag"][-1], g["TF_fsi"]["drag"])
+    assert np.isclose(f["lift"][-1], g["TF_fsi"]["lift"], rtol=1e-4)                 # tests/test_turtleFSI.py:80
+    f = h["tf_fsi_biharmonic_default"]
+    for k in ("dis_x", "dis_y", "drag", "lift"):
+        assert np.isclose(f[k][-1], g["TF_fsi"][k])
+    assert np.isclose(h["tf_cfd"]["drag"][-1], g["TF_cfd"]["drag"]) and np.isclose(h["tf_cfd"]["lift"][-1], g["TF_cfd"]["lift"])
+    assert np.isclose(h["tf_csm"]["dis_x"][-1], g["TF_csm"]["dis_x"]) and np.isclose(h["tf_csm"]["dis_y"][-1], g["TF_csm"]["dis_y"])
+
+
+def test_plaza_refinement_properties():
+    from turtlefsi_b200.mesh import read_dolfin_xml, refine
+    m = read_dolfin_xml(os.path.join(HERE, "golden", "meshes", "TF_cfd.xml.gz"))
+    r = refine(m)
+    assert (r.num_vertices, r.num_cells) == (4858, 9304)                             # SURVEY 8a
+    area = lambda mesh: 0.5 * np.abs(np.linalg.det(np.swapaxes(
+        mesh.coords[mesh.cells][:, 1:] - mesh.coords[mesh.cells][:, :1], 1, 2))).sum()
+    assert abs(area(m) - area(r)) < 1e-13
+    # conforming: every interior edge is shared by exactly two triangles
+    from turtlefsi_b200.boundary import Facets
+    f = Facets(r)
+    assert f.on_boundary.sum() == 2 * Facets(m).on_boundary.sum()

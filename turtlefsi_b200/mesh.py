@@ -73,6 +73,46 @@ def read_dolfin_xml(path):
     return Mesh(coords, cells, np.zeros(len(cl), dtype=np.int32))
 
 
+def refine(mesh):
+    """Uniform refinement of a triangle mesh as DOLFIN's `refine(mesh)` does it (PlazaRefinementND,
+    [dep] DOLFIN 2019.1, used by turtleFSI/problems/TF_cfd.py:49 and TF_csm.py:54): a triangle whose
+    shortest/longest edge ratio is >= sqrt(2)/2 is split into 4 similar triangles ("red"); a more
+    distorted one is bisected at the midpoint of its longest edge and each half again at the midpoint
+    of its other edge. New vertices = edge midpoints. Children of cell c are cells 4c..4c+3."""
+    if mesh.gdim != 2:
+        raise NotImplementedError("refine: triangles only")
+    cells = mesh.cells.astype(np.int64)
+    nv = mesh.num_vertices
+    X = mesh.coords
+    # local edge k is opposite to local vertex k (UFC)
+    loc = [(1, 2), (0, 2), (0, 1)]
+    lo = np.stack([np.minimum(cells[:, a], cells[:, b]) for a, b in loc], axis=1)
+    hi = np.stack([np.maximum(cells[:, a], cells[:, b]) for a, b in loc], axis=1)
+    ukey, inv = np.unique((lo * nv + hi).ravel(), return_inverse=True)
+    mid = nv + inv.reshape(-1, 3)                       # midpoint vertex of local edge k
+    newX = np.vstack([X, 0.5 * (X[ukey // nv] + X[ukey % nv])])
+    length = np.linalg.norm(X[hi] - X[lo], axis=2)     # [nc, 3]
+    ok = length.min(axis=1) / length.max(axis=1) >= np.sqrt(2.0) / 2.0
+    L = np.argmax(length, axis=1)                       # first longest edge
+    out = np.zeros((len(cells), 4, 3), dtype=np.int64)
+    v = cells
+    e = mid
+    # red refinement
+    red = np.stack([np.stack([e[:, 0], e[:, 1], v[:, 2]], 1), np.stack([e[:, 1], e[:, 2], v[:, 0]], 1),
+                    np.stack([e[:, 2], e[:, 0], v[:, 1]], 1), np.stack([e[:, 2], e[:, 1], e[:, 0]], 1)], axis=1)
+    # bisection: v0, v1 at the ends of the longest edge (index L), v2 opposite
+    i0, i1, i2 = (L + 1) % 3, (L + 2) % 3, L
+    r = np.arange(len(cells))
+    V0, V1, V2 = v[r, i0], v[r, i1], v[r, i2]
+    E0, E1, E2 = e[r, i0], e[r, i1], e[r, i2]
+    bis = np.stack([np.stack([E2, V2, E0], 1), np.stack([E2, E0, V1], 1),
+                    np.stack([E2, V2, E1], 1), np.stack([E2, E1, V0], 1)], axis=1)
+    out = np.where(ok[:, None, None], red, bis).reshape(-1, 3)
+    out = np.sort(out, axis=1).astype(np.int32)
+    markers = np.repeat(mesh.markers, 4) if mesh.markers is not None else None
+    return Mesh(newX, out, markers, meta=dict(mesh.meta, refined=True))
+
+
 def _morton3(ix, iy, iz):
     def spread(v):
         v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
