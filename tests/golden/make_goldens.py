@@ -79,9 +79,47 @@ def run_oracle_tf_fsi():
     }
 
 
+def run_numpy_oracle_elastic():
+    """test_elastic (tests/test_turtleFSI.py:106-123): elastic lifting exists only in the numpy oracle
+    (oracle/forms.py, turtleFSI/modules/elastic.py:18-27); ~2 minutes."""
+    import types
+    from oracle.backend import OracleAssembler
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.linear_solver import HostLU
+    mod = types.ModuleType("turtlefsi_b200.modules.elastic")
+
+    def extrapolate_setup(F_fluid_linear, extrapolation_sub_type="constant", **ns):
+        t = dict(F_fluid_linear)
+        t.update(extrapolation="elastic", extrapolation_sub_type=extrapolation_sub_type)
+        return dict(F_fluid_linear=t)
+    mod.extrapolate_setup = extrapolate_setup
+    sys.modules["turtlefsi_b200.modules.elastic"] = mod
+
+    def make_asm(mesh, space, regions, ns):
+        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
+                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
+                      gravity=ns["gravity"])
+        return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"], 10)
+    ns = monolithic.run("TF_fsi", make_asm, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs),
+                        overrides=dict(T=0.05, dt=0.01, theta=0.51, extrapolation="elastic",
+                                       extrapolation_sub_type="constant", verbose=False))
+    return {"problem": "TF_fsi", "overrides": "-e elastic -et constant --theta 0.51", "oracle": "numpy complex-step",
+            "drag": [float(v) for v in ns["drag_list"]], "lift": [float(v) for v in ns["lift_list"]],
+            "dis_x": [float(v) for v in ns["displacement_x_list"]], "dis_y": [float(v) for v in ns["displacement_y_list"]]}
+
+
 if __name__ == "__main__":
     json.dump(GOLDENS, open(os.path.join(HERE, "turek_goldens.json"), "w"), indent=1)
     json.dump(run_oracle_tf_fsi(), open(os.path.join(HERE, "tf_fsi_oracle_history.json"), "w"), indent=1)
     hist = {name: run_oracle(prob, ov) for name, (prob, ov, _) in CASES.items()}
+    if "--elastic" in sys.argv:
+        hist["tf_fsi_elastic_numpy_oracle"] = run_numpy_oracle_elastic()
+    else:   # keep the stored (slow to regenerate) elastic run
+        try:
+            old = json.load(open(os.path.join(HERE, "turek_oracle_histories.json")))
+            if "tf_fsi_elastic_numpy_oracle" in old:
+                hist["tf_fsi_elastic_numpy_oracle"] = old["tf_fsi_elastic_numpy_oracle"]
+        except Exception:
+            pass
     json.dump(hist, open(os.path.join(HERE, "turek_oracle_histories.json"), "w"), indent=1)
     print("written")

@@ -98,6 +98,14 @@ def test_stored_oracle_histories_match_reference_goldens():
     assert np.isclose(h["tf_csm"]["dis_x"][-1], g["TF_csm"]["dis_x"]) and np.isclose(h["tf_csm"]["dis_y"][-1], g["TF_csm"]["dis_y"])
 
 
+def test_stored_elastic_oracle_run_matches_reference_golden():
+    """test_elastic (tests/test_turtleFSI.py:106-123): elastic lifting lives only in the numpy oracle (the
+    kernels refuse it); its 2-minute run is stored by `make_goldens.py --elastic` and checked here."""
+    f, g = _histories()["tf_fsi_elastic_numpy_oracle"], _goldens()["TF_fsi_elastic"]
+    assert abs(f["drag"][-1] / g["drag"] - 1) < 1e-11 and abs(f["dis_x"][-1] / g["dis_x"] - 1) < 1e-10
+    assert abs(f["lift"][-1] / g["lift"] - 1) < 1e-8 and abs(f["dis_y"][-1] / g["dis_y"] - 1) < 1e-7
+
+
 def test_plaza_refinement_properties():
     from turtlefsi_b200.mesh import read_dolfin_xml, refine
     m = read_dolfin_xml(os.path.join(HERE, "golden", "meshes", "TF_cfd.xml.gz"))
