@@ -15,6 +15,7 @@
 // B = K F^-1 maps reference gradients to gradients on the deformed cell, g_i = B^T ghat_i.
 // Sum factorisation: W_sj = C'_st U_jt, then Z_ij += T_is W_sj.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 
@@ -502,11 +503,11 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
             W[0] = 0.0;
             if (MODE & 1) W[0] = C[0][0] * tab.phi2[q][j];
             if (ea == 0) {
-                if (MODE & 2) W[0] += La * C[0][eb] - Lb * Cs[0];
+                if (MODE & 2) { W[0] = fma(La, C[0][eb], W[0]); W[0] = fma(-Lb, Cs[0], W[0]); }
 #pragma unroll
                 for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? La * C[s][eb] - Lb * Cs[s] : 0.0;
             } else {
-                if (MODE & 2) W[0] += La * C[0][eb] + Lb * C[0][ea];
+                if (MODE & 2) { W[0] = fma(La, C[0][eb], W[0]); W[0] = fma(Lb, C[0][ea], W[0]); }
 #pragma unroll
                 for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? La * C[s][eb] + Lb * C[s][ea] : 0.0;
             }
@@ -519,15 +520,16 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
         }
 #pragma unroll
         for (int i = 0; i < N2; ++i) {
+            // one FMA per term, accumulated in sequence: `z += a*b + c*d` would cost DMUL + DFMA + DADD
             double z = Z[i][jj];
-            if (MODE & 3) z += tab.phi2[q][i] * W[0];
+            if (MODE & 3) z = fma(tab.phi2[q][i], W[0], z);
             if (MODE & 4) {
-                if (i == 0) z -= tab.d4[q][0] * Wsum;
-                else if (i <= G) z += tab.d4[q][i] * W[i];
+                if (i == 0) z = fma(-tab.d4[q][0], Wsum, z);
+                else if (i <= G) z = fma(tab.d4[q][i], W[i], z);
                 else {
                     const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
-                    if (ea == 0) z += tab.l4[q][0] * W[eb] - tab.l4[q][eb] * Wsum;
-                    else z += tab.l4[q][ea] * W[eb] + tab.l4[q][eb] * W[ea];
+                    if (ea == 0) { z = fma(tab.l4[q][0], W[eb], z); z = fma(-tab.l4[q][eb], Wsum, z); }
+                    else { z = fma(tab.l4[q][ea], W[eb], z); z = fma(tab.l4[q][eb], W[ea], z); }
                 }
             }
             Z[i][jj] = z;
@@ -546,13 +548,13 @@ TFSI_HD void test_p2_sparse(const Tab& tab, int q, const double (&W)[G + 1], dou
     for (int s = 1; s <= G; ++s) Wsum += W[s];
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
-        double z = Z[i] + tab.phi2[q][i] * W[0];
-        if (i == 0) z -= tab.d4[q][0] * Wsum;
-        else if (i <= G) z += tab.d4[q][i] * W[i];
+        double z = fma(tab.phi2[q][i], W[0], Z[i]);
+        if (i == 0) z = fma(-tab.d4[q][0], Wsum, z);
+        else if (i <= G) z = fma(tab.d4[q][i], W[i], z);
         else {
             const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
-            if (ea == 0) z += tab.l4[q][0] * W[eb] - tab.l4[q][eb] * Wsum;
-            else z += tab.l4[q][ea] * W[eb] + tab.l4[q][eb] * W[ea];
+            if (ea == 0) { z = fma(tab.l4[q][0], W[eb], z); z = fma(-tab.l4[q][eb], Wsum, z); }
+            else { z = fma(tab.l4[q][ea], W[eb], z); z = fma(tab.l4[q][eb], W[ea], z); }
         }
         Z[i] = z;
     }
