@@ -223,8 +223,8 @@ template <int G> struct FluidJac {
     typedef JacSmem<G, L, FluidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
 };
 
-template <int G, int NQ, int FLD, int HALF>
-__device__ __forceinline__ void fluid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
+template <int G, int NQ, int HALF>
+__device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a, const double* basec, const int64_t* rowst,
                                                const uint16_t* srank, uint64_t* mbar, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
@@ -322,13 +322,10 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
             const int c = grp * CPW + cw;
             const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
             const double* basec = base + (size_t)c * STRIDE;
-            if (fld == 0) {
-                if (half == 0) fluid_big_task<G, NQ, 0, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
-                else fluid_big_task<G, NQ, 0, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
-            } else {
-                if (half == 0) fluid_big_task<G, NQ, 1, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
-                else fluid_big_task<G, NQ, 1, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
-            }
+            // the field (delta d | delta v) only selects the C' builder inside the loop (warp-uniform branch):
+            // two code variants (halves) instead of four keep the hot loops inside the instruction cache
+            if (half == 0) fluid_big_task<G, NQ, 0>(fld, a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+            else fluid_big_task<G, NQ, 1>(fld, a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
         } else {
             const int r = t - NBIG;
             const int grp = r % NGRP, kind = r / NGRP;  // 0: psi x dp (lane comp = a), 1: gamma x dd, 2: gamma x dv
