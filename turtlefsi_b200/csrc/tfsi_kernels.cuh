@@ -275,12 +275,30 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
     stage_cells<G, L>(a, scell, sgeo);
     {   // gather of the batch: dofs are pre-blocked [k][cell] (coalesced), the state gathers hit L2
         const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * SM::DOFS_BLK;
-        for (int idx = threadIdx.x; idx < NCOEF * NC; idx += JAC_THREADS) {
-            const int k = idx / NC;
-            const int dof = dblk[idx];
-            coef[idx] = a.x[dof];
-            coef1[idx] = a.x1[dof];
-            if (k >= G * N2) rowst[idx - G * N2 * NC] = a.rowptr[dof];   // psi rows, gamma rows
+        constexpr int NIT = (NCOEF * NC + JAC_THREADS - 1) / JAC_THREADS;
+        int dofs[NIT];
+        double xv[NIT], x1v[NIT];
+        int64_t rp[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {                 // all loads of the batch in flight together
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            dofs[it] = (idx < NCOEF * NC) ? dblk[idx] : 0;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            xv[it] = a.x[dofs[it]];
+            x1v[it] = a.x1[dofs[it]];
+            rp[it] = (idx >= G * N2 * NC) ? a.rowptr[dofs[it]] : 0;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            if (idx < NCOEF * NC) {
+                coef[idx] = xv[it];
+                coef1[idx] = x1v[it];
+                if (idx >= G * N2 * NC) rowst[idx - G * N2 * NC] = rp[it];   // psi rows, gamma rows
+            }
         }
     }
     __syncthreads();
@@ -445,10 +463,25 @@ __global__ void __launch_bounds__(SolidCfg<G>::WARPS * 32, SolidCfg<G>::CTAS) ja
     stage_cells<G, L>(a, scell, sgeo);
     {   // dofs_blk of a solid region: [2*G*N2][NC] = d dofs (trial columns) then v dofs (psi rows)
         const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * (2 * G * N2 * NC);
-        for (int idx = threadIdx.x; idx < 2 * G * N2 * NC; idx += JAC_THREADS) {
-            const int dof = dblk[idx];
-            if (idx < G * N2 * NC) coef[idx] = a.x[dof];
-            else rowst[idx - G * N2 * NC] = a.rowptr[dof];
+        constexpr int NIT = (2 * G * N2 * NC + JAC_THREADS - 1) / JAC_THREADS;
+        int dofs[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {                 // all loads of the batch in flight together
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            dofs[it] = (idx < 2 * G * N2 * NC) ? dblk[idx] : 0;
+        }
+        double xv[NIT];
+        int64_t rp[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            if (idx < G * N2 * NC) xv[it] = a.x[dofs[it]]; else rp[it] = a.rowptr[dofs[it]];
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = threadIdx.x + it * JAC_THREADS;
+            if (idx < G * N2 * NC) coef[idx] = xv[it];
+            else if (idx < 2 * G * N2 * NC) rowst[idx - G * N2 * NC] = rp[it];
         }
     }
     __syncthreads();
