@@ -37,7 +37,10 @@ constexpr int CELLS_PER_CTA = 32;
 // registers are allocated per 4 warps: 8 warps -> 255 regs/thread, 12 warps -> 168 (9..11 gain nothing)
 constexpr int JAC_WARPS = TFSI_JAC_WARPS;
 constexpr int JAC_THREADS = JAC_WARPS * 32;
-constexpr int RES_WARPS = 8;
+#ifndef TFSI_RES_WARPS
+#define TFSI_RES_WARPS 8
+#endif
+constexpr int RES_WARPS = TFSI_RES_WARPS;
 constexpr int RES_THREADS = RES_WARPS * 32;
 
 struct CellArgs {
