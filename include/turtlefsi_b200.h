@@ -106,6 +106,13 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
 int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1,
                            const double* Apre_vals, double* A_vals, void* stream);
 
+/* Fixed LINEAR facet terms of the forms as a sparse operator A_f in COO form (HOST or DEVICE arrays,
+ * duplicates are summed): the exterior-facet terms of the biharmonic lifting with
+ * "constrained_disp_vel" (turtleFSI/modules/biharmonic.py:38-41) — and any other term a problem file
+ * adds to F_*_linear that is linear in dvp_["n"]. Afterwards tfsi_assemble_A_pre adds A_f and
+ * tfsi_assemble_residual subtracts A_f x. Entries must lie inside the CSR pattern. n = 0 removes it. */
+int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n);
+
 /* Optional: register a COMPRESSED copy of A_pre (only its non-zero entries; the linear forms fill
  * ~15-20 % of the pattern). While `Apre_vals` passed to tfsi_assemble_jacobian is the pointer
  * registered here, "A := A_pre" streams A once from a position bitmap + the packed non-zeros instead of

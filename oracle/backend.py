@@ -29,6 +29,21 @@ class OracleAssembler:
         self.rowptr, self.colidx = self.pattern
         self.num_dofs, self.nnz = space.num_dofs, len(self.colidx)
         self.bc_dofs = np.zeros(0, dtype=np.int32)
+        self.facet_op = None
+
+    def set_facet_operator(self, rows, cols, vals):
+        """fixed linear facet terms (COO); added to A_pre, and b -= A_f x (biharmonic.py:38-41)."""
+        import scipy.sparse as sp
+        n = self.num_dofs
+        self.facet_op = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr() if len(vals) else None
+
+    def _facet_vals(self):
+        keys = oa._pattern_keys(self.rowptr, self.colidx, self.num_dofs)
+        M = self.facet_op.tocoo()
+        pos = np.searchsorted(keys, M.row.astype(np.int64) * self.num_dofs + M.col)
+        v = np.zeros(self.nnz)
+        np.add.at(v, pos, M.data)
+        return v
 
     def new_vector(self):
         return np.zeros(self.num_dofs)
@@ -58,6 +73,8 @@ class OracleAssembler:
 
     def assemble_A_pre(self, x, x1, out=None):
         v = self._c_matrix(x, x1, "lin") if self.use_c else oa.assemble_matrix(self.mesh, self.space, self.regions, self.common, x, x1, "lin", self.degJ, self.pattern)
+        if self.facet_op is not None:
+            v = v + self._facet_vals()
         if out is not None:
             out[:] = v
             return out
@@ -82,6 +99,8 @@ class OracleAssembler:
                                     gravity=float(self.common.get("gravity") or 0.0))
         else:
             b = oa.assemble_vector(self.mesh, self.space, self.regions, self.common, x, x1, self.degR)
+        if self.facet_op is not None:
+            b = b - self.facet_op @ np.asarray(x)
         if out is not None:
             out[:] = b
             return out

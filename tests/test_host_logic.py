@@ -90,3 +90,25 @@ def test_no_cpu_fallback_without_gpu():
     L = lib.load()
     tf, ms = C.c_double(), C.c_double()
     assert L.tfsi_probe_fp64_peak(C.byref(tf), C.byref(ms)) != 0
+
+
+def test_biharmonic_facet_operator_matches_oracle():
+    """product facet operator (Gauss rules) vs the oracle's (Simpson / degree-6 rule), 2-D and 3-D"""
+    import scipy.sparse as sp
+    from oracle.facets import biharmonic_facet_matrix
+    from turtlefsi_b200.boundary import Facets, biharmonic_facet_operator
+    for mesh in (square_mesh(5), tube_mesh(3)):
+        space = MixedSpace(mesh, biharmonic=True)
+        facets = Facets(mesh)
+        facets.mark(lambda x, on: on & (x[:, 0] < 0.3), 7)
+        facets.mark(lambda x, on: on & (x[:, 0] > 0.7), 9)
+        r, c, v = biharmonic_facet_operator(mesh, space, facets, [7, 9])
+        sel = np.nonzero(np.isin(facets.markers, [7, 9]) & facets.on_boundary)[0]
+        assert len(sel) > 0
+        r0, c0, v0 = biharmonic_facet_matrix(mesh, space, facets.vertices[sel], facets.cell0[sel], facets.local0[sel])
+        n = space.num_dofs
+        A = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        B = sp.coo_matrix((v0, (r0, c0)), shape=(n, n)).tocsr()
+        assert abs(A - B).max() < 1e-14 * abs(B).max()
+        # antisymmetric coupling: rows(w) x cols(d) = - rows(d) x cols(w) transposed positions
+        assert abs(A).sum() > 0

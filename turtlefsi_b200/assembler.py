@@ -161,6 +161,13 @@ class FSIAssembler:
         self._check(self.lib.tfsi_assemble_A_pre(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
         return out
 
+    def set_facet_operator(self, rows, cols, vals):
+        """fixed linear facet terms as a COO operator (turtlefsi_b200.boundary.biharmonic_facet_operator)."""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        self._check(self.lib.tfsi_set_facet_operator(self.h, _ptr(r), _ptr(c), _ptr(v), len(v)))
+
     def compress_A_pre(self, A_pre):
         """register the non-zeros of A_pre so that A := A_pre costs a zero-fill + sparse overwrite."""
         self._check(self.lib.tfsi_compress_A_pre(self.h, _ptr(A_pre), self._stream()))

@@ -178,6 +178,61 @@ def surface_traction(mesh, space, facets, x, mu_f, facet_ids, npts=6):
     return total
 
 
+def biharmonic_facet_operator(mesh, space, facets, bc_ids, alpha_u=0.01):
+    """COO triplets (rows, cols, vals) of the exterior-facet terms of the biharmonic lifting with
+    `extrapolation_sub_type="constrained_disp_vel"` (turtleFSI/modules/biharmonic.py:38-41):
+        F_ext1 += alpha_u (grad(d) n) . beta  ds(i)        rows: w-test (beta), cols: d
+        F_ext2 -= alpha_u (grad(w) n) . phi   ds(i)        rows: d-test (phi),  cols: w
+    for i in bc_ids. Both are LINEAR, so they are a fixed sparse operator A_f: it is added to A_pre
+    and b -= A_f x is added to the residual (tfsi_set_facet_operator). Facet quadrature:
+    Gauss-Legendre (2-D) / the degree-4 triangle rule (3-D): exact for the P2 x P1 integrand."""
+    from .quadrature import default_rule
+    g = mesh.gdim
+    n2 = space.n2
+    ow = 2 * g * n2 + g + 1
+    if g == 2:
+        s, w = _gauss_legendre_01(3)
+        fpts = np.stack([1.0 - s, s], axis=1)                 # barycentric on the facet
+        fw = w
+    else:
+        P, W = default_rule(2, 4)
+        fpts = np.concatenate([1.0 - P.sum(axis=1, keepdims=True), P], axis=1)
+        fw = W * 2.0                                          # weights sum to 1 (fraction of the facet area)
+    ref_vertices = np.vstack([np.zeros(g), np.eye(g)])
+    rows, cols, vals = [], [], []
+    sel = np.nonzero(np.isin(facets.markers, list(bc_ids)) & facets.on_boundary)[0]
+    for f in sel:
+        c, k = facets.cell0[f], facets.local0[f]
+        vloc = [v for v in range(g + 1) if v != k]
+        X = mesh.coords[mesh.cells[c]]
+        K = np.linalg.inv((X[1:] - X[0]).T)
+        if g == 2:
+            t = X[vloc[1]] - X[vloc[0]]
+            meas = np.linalg.norm(t)
+            nrm = np.array([t[1], -t[0]]) / meas
+        else:
+            cr = np.cross(X[vloc[1]] - X[vloc[0]], X[vloc[2]] - X[vloc[0]])
+            meas = 0.5 * np.linalg.norm(cr)
+            nrm = cr / np.linalg.norm(cr)
+        if np.dot(nrm, X[k] - X[vloc[0]]) > 0:
+            nrm = -nrm
+        pts = fpts @ ref_vertices[vloc]
+        phi2, dphi2, _ = tabulate(g, pts)
+        dn = np.einsum('qik,kb,b->qi', dphi2, K, nrm)          # d phi_j / d n
+        M = alpha_u * meas * np.einsum('q,qi,qj->ij', fw, phi2, dn)   # M[i, j] = int phi_i dn(phi_j)
+        dofs = space.cell_dofs[c]
+        for a in range(g):
+            wd = dofs[ow + a * n2: ow + (a + 1) * n2]
+            dd = dofs[a * n2:(a + 1) * n2]
+            rows += [np.repeat(wd, n2), np.repeat(dd, n2)]
+            cols += [np.tile(dd, n2), np.tile(wd, n2)]
+            vals += [M.ravel(), -M.ravel()]
+    if not rows:
+        z = np.zeros(0)
+        return z.astype(np.int32), z.astype(np.int32), z
+    return (np.concatenate(rows).astype(np.int32), np.concatenate(cols).astype(np.int32), np.concatenate(vals))
+
+
 def point_eval(mesh, space, x, point, field=0):
     """value of P2 vector field `field` at a point (first containing cell, as DOLFIN's bounding-box
     tree returns one of the colliding cells; the field is continuous)."""

@@ -64,6 +64,8 @@ struct tfsi_handle {
     int64_t launches;
     int sm_count;
     int profiling;
+    // fixed linear facet operator (tfsi_set_facet_operator)
+    int32_t *fo_rows, *fo_cols; int64_t* fo_pos; double* fo_vals; int64_t fo_n;
     // compressed copy of A_pre (tfsi_compress_A_pre)
     const double* cpre_src;
     uint32_t* cpre_bitmap; int64_t* cpre_base; double* cpre_val; int64_t cpre_nnz, cpre_words;
@@ -307,6 +309,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs); cudaFree(h->colidx);
     cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
+    cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -336,6 +339,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->hx = h->hx1 = h->hb = h->hg = nullptr;
     h->nbc = 0; h->launches = 0; h->profiling = 0;
     h->copy_stream = nullptr; h->ev_begin = nullptr; h->n_ev = 0;
+    h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
@@ -493,7 +497,13 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(Apre, 0, (size_t)h->nnz * sizeof(double), st));
-    return h->gdim == 3 ? launch_linear<3>(h, x, x1, Apre, st) : launch_linear<2>(h, x, x1, Apre, st);
+    if (int rc = (h->gdim == 3 ? launch_linear<3>(h, x, x1, Apre, st) : launch_linear<2>(h, x, x1, Apre, st))) return rc;
+    if (h->fo_n) {
+        coo_add_matrix_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_pos, h->fo_vals, h->fo_n, Apre);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
 }
 
 int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, void* stream) {
@@ -501,6 +511,25 @@ int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, co
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     return launch_jacobian(h, x, x1, Apre, A, st);
+}
+
+int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n) {
+    if (!h || n < 0 || (n && (!rows || !cols || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
+    h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
+    if (n == 0) return 0;
+    if (int rc = upload(h, &h->fo_rows, rows, (size_t)n)) return rc;
+    if (int rc = upload(h, &h->fo_cols, cols, (size_t)n)) return rc;
+    if (int rc = upload(h, &h->fo_vals, vals, (size_t)n)) return rc;
+    CK(h, cudaMalloc((void**)&h->fo_pos, (size_t)n * sizeof(int64_t)));
+    int* derr = reinterpret_cast<int*>(h->scratch + 1);
+    CK(h, cudaMemset(derr, 0, sizeof(int)));
+    coo_positions_kernel<<<grid_for(n, 256, h->sm_count), 256>>>(h->fo_rows, h->fo_cols, n, h->rowptr, h->colidx, h->fo_pos, derr);
+    int herr = 0;
+    CK(h, cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return fail(h, TFSI_ERR_PATTERN, "%d facet-operator entries are outside the CSR pattern", herr);
+    h->fo_n = n;
+    return 0;
 }
 
 int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
@@ -543,7 +572,13 @@ int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, do
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(b, 0, (size_t)h->N * sizeof(double), st));
-    return launch_residual(h, x, x1, b, st);
+    if (int rc = launch_residual(h, x, x1, b, st)) return rc;
+    if (h->fo_n) {
+        coo_sub_matvec_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_rows, h->fo_cols, h->fo_vals, h->fo_n, x, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
 }
 
 int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {

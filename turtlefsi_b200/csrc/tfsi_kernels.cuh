@@ -941,6 +941,28 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
     }
 }
 
+// ---- fixed linear facet operator (COO): A_pre += A_f ; b -= A_f x  (biharmonic.py:38-41 ds terms)
+__global__ void coo_positions_kernel(const int32_t* rows, const int32_t* cols, int64_t n, const int64_t* rowptr,
+                                     const int32_t* colidx, int64_t* pos, int* err)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lo = rowptr[rows[i]], hi = rowptr[rows[i] + 1];
+        const int64_t p = find_col(colidx, lo, hi, cols[i]);
+        if (p >= hi || colidx[p] != cols[i]) { atomicAdd(err, 1); pos[i] = lo; } else pos[i] = p;
+    }
+}
+__global__ void coo_add_matrix_kernel(const int64_t* pos, const double* vals, int64_t n, double* A)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(A + pos[i], vals[i]);
+}
+__global__ void coo_sub_matvec_kernel(const int32_t* rows, const int32_t* cols, const double* vals, int64_t n,
+                                      const double* x, double* b)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(b + rows[i], -vals[i] * x[cols[i]]);
+}
+
 // dof-level CSR columns from the P2-node adjacency (node-interleaved numbering): one thread per
 // node-adjacency entry (I, J); writes the ncomp[I] x ncomp[J] block of column indices.
 __global__ void expand_node_pattern_kernel(int64_t num_nodes, const int64_t* nrowptr, const int32_t* ncol,

@@ -60,6 +60,9 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
         ns.update(getattr(m, fn)(**ns))
     assembler = make_assembler(mesh, DVP, ns["regions"], ns)
     ns["assembler"] = assembler
+    ext_mod = importlib.import_module("turtlefsi_b200.modules." + ns["extrapolation"])
+    if hasattr(ext_mod, "facet_terms"):                                                              # biharmonic.py:38-41
+        ext_mod.facet_terms(**ns)
     dvp_ = {k: assembler.new_vector() for k in ("n-2", "n-1", "n")}                                   # :95-111
     ns["dvp_"] = dvp_
     ns["up_sol"] = make_solver(assembler)                                                             # :136
