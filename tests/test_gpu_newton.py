@@ -121,3 +121,41 @@ def test_tube3d_newton_matches_oracle():
     assert np.allclose(np.array(ns["probe_v"]), np.array(ref["probe_v"]), rtol=1e-8, atol=1e-14)
     assert np.allclose(np.array(ns["probe_d"]), np.array(ref["probe_d"]), rtol=1e-7, atol=1e-16)
     assert abs(np.array(ns["probe_v"])[-1, 2]) > 1e-4          # the flow actually moves
+
+
+def test_turtle_demo_two_steps_match_oracle():
+    """BASELINE config 3 (the reference's default problem): turtle_demo, biharmonic "constrained_disp",
+    Jacobian re-used (recompute = 15) — CUDA path vs the ORACLE driven by the same problem file."""
+    from oracle.backend import OracleAssembler
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.linear_solver import HostLU
+
+    def make_oracle(mesh, space, regions, ns):
+        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
+                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
+                      gravity=ns["gravity"])
+        return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"], 10,
+                               use_c_port=True)
+    ref = monolithic.run("turtle_demo", make_oracle, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs),
+                         overrides=dict(verbose=False), max_steps=2)
+    from turtlefsi_b200.assembler import FSIAssembler
+
+    def make_gpu(mesh, space, regions, ns):
+        return FSIAssembler(mesh, space, regions, ns["dt"], ns["theta"], fluid=ns["fluid"], solid=ns["solid"],
+                            extrapolation=ns["extrapolation"], extrapolation_sub_type=ns["extrapolation_sub_type"],
+                            quad_degree_jacobian=ns["compiler_parameters"]["quadrature_degree"], quad_degree_residual=10)
+    ns = monolithic.run("turtle_demo", make_gpu,
+                        lambda a: HostLU(a.rowptr.cpu().numpy(), a.colidx.cpu().numpy(), a.num_dofs),
+                        overrides=dict(verbose=False), max_steps=2)
+    assert ns["DVP"].num_dofs == 83012                                   # SURVEY 8a
+    assert len(ns["residual_history"]) == len(ref["residual_history"])
+    rmax = max(h[2] for h in ref["residual_history"])
+    for (c, i, r, rr), (c0, i0, r0, rr0) in zip(ns["residual_history"], ref["residual_history"]):
+        assert (c, i) == (c0, i0)
+        if r0 > 1e-4 * rmax:
+            assert abs(r / r0 - 1) < 1e-8
+    x, x0 = ns["dvp_"]["n"].cpu().numpy(), ref["dvp_"]["n"]
+    sp = ns["DVP"]
+    for field in (0, 1, 2, 3):
+        d = sp.sub_dofs(field)
+        assert np.linalg.norm(x[d] - x0[d]) < 1e-8 * np.linalg.norm(x0[d]), field

@@ -73,6 +73,29 @@ def read_dolfin_xml(path):
     return Mesh(coords, cells, np.zeros(len(cl), dtype=np.int32))
 
 
+def read_turtle_demo(folder):
+    """The default problem's mesh (turtleFSI/mesh/turtle_demo/{mc,mf}.h5, read by
+    turtleFSI/problems/turtle_demo.py:58-87 through DOLFIN's XDMFFile [dep]). h5py is not available;
+    the files are plain HDF5 with contiguous, uncompressed datasets whose byte offsets are fixed
+    (SURVEY Appendix C): mc.h5 = coordinates f8[3350,2] @2048, triangles i8[6578,3] @55648, cell markers
+    i8[6578] @213520; mf.h5 = marked facets i8[137,2] @55648 and their markers i8[137] @57840.
+    Returns (Mesh, facet_vertices [137, 2], facet_markers [137])."""
+    import os
+    mc = open(os.path.join(folder, "mc.h5"), "rb").read()
+    mf = open(os.path.join(folder, "mf.h5"), "rb").read()
+    if mc[:8] != b"\x89HDF\r\n\x1a\n" or len(mc) != 266144 or len(mf) != 58936:
+        raise RuntimeError("unexpected turtle_demo mesh files")
+    coords = np.frombuffer(mc, dtype="<f8", count=3350 * 2, offset=2048).reshape(3350, 2).copy()
+    cells = np.frombuffer(mc, dtype="<i8", count=6578 * 3, offset=55648).reshape(6578, 3).astype(np.int32)
+    markers = np.frombuffer(mc, dtype="<i8", count=6578, offset=213520).astype(np.int32)
+    fverts = np.frombuffer(mf, dtype="<i8", count=137 * 2, offset=55648).reshape(137, 2).astype(np.int64)
+    fmark = np.frombuffer(mf, dtype="<i8", count=137, offset=57840).astype(np.int64)
+    assert cells.min() == 0 and cells.max() == 3349 and set(np.unique(markers)) == {1, 2}
+    assert fverts.max() < 3350 and set(np.unique(fmark)) <= {11, 12, 13, 14, 15}
+    cells = np.sort(cells, axis=1)
+    return Mesh(coords, cells, markers.copy(), meta=dict(kind="turtle_demo")), fverts, fmark
+
+
 def refine(mesh):
     """Uniform refinement of a triangle mesh as DOLFIN's `refine(mesh)` does it (PlazaRefinementND,
     [dep] DOLFIN 2019.1, used by turtleFSI/problems/TF_cfd.py:49 and TF_csm.py:54): a triangle whose
