@@ -230,3 +230,42 @@ def test_facet_operator_in_A_pre_and_residual(gdim, tube_params):
     assert np.abs(ref_pre - base.assemble_A_pre(x, x1)).max() > 0           # the term is really there
     assert _row_rel_err(A_pre, ref_pre, pattern[0]) < TOL
     assert np.abs(b - ref_b).max() < TOL * np.abs(ref_b).max()
+
+
+def test_abi_error_behaviour(tube_params):
+    """the boundary fails loudly: a pattern that is not DOLFIN's dense-cell-block union, unsupported
+    forms, oversized quadrature rules and null pointers give error codes + messages, never a silent path"""
+    import ctypes as C
+    import torch
+    from turtlefsi_b200 import lib as L
+    from turtlefsi_b200.assembler import FSIAssembler
+    common, regions = tube_params
+    mesh, space, x, x1 = _setup(3, False, 3)
+    rp, ci = space.pattern()
+    # (a) drop one off-diagonal entry from the pattern
+    k = int(rp[5]) + 1
+    rp2 = rp.copy()
+    rp2[6:] -= 1
+    ci2 = np.delete(ci, k)
+    with pytest.raises(RuntimeError, match="CSR pattern"):
+        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], pattern=(rp2, ci2))
+    # (b) forms outside the kernels' scope are refused, not approximated
+    with pytest.raises(RuntimeError, match="not available on the B200 path"):
+        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="elastic", pattern=(rp, ci))
+    with pytest.raises(RuntimeError, match="Could not find extrapolation method"):
+        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="laplace",
+                     extrapolation_sub_type="volume_change", pattern=(rp, ci))
+    # (c) a 15-point Jacobian rule does not fit the shared-memory budget in 3-D: error at assembly
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], quad_degree_jacobian=5, pattern=(rp, ci))
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    with pytest.raises(RuntimeError, match="shared memory"):
+        asm.assemble_jacobian(xd, x1d, None)
+    # (d) null pointers
+    lib = L.load()
+    assert lib.tfsi_assemble_residual(asm.h, None, None, None, None) == -1
+    assert b"null" in lib.tfsi_last_error(asm.h)
+    assert lib.tfsi_create(None, None) == -1
+    # (e) facet-operator entries outside the pattern
+    far = np.array([0], dtype=np.int32), np.array([space.num_dofs - 1], dtype=np.int32), np.array([1.0])
+    with pytest.raises(RuntimeError, match="outside the CSR pattern"):
+        asm.set_facet_operator(*far)
