@@ -146,7 +146,8 @@ int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out_sumsq, vo
 /* Host-buffer variants (reference-facing end-to-end call): x, x1 HOST [N]; b_host HOST [N];
  * A_vals stays on the device (consumer is the device sparse LU).  Includes H2D of x, x1, the
  * Jacobian (+A_pre, ident_zeros, BC rows) and residual (+BC) assembly, and D2H of b.
- * g_host: BC values [nbc] or NULL. Synchronous. */
+ * g_host: BC values [nbc] or NULL. Synchronous: ordered after the work queued on the legacy default
+ * stream, runs on two internal streams (copies under kernels), returns when b_host and A_vals are final. */
 int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host,
                               const double* g_host, const double* Apre_vals, double* A_vals,
                               double* b_host, double* out_sumsq_b, int32_t recompute_jacobian);

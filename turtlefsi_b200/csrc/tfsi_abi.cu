@@ -55,7 +55,8 @@ struct tfsi_handle {
     int64_t nbc;
     std::vector<Region> regions;
     std::vector<Segment> segments;
-    cudaStream_t copy_stream;
+    cudaStream_t copy_stream, main_stream;   // copy_stream: A_pre chunks / host-entry H2D+D2H; main_stream: host-entry kernels
+    cudaEvent_t ev_entry, ev_in, ev_b;
     cudaEvent_t ev_begin, ev_seg[2 * JAC_CHUNKS * 8];
     int n_ev;
     QuadTab<MAXQ_J> tabJ;
@@ -176,17 +177,23 @@ int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, 
     return 0;
 }
 
-// A := (A_pre | 0) + J_nl, initialisation pipelined with the segment kernels (see Segment)
-int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st) {
-    CK(h, cudaEventRecord(h->ev_begin, st));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_begin, 0));
+// A := (A_pre | 0) + J_nl, initialisation pipelined with the segment kernels (see Segment).
+// phase 0: everything; 1: only the x-independent initialisation A := A_pre; 2: only the cell kernels
+// (the host entry runs phase 1 under the H2D copy of x)
+int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st, int phase = 0) {
     const bool use_compressed = Apre && Apre == h->cpre_src && h->segments.size() <= h->regions.size();
-    if (use_compressed) {
+    if (use_compressed || phase != 0) {
         // A := A_pre as zero-fill + sparse overwrite (one kernel, whole matrix), then the cell kernels
-        bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
-            h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A);
-        h->launches++;
-        CK(h, cudaGetLastError());
+        if (phase != 2) {
+            if (use_compressed) {
+                bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
+                    h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A);
+                CK(h, cudaGetLastError());
+            } else if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            else CK(h, cudaMemsetAsync(A, 0, (size_t)h->nnz * sizeof(double), st));
+            h->launches++;
+        }
+        if (phase == 1) return 0;
         for (const Segment& sg : h->segments) {
             const Region& r = h->regions[sg.region];
             if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
@@ -195,6 +202,8 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const dou
         }
         return 0;
     }
+    CK(h, cudaEventRecord(h->ev_begin, st));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_begin, 0));
     auto init = [&](int64_t lo, int64_t hi) -> int {
         if (hi <= lo) return 0;
         if (Apre) CK(h, cudaMemcpyAsync(A + lo, Apre + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, h->copy_stream));
@@ -313,6 +322,10 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->main_stream) cudaStreamDestroy(h->main_stream);
+    if (h->ev_entry) cudaEventDestroy(h->ev_entry);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     for (int i = 0; i < h->n_ev; ++i) cudaEventDestroy(h->ev_seg[i]);
     if (g_tab_owner == h->id) g_tab_owner = 0;
@@ -338,7 +351,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
     h->hx = h->hx1 = h->hb = h->hg = nullptr;
     h->nbc = 0; h->launches = 0; h->profiling = 0;
-    h->copy_stream = nullptr; h->ev_begin = nullptr; h->n_ev = 0;
+    h->copy_stream = h->main_stream = nullptr; h->ev_begin = h->ev_entry = h->ev_in = h->ev_b = nullptr; h->n_ev = 0;
     h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
@@ -429,6 +442,10 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             }
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming);
+        cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming);
         h->n_ev = (int)h->segments.size() + 1;
         if (h->n_ev > 2 * JAC_CHUNKS * 8) { h->n_ev = 0; tfsi_destroy(h); return fail(nullptr, TFSI_ERR_UNSUPPORTED, "too many regions"); }
         for (int i = 0; i < h->n_ev; ++i) cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming);
@@ -583,7 +600,7 @@ int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, do
 
 int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {
     if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
-    ident_zeros_kernel<<<grid_for(h->N * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, A, h->N, 3.0e-16);
+    ident_zeros_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, A, h->N, 3.0e-16);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -642,22 +659,44 @@ int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out, void* st
 int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host, const double* g_host,
                               const double* Apre, double* A, double* b_host, double* out_sumsq_b, int32_t recompute) {
     if (!h || !x_host || !x1_host || !b_host) return fail(h, TFSI_ERR_ARG, "null argument");
-    cudaStream_t st = 0;
+    if (recompute && !A) return fail(h, TFSI_ERR_ARG, "null A");
+    // Two streams: `io` carries the host<->device copies, `st` the kernels. The x-independent A := A_pre
+    // runs under the H2D copy of x; the residual is assembled BEFORE the Jacobian so that its D2H copy
+    // and norm run under the Jacobian kernels. Both streams start after everything the caller has
+    // queued on the legacy default stream (A_pre, A are the caller's buffers).
+    cudaStream_t st = h->main_stream, io = h->copy_stream;
     const size_t nb = (size_t)h->N * sizeof(double);
-    CK(h, cudaMemcpyAsync(h->hx, x_host, nb, cudaMemcpyHostToDevice, st));
-    CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, st));
-    if (h->nbc && g_host) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, st));
+    const bool bcs = h->nbc && g_host;
+    CK(h, cudaEventRecord(h->ev_entry, 0));
+    CK(h, cudaStreamWaitEvent(st, h->ev_entry, 0));
+    CK(h, cudaStreamWaitEvent(io, h->ev_entry, 0));
+    CK(h, cudaMemcpyAsync(h->hx, x_host, nb, cudaMemcpyHostToDevice, io));
+    CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, io));
+    if (bcs) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, io));
+    CK(h, cudaEventRecord(h->ev_in, io));
     if (recompute) {
-        if (!A) return fail(h, TFSI_ERR_ARG, "null A");
-        if (int rc = tfsi_assemble_jacobian(h, h->hx, h->hx1, Apre, A, st)) return rc;
+        if (int rc = bind_tables(h, st)) return rc;
+        if (int rc = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 1)) return rc;
+    }
+    CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
+    if (int rc = tfsi_assemble_residual(h, h->hx, h->hx1, h->hb, st)) return rc;
+    if (bcs) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, st)) return rc;
+    CK(h, cudaEventRecord(h->ev_b, st));
+    CK(h, cudaStreamWaitEvent(io, h->ev_b, 0));
+    CK(h, cudaMemcpyAsync(b_host, h->hb, nb, cudaMemcpyDeviceToHost, io));
+    CK(h, cudaMemsetAsync(h->scratch, 0, sizeof(double), io));
+    sumsq_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, io>>>(h->hb, h->N, h->scratch);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (recompute) {
+        if (int rc = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 2)) return rc;
         if (int rc = tfsi_ident_zeros(h, A, st)) return rc;
         if (int rc = tfsi_apply_bc_matrix(h, A, st)) return rc;
     }
-    if (int rc = tfsi_assemble_residual(h, h->hx, h->hx1, h->hb, st)) return rc;
-    if (h->nbc && g_host) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, st)) return rc;
-    CK(h, cudaMemcpyAsync(b_host, h->hb, nb, cudaMemcpyDeviceToHost, st));
     double ss = 0;
-    if (int rc = tfsi_sumsq(h, h->hb, h->N, &ss, st)) return rc;
+    CK(h, cudaMemcpyAsync(&ss, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, io));
+    CK(h, cudaStreamSynchronize(io));
+    CK(h, cudaStreamSynchronize(st));
     if (out_sumsq_b) *out_sumsq_b = ss;
     return 0;
 }

@@ -796,19 +796,32 @@ __global__ void diagpos_kernel(const int64_t* rowptr, const int32_t* colidx, int
     }
 }
 
-// A.ident_zeros(): one warp per row
+// A.ident_zeros(): a row is "zero" when sum_j |a_ij| < eps (DOLFIN's GenericMatrix::ident_zeros). Since
+// |a_ii| <= sum_j |a_ij|, a row whose DIAGONAL is >= eps can be skipped without reading it: every lane
+// tests the diagonal of one row (one 32-byte sector), and the warp then sums, one after the other, only
+// the rows whose diagonal is tiny (the pressure rows inside the solid). Same result as summing every
+// row, ~N sectors of traffic instead of the whole matrix.
 __global__ void ident_zeros_kernel(const int64_t* rowptr, const int64_t* diagpos, double* A, int64_t n, double eps)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = wid; r < n; r += nw) {
-        const int64_t lo = rowptr[r], hi = rowptr[r + 1];
-        double s = 0;
-        for (int64_t k = lo + lane; k < hi; k += 32) s += fabs(A[k]);
+    for (int64_t r0 = wid * 32; r0 < n; r0 += nw * 32) {
+        const int64_t r = r0 + lane;
+        bool cand = false;
+        if (r < n) cand = !(fabs(A[diagpos[r]]) >= eps);
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t rr = r0 + src;
+            const int64_t lo = rowptr[rr], hi = rowptr[rr + 1];
+            double s = 0;
+            for (int64_t k = lo + lane; k < hi; k += 32) s += fabs(A[k]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && s < eps) A[diagpos[r]] = 1.0;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && s < eps) A[diagpos[rr]] = 1.0;
+        }
     }
 }
 
