@@ -113,6 +113,20 @@ int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1,
  * tfsi_assemble_residual subtracts A_f x. Entries must lie inside the CSR pattern. n = 0 removes it. */
 int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n);
 
+/* The same for linear facet terms that act on the PREVIOUS time level dvp_["n-1"], e.g. the explicit
+ * half of the Robin condition  theta1 (k_s d^{n-1} + c_s v^{n-1}).psi ds_s   (turtleFSI/modules/solid.py:84;
+ * its implicit half :83 goes to tfsi_set_facet_operator). No Jacobian contribution:
+ * tfsi_assemble_residual subtracts A_p x1. HOST arrays, indices range-checked. n = 0 removes it. */
+int tfsi_set_facet_operator_prev(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n);
+
+/* State-independent facet load added to F_solid_linear by a problem file, e.g. the interior-facet
+ * pressure  p(t) n('+').psi('+') dS(fsi_id)  (problems/Test_Cylinder/problem_aneu.py:212-214,
+ * problems/Stenosis_2D.py:172-174): a sparse vector l (HOST arrays dofs/vals, duplicates summed) and a
+ * scalar that the caller updates per time step (pre_solve: p_out_bc_val.t = t);
+ * tfsi_assemble_residual subtracts scale * l. Default scale 1. n = 0 removes the load. */
+int tfsi_set_facet_load(tfsi_handle* h, const int32_t* dofs, const double* vals, int64_t n);
+int tfsi_set_facet_load_scale(tfsi_handle* h, double scale);
+
 /* Optional: register a COMPRESSED copy of A_pre (only its non-zero entries; the linear forms fill
  * ~15-20 % of the pattern). While `Apre_vals` passed to tfsi_assemble_jacobian is the pointer
  * registered here, "A := A_pre" streams A once from a position bitmap + the packed non-zeros instead of

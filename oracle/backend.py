@@ -30,12 +30,29 @@ class OracleAssembler:
         self.num_dofs, self.nnz = space.num_dofs, len(self.colidx)
         self.bc_dofs = np.zeros(0, dtype=np.int32)
         self.facet_op = None
+        self.facet_op_prev = None
+        self.facet_load, self.facet_load_scale = None, 1.0
 
     def set_facet_operator(self, rows, cols, vals):
         """fixed linear facet terms (COO); added to A_pre, and b -= A_f x (biharmonic.py:38-41)."""
         import scipy.sparse as sp
         n = self.num_dofs
         self.facet_op = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr() if len(vals) else None
+
+    def set_facet_operator_prev(self, rows, cols, vals):
+        """linear facet terms on the previous time level (solid.py:84): b -= A_p x1."""
+        import scipy.sparse as sp
+        n = self.num_dofs
+        self.facet_op_prev = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr() if len(vals) else None
+
+    def set_facet_load(self, dofs, vals, scale=1.0):
+        """state-independent facet load (problem_aneu.py:214): b -= scale * l."""
+        l = np.zeros(self.num_dofs)
+        np.add.at(l, np.asarray(dofs, dtype=np.int64), vals)
+        self.facet_load, self.facet_load_scale = (l if len(vals) else None), float(scale)
+
+    def set_facet_load_scale(self, scale):
+        self.facet_load_scale = float(scale)
 
     def _facet_vals(self):
         keys = oa._pattern_keys(self.rowptr, self.colidx, self.num_dofs)
@@ -101,6 +118,10 @@ class OracleAssembler:
             b = oa.assemble_vector(self.mesh, self.space, self.regions, self.common, x, x1, self.degR)
         if self.facet_op is not None:
             b = b - self.facet_op @ np.asarray(x)
+        if self.facet_op_prev is not None:
+            b = b - self.facet_op_prev @ np.asarray(x1)
+        if self.facet_load is not None:
+            b = b - self.facet_load_scale * self.facet_load
         if out is not None:
             out[:] = b
             return out

@@ -159,3 +159,37 @@ def test_turtle_demo_two_steps_match_oracle():
     for field in (0, 1, 2, 3):
         d = sp.sub_dofs(field)
         assert np.linalg.norm(x[d] - x0[d]) < 1e-8 * np.linalg.norm(x0[d]), field
+
+
+def test_taylor_green_matches_oracle_and_the_analytic_solution():
+    """TaylorGreen2D (the reference's DOLFIN-free known answer): CUDA path vs the oracle run of the same
+    problem file, and the error against the analytic solution."""
+    from tests.test_turek_pin import _run_oracle
+    ov = dict(N=16, T=0.1, dt=0.01)
+    ref = _run_oracle("TaylorGreen2D", ov)
+    ns = _run_gpu("TaylorGreen2D", **ov)
+    assert len(ns["residual_history"]) == len(ref["residual_history"])
+    assert np.allclose(ns["error_v_list"], ref["error_v_list"], rtol=1e-8, atol=0)
+    assert np.allclose(ns["error_p_list"], ref["error_p_list"], rtol=1e-8, atol=0)
+    assert ns["error_v_list"][-1] < 5e-3 and ns["error_p_list"][-1] < 7e-2
+
+
+def test_robin_validation_and_inner_pressure_match_oracle():
+    """8f-1 facet terms end to end: RobinBC_validation (solid only, Robin wall, gravity) and the 3-D tube with
+    the interior-facet pressure load of problem_aneu.py:212-214 — CUDA path vs oracle, same problem files."""
+    from tests.test_known_answers import STIFF, _oracle_run
+    ov = dict(dt=0.005, T=0.02, ncube=3, **STIFF)
+    ref = _oracle_run("RobinBC_validation", **ov)
+    ns = _run_gpu("RobinBC_validation", **ov)
+    assert len(ns["residual_history"]) == len(ref["residual_history"])
+    assert np.allclose(ns["d_list"], ref["d_list"], rtol=1e-8, atol=0)
+    a = ns["default_variables"]["analytical_displacement"]
+    assert np.abs(np.array(ns["d_list"]) - a).max() < 2e-3 * np.abs(a).max()      # the ODE itself
+    ov = dict(T=0.003, dt=0.001, ncube=3, inner_pressure=True)
+    ref = _oracle_run("tube3d", **ov)
+    ns = _run_gpu("tube3d", **ov)
+    base = _run_gpu("tube3d", **dict(ov, inner_pressure=False))
+    assert len(ns["residual_history"]) == len(ref["residual_history"])
+    assert np.allclose(np.array(ns["probe_v"]), np.array(ref["probe_v"]), rtol=1e-7, atol=1e-12)
+    assert np.allclose(np.array(ns["probe_d"]), np.array(ref["probe_d"]), rtol=1e-6, atol=1e-14)
+    assert np.abs(np.array(ns["probe_d"])[-1] - np.array(base["probe_d"])[-1]).max() > 1e-8   # the load acts

@@ -232,6 +232,68 @@ def test_facet_operator_in_A_pre_and_residual(gdim, tube_params):
     assert np.abs(b - ref_b).max() < TOL * np.abs(ref_b).max()
 
 
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_robin_and_pressure_load_facet_terms(gdim, tube_params):
+    """Robin ds_s terms (solid.py:83-84: implicit half -> A_pre and b, explicit half -> b only) and the
+    interior-facet load p(t) n('+').psi('+') dS (problem_aneu.py:214) through the C-ABI
+    (tfsi_set_facet_operator[_prev], tfsi_set_facet_load[_scale]) against the oracle's closed-form facet
+    matrices."""
+    import torch
+    from oracle.backend import OracleAssembler
+    from oracle.facets import normal_load, robin_matrices
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.boundary import Facets, interior_facet_normal_load, robin_facet_operators
+    common, regions = tube_params
+    mesh, space, x, x1 = _setup(gdim, False, 3 if gdim == 3 else 6)
+    facets = Facets(mesh)
+    solid_facet = facets.on_boundary & (mesh.markers[facets.cell0] == 2)
+    facets.markers[solid_facet] = 33                                           # Robin wall: boundary facets of solid cells
+    interface = ~facets.on_boundary & (mesh.markers[facets.cell0] != mesh.markers[np.maximum(facets.cell1, 0)])
+    facets.markers[interface] = 22                                             # fsi_id
+    assert solid_facet.sum() > 0 and interface.sum() > 0
+    degJ, degR = (4, 6) if gdim == 3 else (5, 10)
+    pattern = space.pattern()
+    k_s, c_s, p_t = [1.0e5], [1.0e2], 1.3e4
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"],
+                       quad_degree_jacobian=degJ, quad_degree_residual=degR, pattern=pattern)
+    now, prev = robin_facet_operators(mesh, space, facets, [33], k_s, c_s, common["theta"])
+    asm.set_facet_operator(*now)
+    asm.set_facet_operator_prev(*prev)
+    asm.set_facet_load(*interior_facet_normal_load(mesh, space, facets, 22))
+    asm.set_facet_load_scale(p_t)
+    # oracle: closed-form facet mass matrices; "+" = the solid cell (higher marker)
+    ora = OracleAssembler(mesh, space, regions, common, degJ, degR, pattern=pattern, use_c_port=True)
+    sel = np.nonzero(solid_facet)[0]
+    onow, oprev = robin_matrices(mesh, space, facets.cell0[sel], facets.local0[sel], k_s[0], c_s[0], common["theta"])
+    ora.facet_op, ora.facet_op_prev = onow, oprev
+    fi = np.nonzero(interface)[0]
+    plus_is_1 = mesh.markers[facets.cell1[fi]] > mesh.markers[facets.cell0[fi]]
+    pc = np.where(plus_is_1, facets.cell1[fi], facets.cell0[fi])
+    pl = np.where(plus_is_1, facets.local1[fi], facets.local0[fi])
+    assert (mesh.markers[pc] == 2).all()
+    ora.facet_load, ora.facet_load_scale = normal_load(mesh, space, pc, pl), p_t
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    A_pre = asm.assemble_A_pre(xd, x1d).cpu().numpy()
+    b = asm.assemble_residual(xd, x1d).cpu().numpy()
+    ref_pre, ref_b = ora.assemble_A_pre(x, x1), ora.assemble_residual(x, x1)
+    base = OracleAssembler(mesh, space, regions, common, degJ, degR, pattern=pattern, use_c_port=True)
+    base_b = base.assemble_residual(x, x1)
+    assert np.abs(ref_pre - base.assemble_A_pre(x, x1)).max() > 0 and np.abs(ref_b - base_b).max() > 1e-6 * np.abs(base_b).max()
+    assert _row_rel_err(A_pre, ref_pre, pattern[0]) < TOL
+    assert np.abs(b - ref_b).max() < TOL * np.abs(ref_b).max()
+    # the load follows the scalar the problem file updates per step, and n = 0 removes the terms again
+    asm.set_facet_load_scale(0.0)
+    ora.facet_load_scale = 0.0
+    assert np.abs(asm.assemble_residual(xd, x1d).cpu().numpy() - ora.assemble_residual(x, x1)).max() < TOL * np.abs(ref_b).max()
+    z = np.zeros(0)
+    asm.set_facet_operator(z, z, z)
+    asm.set_facet_operator_prev(z, z, z)
+    asm.set_facet_load(z, z)
+    assert np.abs(asm.assemble_residual(xd, x1d).cpu().numpy() - base_b).max() < TOL * np.abs(base_b).max()
+    with pytest.raises(RuntimeError, match="out of range"):
+        asm.set_facet_load(np.array([space.num_dofs]), np.array([1.0]))
+
+
 def test_abi_error_behaviour(tube_params):
     """the boundary fails loudly: a pattern that is not DOLFIN's dense-cell-block union, unsupported
     forms, oversized quadrature rules and null pointers give error codes + messages, never a silent path"""

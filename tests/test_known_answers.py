@@ -1,0 +1,131 @@
+"""DOLFIN-free KNOWN ANSWERS the reference itself ships (SURVEY 8c "Additional known answers"):
+the Taylor-Green vortex (turtleFSI/problems/TaylorGreen2D.py: analytic u, p :134-155) driven through
+the ORACLE and the reference's Newton loop. The discrete solution converges to the analytic one at
+the Taylor-Hood rates, which pins the fluid forms N1-N5 (fluid.py:32-52), the theta scheme and the
+time-dependent Dirichlet data independently of any FEniCS output."""
+import numpy as np
+
+
+def _run(N, **over):
+    from tests.test_turek_pin import _run_oracle
+    ov = dict(N=N, T=0.1, dt=0.01)
+    ov.update(over)
+    return _run_oracle("TaylorGreen2D", ov)
+
+
+def test_rectangle_mesh_is_dolfins():
+    from turtlefsi_b200.mesh import rectangle_mesh
+    m = rectangle_mesh((-1, -1), (1, 1), 3, 2, "right")
+    assert m.num_vertices == 12 and m.num_cells == 12
+    assert np.allclose(m.coords[5], (-1 + 2 / 3, 0.0))                  # vertex iy*(nx+1)+ix
+    assert m.cells[:2].tolist() == [[0, 1, 5], [0, 4, 5]]               # "right": (v0,v1,v3),(v0,v2,v3)
+    left = rectangle_mesh((-1, -1), (1, 1), 3, 2, "left")
+    assert left.cells[:2].tolist() == [[0, 1, 4], [1, 4, 5]]
+    X = m.coords[m.cells]
+    area = 0.5 * np.abs(np.linalg.det(np.swapaxes(X[:, 1:] - X[:, :1], 1, 2))).sum()
+    assert abs(area - 4.0) < 1e-14
+
+
+def test_taylor_green_converges_to_the_analytic_solution():
+    a, b = _run(8), _run(16)
+    ev = (a["error_v_list"][-1], b["error_v_list"][-1])
+    ep = (a["error_p_list"][-1], b["error_p_list"][-1])
+    # P2 velocity against its interpolant: better than third order; P1 pressure: second order
+    assert ev[1] < 5e-3 and ev[0] / ev[1] > 8.0
+    assert ep[1] < 7e-2 and ep[0] / ep[1] > 3.5
+    # the pressure is pinned at the corner to the analytic value (pointwise BC)
+    sp, mesh = b["DVP"], b["mesh"]
+    corner = np.nonzero((np.abs(mesh.coords - 1.0) < 1e-14).all(axis=1))[0]
+    x = b["dvp_"]["n"]
+    assert np.allclose(x[sp.vertex_dof_p()[corner]], b["p_bc_val"](mesh.coords[corner]), rtol=0, atol=1e-14)
+    # no mesh motion: the d rows are ident_zeros rows and d stays 0
+    assert np.abs(x[sp.sub_dofs(0)]).max() == 0.0
+    # Jacobian re-used over the whole run (recompute = recompute_tstep = 100): Newton still converges
+    assert all(h[1] < 10 for h in b["residual_history"])
+    assert b["total_error_v"] > 0 and abs(b["total_error_v"] - 0.01 * sum(b["error_v_list"])) < 1e-15
+
+
+def _oracle_run(problem, **over):
+    from oracle.backend import OracleAssembler
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.linear_solver import HostLU
+
+    def make_oracle(mesh, space, regions, ns):
+        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
+                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
+                      gravity=ns["gravity"])
+        return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"],
+                               ns.get("residual_quadrature_degree", 10), use_c_port=True)
+    ov = dict(verbose=False)
+    ov.update(over)
+    return monolithic.run(problem, make_oracle, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs), overrides=ov)
+
+
+STIFF = dict(mu_s=1e9 / (2 * 1.45), lambda_s=0.45 * 2 * (1e9 / (2 * 1.45)) / (1 - 2 * 0.45))
+
+
+def test_robin_condition_reproduces_the_mass_spring_damper():
+    """RobinBC_validation.py: a cylinder under gravity held by the Robin wall follows
+    m x'' = F - c A x' - k A x (:96-108). With a stiff body (E = 1e9 instead of 1e6, so that the mid-point
+    moves with the wall) the oracle's mid-point displacement matches the ODE to 6e-4 of its peak at
+    dt = 5e-3 — inertia, gravity and both halves of the Robin term (solid.py:41,66-68,83-84)."""
+    ns = _oracle_run("RobinBC_validation", dt=0.005, T=0.1, ncube=3, **STIFF)
+    d = np.array(ns["d_list"])
+    a = ns["default_variables"]["analytical_displacement"]
+    assert len(d) == 21 and abs(a).max() > 5e-3
+    assert np.abs(d - a).max() < 1e-3 * np.abs(a).max()
+    p = ns["default_variables"]["ode_params"]
+    assert abs(p["A"] / (2 * np.pi * 4.0) - 1) < 0.02 and abs(p["m"] / (1e3 * np.pi * 4.0) - 1) < 0.06   # polyhedral cylinder
+
+
+def test_facet_builders_match_the_oracle_closed_forms():
+    """host-side COO builders (quadrature) vs the oracle's closed-form P2 facet matrices, and the
+    closed-surface identity  sum_i l_i = int n dS = 0  of the interior-facet load."""
+    import scipy.sparse as sp
+    from oracle.facets import normal_load, robin_matrices
+    from tests.helpers import square_mesh
+    from turtlefsi_b200.boundary import Facets, interior_facet_normal_load, robin_facet_operators
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    for mesh in (square_mesh(6), box_mesh(4)):
+        g = mesh.gdim
+        cen = mesh.coords[mesh.cells].mean(axis=1)
+        mesh.markers = np.where(np.linalg.norm(cen - 0.5, axis=1) < 0.3, 2, 1).astype(np.int32)   # enclosed solid
+        space = MixedSpace(mesh)
+        N = space.num_dofs
+        facets = Facets(mesh)
+        facets.markers[facets.on_boundary] = 7
+        interface = ~facets.on_boundary & (mesh.markers[facets.cell0] != mesh.markers[np.maximum(facets.cell1, 0)])
+        facets.markers[interface] = 22
+        (r, c, v), (rp, cp, vp) = robin_facet_operators(mesh, space, facets, [7], [3.0], [0.5], 0.6)
+        sel = np.nonzero(facets.on_boundary)[0]
+        onow, oprev = robin_matrices(mesh, space, facets.cell0[sel], facets.local0[sel], 3.0, 0.5, 0.6)
+        now = sp.coo_matrix((v, (r, c)), shape=(N, N)).tocsr()
+        prev = sp.coo_matrix((vp, (rp, cp)), shape=(N, N)).tocsr()
+        assert abs(now - onow).max() < 1e-15 * abs(onow).max() * 10 and abs(prev - oprev).max() < 1e-14 * abs(oprev).max()
+        # rows are psi (v-test) dofs only; k_s d + c_s v: the d- and v-column blocks are 3.0 : 0.5
+        assert set(np.unique(r)) <= set(space.sub_dofs(1))
+        ones_d, ones_v = np.zeros(N), np.zeros(N)
+        ones_d[space.sub_dofs(0, 0)] = 1.0
+        ones_v[space.sub_dofs(1, 0)] = 1.0
+        length = facets.on_boundary.sum() and (now @ ones_d)[space.sub_dofs(1, 0)].sum() / (0.6 * 3.0)
+        assert abs(length - (4.0 if g == 2 else 6.0)) < 1e-12                  # = measure of the boundary
+        assert abs((now @ ones_v)[space.sub_dofs(1, 0)].sum() / (0.6 * 0.5) - length) < 1e-12
+        # interior-facet load: "+" = the higher cell marker (the enclosed solid), n points out of it
+        dofs, vals = interior_facet_normal_load(mesh, space, facets, 22)
+        fi = np.nonzero(interface)[0]
+        plus1 = mesh.markers[facets.cell1[fi]] > mesh.markers[facets.cell0[fi]]
+        pc = np.where(plus1, facets.cell1[fi], facets.cell0[fi])
+        pl = np.where(plus1, facets.local1[fi], facets.local0[fi])
+        ref = normal_load(mesh, space, pc, pl)
+        l = np.zeros(N)
+        l[dofs] = vals
+        assert np.abs(l - ref).max() < 1e-14 * np.abs(ref).max() and np.abs(ref).max() > 0
+        for a in range(g):
+            assert abs(l[space.sub_dofs(1, a)].sum()) < 1e-14                  # closed surface: int n dS = 0
+        # divergence theorem with psi = x e_a: sum_i l_i x_i(a) = int n_a x_a dS = volume of the enclosed solid
+        X = space.node_coords(mesh)
+        Xc = mesh.coords[mesh.cells[mesh.markers == 2]]
+        vol = np.abs(np.linalg.det(Xc[:, 1:] - Xc[:, :1])).sum() / (2 if g == 2 else 6)
+        for a in range(g):
+            assert abs(l[space.node_dof(1, a)] @ X[:, a] - vol) < 1e-13

@@ -168,6 +168,23 @@ class FSIAssembler:
         v = np.ascontiguousarray(vals, dtype=np.float64)
         self._check(self.lib.tfsi_set_facet_operator(self.h, _ptr(r), _ptr(c), _ptr(v), len(v)))
 
+    def set_facet_operator_prev(self, rows, cols, vals):
+        """linear facet terms acting on dvp_["n-1"] (Robin, solid.py:84): residual only."""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        self._check(self.lib.tfsi_set_facet_operator_prev(self.h, _ptr(r), _ptr(c), _ptr(v), len(v)))
+
+    def set_facet_load(self, dofs, vals, scale=1.0):
+        """state-independent facet load l (problem_aneu.py:212-214): b -= scale * l."""
+        d = np.ascontiguousarray(dofs, dtype=np.int32)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        self._check(self.lib.tfsi_set_facet_load(self.h, _ptr(d), _ptr(v), len(v)))
+        self.set_facet_load_scale(scale)
+
+    def set_facet_load_scale(self, scale):
+        self._check(self.lib.tfsi_set_facet_load_scale(self.h, float(scale)))
+
     def compress_A_pre(self, A_pre):
         """register the non-zeros of A_pre so that A := A_pre costs a zero-fill + sparse overwrite."""
         self._check(self.lib.tfsi_compress_A_pre(self.h, _ptr(A_pre), self._stream()))

@@ -114,6 +114,65 @@ class DirichletBC:
         return [np.full(n, v[a]) for a in self.comps]
 
 
+class PointwiseBC:
+    """DirichletBC(DVP.sub(field), value, inside, method="pointwise") [dep]: every dof of the sub-space
+    whose coordinate satisfies inside(x [n, g]) -> bool [n] (problems/TaylorGreen2D.py:157-178: the
+    pressure is pinned at one corner). Same dofs/values() protocol as DirichletBC."""
+
+    def __init__(self, space, mesh, field, value, inside, comp=None):
+        self.field, self.comp, self.value = field, comp, value
+        g = mesh.gdim
+        if field == 2:
+            sel = np.nonzero(inside(mesh.coords))[0]
+            self.dofs = [np.asarray(space.vertex_dof_p())[sel]]
+            self.coords = mesh.coords[sel]
+            self.comps = [0]
+            return
+        X = space.node_coords(mesh)
+        sel = np.nonzero(inside(X))[0]
+        self.comps = list(range(g)) if comp is None else [comp]
+        self.dofs = [space.node_dof(field, a)[sel] for a in self.comps]
+        self.coords = X[sel]
+
+    values = DirichletBC.values
+
+
+def interpolate(space, mesh, x, field, fn):
+    """x[dofs of sub-space `field`] = fn(dof coordinates) — DOLFIN interpolate + assign of a Lagrange
+    field (problems/TaylorGreen2D.py:186-198). fn(X [n, g]) -> [n, ncomp] (or [n] for p)."""
+    if field == 2:
+        x[np.asarray(space.vertex_dof_p())] = np.asarray(fn(mesh.coords)).reshape(-1)
+        return x
+    val = np.asarray(fn(space.node_coords(mesh))).reshape(space.num_nodes, -1)
+    for a in range(mesh.gdim):
+        x[space.node_dof(field, a)] = val[:, a]
+    return x
+
+
+def l2_norm(mesh, space, x, field):
+    """sqrt(int |u_h|^2 dx) of the Lagrange field `field` of x, exactly (element mass matrices) — what
+    DOLFIN's errornorm(ue, uh, "L2") returns when both arguments live in the same space
+    (problems/TaylorGreen2D.py:216-221)."""
+    from .quadrature import default_rule
+    g = mesh.gdim
+    P, W = default_rule(g, 4)
+    phi2, _, phi1 = tabulate(g, P)
+    X = mesh.coords[mesh.cells]
+    detJ = np.abs(np.linalg.det(np.swapaxes(X[:, 1:] - X[:, :1], 1, 2)))
+    n2 = space.n2
+    if field == 2:
+        M = np.einsum('q,qi,qj->ij', W, phi1, phi1)
+        u = x[space.cell_dofs[:, 2 * g * n2:2 * g * n2 + g + 1]]
+        return float(np.sqrt(np.einsum('c,ci,ij,cj->', detJ, u, M, u)))
+    M = np.einsum('q,qi,qj->ij', W, phi2, phi2)
+    off = {0: 0, 1: g * n2, 3: 2 * g * n2 + g + 1}[field]
+    total = 0.0
+    for a in range(g):
+        u = x[space.cell_dofs[:, off + a * n2: off + (a + 1) * n2]]
+        total += np.einsum('c,ci,ij,cj->', detJ, u, M, u)
+    return float(np.sqrt(total))
+
+
 def flatten_bcs(bcs):
     """(dofs int32 [n], values [n]) in list order, later BCs win on shared dofs (DOLFIN applies
     the list sequentially: newtonsolver.py:82,91,98)."""
@@ -231,6 +290,102 @@ def biharmonic_facet_operator(mesh, space, facets, bc_ids, alpha_u=0.01):
         z = np.zeros(0)
         return z.astype(np.int32), z.astype(np.int32), z
     return (np.concatenate(rows).astype(np.int32), np.concatenate(cols).astype(np.int32), np.concatenate(vals))
+
+
+def _facet_rule(g, degree):
+    """(barycentric points on the facet [nq, g], weights summing to 1) exact to `degree`."""
+    from .quadrature import default_rule
+    if g == 2:
+        s, w = _gauss_legendre_01(degree // 2 + 1)
+        return np.stack([1.0 - s, s], axis=1), w
+    P, W = default_rule(2, degree)
+    return np.concatenate([1.0 - P.sum(axis=1, keepdims=True), P], axis=1), W * 2.0
+
+
+def _facet_frame(mesh, c, k):
+    """(local vertex ids of the facet opposite to local vertex k of cell c, measure, outward unit normal)."""
+    g = mesh.gdim
+    vloc = [v for v in range(g + 1) if v != k]
+    X = mesh.coords[mesh.cells[c]]
+    if g == 2:
+        t = X[vloc[1]] - X[vloc[0]]
+        meas = np.linalg.norm(t)
+        nrm = np.array([t[1], -t[0]]) / meas
+    else:
+        cr = np.cross(X[vloc[1]] - X[vloc[0]], X[vloc[2]] - X[vloc[0]])
+        meas = 0.5 * np.linalg.norm(cr)
+        nrm = cr / np.linalg.norm(cr)
+    if np.dot(nrm, X[k] - X[vloc[0]]) > 0:
+        nrm = -nrm
+    return vloc, meas, nrm
+
+
+def robin_facet_operators(mesh, space, facets, ds_s_ids, k_s, c_s, theta):
+    """Robin condition of the solid (turtleFSI/modules/solid.py:76-86), for i over ds_s_ids:
+        F_solid_linear += theta0 (k_s[i] d^n     + c_s[i] v^n    ) . psi ds(ds_s_ids[i])      :83
+        F_solid_linear += theta1 (k_s[i] d^{n-1} + c_s[i] v^{n-1}) . psi ds(ds_s_ids[i])      :84
+    Linear in the state: returns two COO operators (rows psi = v-test dofs; cols d and v),
+    `now` (-> tfsi_set_facet_operator: A_pre += , b -= now x) and `prev` (-> tfsi_set_facet_operator_prev:
+    b -= prev x1). The P2 x P2 facet mass matrix is integrated exactly (degree 4)."""
+    g = mesh.gdim
+    n2 = space.n2
+    bary, fw = _facet_rule(g, 4)
+    ref_vertices = np.vstack([np.zeros(g), np.eye(g)])
+    th0, th1 = theta, 1.0 - theta
+    out = {"now": ([], [], []), "prev": ([], [], [])}
+    for sid, ks, cs in zip(ds_s_ids, k_s, c_s):
+        for f in np.nonzero((facets.markers == sid) & facets.on_boundary)[0]:
+            c, k = facets.cell0[f], facets.local0[f]
+            vloc, meas, _ = _facet_frame(mesh, c, k)
+            phi2, _, _ = tabulate(g, bary @ ref_vertices[vloc])
+            M = meas * np.einsum('q,qi,qj->ij', fw, phi2, phi2)
+            dofs = space.cell_dofs[c]
+            for a in range(g):
+                dd = dofs[a * n2:(a + 1) * n2]
+                vd = dofs[(g + a) * n2:(g + a + 1) * n2]
+                for key, th in (("now", th0), ("prev", th1)):
+                    r, cc, v = out[key]
+                    r += [np.repeat(vd, n2), np.repeat(vd, n2)]
+                    cc += [np.tile(dd, n2), np.tile(vd, n2)]
+                    v += [th * ks * M.ravel(), th * cs * M.ravel()]
+
+    def pack(t):
+        if not t[0]:
+            z = np.zeros(0)
+            return z.astype(np.int32), z.astype(np.int32), z
+        return np.concatenate(t[0]).astype(np.int32), np.concatenate(t[1]).astype(np.int32), np.concatenate(t[2])
+    return pack(out["now"]), pack(out["prev"])
+
+
+def interior_facet_normal_load(mesh, space, facets, marker):
+    """l_i = int n('+') . psi_i('+') dS(marker) over the INTERIOR facets with the given marker: the
+    load a problem file adds as  p(t) * inner(n('+'), psi('+')) * dS(fsi_id)  to F_solid_linear
+    (problems/Test_Cylinder/problem_aneu.py:212-214, problems/Stenosis_2D.py:172-174).
+    "+" side [dep, DOLFIN Assembler]: the form carries cell sub-domains (dx_f, dx_s), so "+" is the
+    incident cell with the HIGHER cell marker (the solid in the shipped problems); equal markers ->
+    the lower cell index. Returns (dofs int32, vals) with duplicates merged."""
+    g = mesh.gdim
+    n2 = space.n2
+    bary, fw = _facet_rule(g, 2)
+    ref_vertices = np.vstack([np.zeros(g), np.eye(g)])
+    acc = {}
+    for f in np.nonzero((facets.markers == marker) & ~facets.on_boundary)[0]:
+        c, k = facets.cell0[f], facets.local0[f]
+        c1 = facets.cell1[f]
+        if mesh.markers is not None and mesh.markers[c1] > mesh.markers[c]:
+            c, k = c1, facets.local1[f]
+        vloc, meas, nrm = _facet_frame(mesh, c, k)
+        phi2, _, _ = tabulate(g, bary @ ref_vertices[vloc])
+        w = meas * (fw @ phi2)
+        dofs = space.cell_dofs[c]
+        for a in range(g):
+            for i in np.nonzero(np.abs(w) > 0)[0]:
+                d = int(dofs[(g + a) * n2 + i])
+                acc[d] = acc.get(d, 0.0) + nrm[a] * w[i]
+    d = np.fromiter(acc.keys(), dtype=np.int64, count=len(acc))
+    v = np.fromiter(acc.values(), dtype=np.float64, count=len(acc))
+    order = np.argsort(d)
+    return d[order].astype(np.int32), v[order]
 
 
 def point_eval(mesh, space, x, point, field=0):

@@ -67,6 +67,8 @@ struct tfsi_handle {
     int profiling;
     // fixed linear facet operator (tfsi_set_facet_operator)
     int32_t *fo_rows, *fo_cols; int64_t* fo_pos; double* fo_vals; int64_t fo_n;
+    int32_t *fp_rows, *fp_cols; double* fp_vals; int64_t fp_n;      // facet operator on the previous time level (residual only)
+    int32_t* fl_dofs; double* fl_vals; int64_t fl_n; double fl_scale;  // state-independent facet load
     // compressed copy of A_pre (tfsi_compress_A_pre)
     const double* cpre_src;
     uint32_t* cpre_bitmap; int64_t* cpre_base; double* cpre_val; int64_t cpre_nnz, cpre_words;
@@ -319,6 +321,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
+    cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals); cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -353,6 +356,8 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->nbc = 0; h->launches = 0; h->profiling = 0;
     h->copy_stream = h->main_stream = nullptr; h->ev_begin = h->ev_entry = h->ev_in = h->ev_b = nullptr; h->n_ev = 0;
     h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
+    h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
+    h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0; h->fl_scale = 1.0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
@@ -549,6 +554,39 @@ int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* 
     return 0;
 }
 
+int tfsi_set_facet_operator_prev(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n) {
+    if (!h || n < 0 || (n && (!rows || !cols || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals);
+    h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (rows[i] < 0 || rows[i] >= h->N || cols[i] < 0 || cols[i] >= h->N) return fail(h, TFSI_ERR_ARG, "facet-operator index out of range");
+    if (int rc = upload(h, &h->fp_rows, rows, (size_t)n)) return rc;
+    if (int rc = upload(h, &h->fp_cols, cols, (size_t)n)) return rc;
+    if (int rc = upload(h, &h->fp_vals, vals, (size_t)n)) return rc;
+    h->fp_n = n;
+    return 0;
+}
+
+int tfsi_set_facet_load(tfsi_handle* h, const int32_t* dofs, const double* vals, int64_t n) {
+    if (!h || n < 0 || (n && (!dofs || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
+    h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0;
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (dofs[i] < 0 || dofs[i] >= h->N) return fail(h, TFSI_ERR_ARG, "facet-load index out of range");
+    if (int rc = upload(h, &h->fl_dofs, dofs, (size_t)n)) return rc;
+    if (int rc = upload(h, &h->fl_vals, vals, (size_t)n)) return rc;
+    h->fl_n = n;
+    return 0;
+}
+
+int tfsi_set_facet_load_scale(tfsi_handle* h, double scale) {
+    if (!h) return fail(h, TFSI_ERR_ARG, "null argument");
+    h->fl_scale = scale;
+    return 0;
+}
+
 int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
     if (!h || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -592,6 +630,16 @@ int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, do
     if (int rc = launch_residual(h, x, x1, b, st)) return rc;
     if (h->fo_n) {
         coo_sub_matvec_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_rows, h->fo_cols, h->fo_vals, h->fo_n, x, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (h->fp_n) {
+        coo_sub_matvec_kernel<<<grid_for(h->fp_n, 256, h->sm_count), 256, 0, st>>>(h->fp_rows, h->fp_cols, h->fp_vals, h->fp_n, x1, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (h->fl_n && h->fl_scale != 0.0) {
+        sparse_sub_scaled_kernel<<<grid_for(h->fl_n, 256, h->sm_count), 256, 0, st>>>(h->fl_dofs, h->fl_vals, h->fl_n, h->fl_scale, b);
         h->launches++;
         CK(h, cudaGetLastError());
     }

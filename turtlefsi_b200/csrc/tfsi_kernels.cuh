@@ -976,6 +976,13 @@ __global__ void coo_sub_matvec_kernel(const int32_t* rows, const int32_t* cols, 
         atomicAdd(b + rows[i], -vals[i] * x[cols[i]]);
 }
 
+// b[dofs[i]] -= scale * vals[i]  (state-independent facet load, e.g. p(t) n.psi dS)
+__global__ void sparse_sub_scaled_kernel(const int32_t* dofs, const double* vals, int64_t n, double scale, double* b)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(b + dofs[i], -scale * vals[i]);
+}
+
 // dof-level CSR columns from the P2-node adjacency (node-interleaved numbering): one thread per
 // node-adjacency entry (I, J); writes the ncomp[I] x ncomp[J] block of column indices.
 __global__ void expand_node_pattern_kernel(int64_t num_nodes, const int64_t* nrowptr, const int32_t* ncol,

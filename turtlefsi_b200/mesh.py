@@ -5,6 +5,7 @@ turtleFSI/problems/TF_fsi.py:68, problems/Test_Cylinder/problem_aneu.py:68-78). 
 available, so the hot path takes plain arrays; this module produces them:
 
 * `read_dolfin_xml`  — the shipped `turtleFSI/mesh/TF_*.xml.gz` format
+* `rectangle_mesh`   — DOLFIN `RectangleMesh(p0, p1, nx, ny, diagonal)` (problems/TaylorGreen2D.py:123)
 * `box_mesh`         — N^3 cubes x 6 tets sharing the main diagonal (DOLFIN BoxMesh pattern),
                        jittered interior vertices (SURVEY 8d "Synthetic 3-D inputs")
 * `tube_mesh`        — the same box mapped to a cylinder (R_o = 1, length 4), marker 1 (fluid)
@@ -240,3 +241,24 @@ def synthetic_state(mesh, space, seed, h=None):
         for a in range(g):
             x[space.node_dof(3, a)] = w[:, a]
     return x
+
+
+def rectangle_mesh(p0, p1, nx, ny, diagonal="right"):
+    """DOLFIN RectangleMesh [dep]: vertex iy*(nx+1)+ix at p0 + (ix*hx, iy*hy); every square
+    (v0 v1 / v2 v3, v1 = v0+1, v2 = v0+nx+1) is cut into (v0,v1,v3),(v0,v2,v3) for "right" and into
+    (v0,v1,v2),(v1,v2,v3) for "left". All cells get marker 1."""
+    if diagonal not in ("right", "left"):
+        raise ValueError("diagonal must be 'right' or 'left'")
+    xs = np.linspace(p0[0], p1[0], nx + 1)
+    ys = np.linspace(p0[1], p1[1], ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords = np.stack([X.ravel(), Y.ravel()], axis=1)
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    v0 = (iy * (nx + 1) + ix).ravel()
+    v1, v2, v3 = v0 + 1, v0 + nx + 1, v0 + nx + 2
+    if diagonal == "right":
+        tri = np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], axis=1)
+    else:
+        tri = np.stack([np.stack([v0, v1, v2], 1), np.stack([v1, v2, v3], 1)], axis=1)
+    cells = np.sort(tri.reshape(-1, 3), axis=1).astype(np.int32)
+    return Mesh(coords, cells, np.ones(len(cells), dtype=np.int32), dict(kind="rectangle", nx=nx, ny=ny))

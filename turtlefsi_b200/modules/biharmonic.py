@@ -11,8 +11,9 @@ def extrapolate_setup(F_fluid_linear, extrapolation_sub_type="constant", **names
 def facet_terms(assembler, mesh, DVP, boundaries, bc_ids, extrapolation_sub_type, **namespace):
     """biharmonic.py:38-41: with "constrained_disp_vel" the lifting gets the exterior-facet terms
     alpha_u (grad(d) n).beta ds(i) - alpha_u (grad(w) n).phi ds(i), i in bc_ids. They are linear in
-    (d, w): a fixed sparse operator handed to the assembler once (A_pre += A_f, b -= A_f x)."""
+    (d, w): a fixed sparse operator (COO) that the driver hands to the assembler once
+    (A_pre += A_f, b -= A_f x)."""
     if extrapolation_sub_type != "constrained_disp_vel" or not bc_ids:
-        return
+        return None
     from ..boundary import biharmonic_facet_operator
-    assembler.set_facet_operator(*biharmonic_facet_operator(mesh, DVP, boundaries, bc_ids, alpha_u=0.01))
+    return dict(now=biharmonic_facet_operator(mesh, DVP, boundaries, bc_ids, alpha_u=0.01))

@@ -12,7 +12,7 @@ from .space import MixedSpace
 
 
 def assign_domain_properties(dx_f_id, rho_f, mu_f, fluid_properties, dx_s_id, material_model, rho_s, mu_s,
-                             lambda_s, solid_properties, **namespace):
+                             lambda_s, solid_properties, ds_s_id=None, robin_bc=False, **namespace):
     """turtleFSI/modules/domain.py:16-121: scalar-or-list inputs -> per-region property lists."""
     as_list = lambda v: v if isinstance(v, list) else [v]
     dx_f_id_list, dx_s_id_list = as_list(dx_f_id), as_list(dx_s_id)
@@ -34,8 +34,25 @@ def assign_domain_properties(dx_f_id, rho_f, mu_f, fluid_properties, dx_s_id, ma
     regions = [dict(marker=fp["dx_f_id"], kind="fluid", rho=fp["rho_f"], mu=fp["mu_f"]) for fp in fluid_properties]
     regions += [dict(marker=sp["dx_s_id"], kind="solid", rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"])
                 for sp in solid_properties]
+    ds_s_ext_id_list = (ds_s_id if isinstance(ds_s_id, list) else [ds_s_id]) if robin_bc else None   # domain.py:106-119
     return dict(dx_f_id_list=dx_f_id_list, dx_s_id_list=dx_s_id_list, fluid_properties=fluid_properties,
-                solid_properties=solid_properties, regions=regions)
+                solid_properties=solid_properties, regions=regions, ds_s_ext_id_list=ds_s_ext_id_list)
+
+
+def _set_facet_terms(assembler, ns):
+    """the LINEAR facet integrals of the selected modules (biharmonic.py:38-41 ds(i) terms, solid.py:76-86
+    Robin ds_s terms) as fixed COO operators, handed to the assembler once."""
+    import numpy as np
+    terms = {"now": [], "prev": []}
+    for key in ("extrapolation", "solid"):
+        m = importlib.import_module("turtlefsi_b200.modules." + ns[key])
+        t = m.facet_terms(**ns) if hasattr(m, "facet_terms") else None
+        for lvl in terms:
+            if t and t.get(lvl) is not None and len(t[lvl][2]):
+                terms[lvl].append(t[lvl])
+    for lvl, setter in (("now", "set_facet_operator"), ("prev", "set_facet_operator_prev")):
+        if terms[lvl]:
+            getattr(assembler, setter)(*[np.concatenate([t[i] for t in terms[lvl]]) for i in range(3)])
 
 
 def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
@@ -60,9 +77,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
         ns.update(getattr(m, fn)(**ns))
     assembler = make_assembler(mesh, DVP, ns["regions"], ns)
     ns["assembler"] = assembler
-    ext_mod = importlib.import_module("turtlefsi_b200.modules." + ns["extrapolation"])
-    if hasattr(ext_mod, "facet_terms"):                                                              # biharmonic.py:38-41
-        ext_mod.facet_terms(**ns)
+    _set_facet_terms(assembler, ns)
     dvp_ = {k: assembler.new_vector() for k in ("n-2", "n-1", "n")}                                   # :95-111
     ns["dvp_"] = dvp_
     ns["up_sol"] = make_solver(assembler)                                                             # :136
