@@ -27,6 +27,7 @@ struct Region {
     int32_t* cell_list;   // device
     uint16_t* rank_blk;   // device, per CTA batch (Jacobian kernels)
     int32_t* dofs_blk;    // device, per CTA batch
+    int32_t* res_dofs_blk; // device, per residual CTA batch: [ndof][res_nc]
     size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
 };
 
@@ -51,6 +52,7 @@ struct tfsi_handle {
     int64_t *rowptr, *diagpos;
     uint16_t* rank;
     double* scratch;          // 1 double (sumsq)
+    int res_nc;               // cells per residual CTA (32 | 16 | 0 = unsupported rule)
     double *hx, *hx1, *hb, *hg;   // device staging for the _host entry
     int64_t nbc;
     std::vector<Region> regions;
@@ -284,20 +286,35 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
         if (rc.kind == TFSI_KIND_FLUID && !rc.fluid_on && rc.ext == 0) continue;
         if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
+        a.dofs_blk = r.res_dofs_blk;
         KernelTimer kt(h, 2, st);
-        residual_kernel<G, BIH, NC><<<(unsigned)((r.ncells + NC - 1) / NC), RES_THREADS, smem, st>>>(a);
+        residual_kernel<G, BIH, NC><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
     }
     return 0;
 }
 
+size_t residual_smem(const tfsi_handle* h, int nc) {
+    const int nq = h->tabR.nq;
+    if (h->gdim == 3) return h->biharmonic ? ResCfg<3, true>::bytes(nq, nc) : ResCfg<3, false>::bytes(nq, nc);
+    return h->biharmonic ? ResCfg<2, true>::bytes(nq, nc) : ResCfg<2, false>::bytes(nq, nc);
+}
+
+// cells per residual CTA: 16 (4 warps, two CTAs per SM overlap their phases) when two of them fit into the
+// shared memory of one SM, else 32 (8 warps, one CTA per SM), else 16 alone; 0 = the rule does not fit
+int residual_nc(const tfsi_handle* h) {
+    static const int pref = getenv("TFSI_RES_NC") ? atoi(getenv("TFSI_RES_NC")) : 16;
+    if (pref == 16 && residual_smem(h, 16) <= 112 * 1024) return 16;
+    if (residual_smem(h, 32) <= 220 * 1024) return 32;
+    if (residual_smem(h, 16) <= 220 * 1024) return 16;
+    return 0;
+}
+
 template <int G, bool BIH>
 int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
-    typedef ResCfg<G, BIH> R;
-    // cells per CTA: as many as the per-point flux table allows in shared memory
-    if (R::bytes(h->tabR.nq, 32) <= 220 * 1024) return launch_residual_nc<G, BIH, 32>(h, x, x1, b, st);
-    if (R::bytes(h->tabR.nq, 16) <= 220 * 1024) return launch_residual_nc<G, BIH, 16>(h, x, x1, b, st);
+    if (h->res_nc == 32) return launch_residual_nc<G, BIH, 32>(h, x, x1, b, st);
+    if (h->res_nc == 16) return launch_residual_nc<G, BIH, 16>(h, x, x1, b, st);
     return fail(h, TFSI_ERR_UNSUPPORTED, "residual rule with %d points does not fit in shared memory", h->tabR.nq);
 }
 
@@ -323,7 +340,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals); cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
-    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); }
+    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
@@ -405,7 +422,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
             r.ncells = (int64_t)list.size();
-            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
+            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
             CKC(upload(h, &r.cell_list, list.data(), list.size()));
             h->regions.push_back(r);
         }
@@ -486,6 +503,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         }
     }
     // per-CTA-batch blocked copies for the Jacobian kernels (bulk-copy / coalesced staging)
+    h->res_nc = residual_nc(h);
     for (Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const int g3 = (g == 3);
@@ -506,6 +524,12 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             h->rank, r.cell_list, r.ncells, h->n2, h->ndof_pad, ncols, ncta, rks, r.rank_blk_elems, r.rank_blk);
         build_dofs_blocked_kernel<<<grid_for(nb * ncoef * ncta, 256, h->sm_count), 256>>>(
             h->cell_dofs, r.cell_list, r.ncells, h->ndof, ncoef, ncta, r.dofs_blk);
+        if (h->res_nc) {                                     // residual kernel: [ndof][res_nc] per batch
+            const int64_t nbr = (r.ncells + h->res_nc - 1) / h->res_nc;
+            CKC(cka(cudaMalloc((void**)&r.res_dofs_blk, (size_t)nbr * h->ndof * h->res_nc * sizeof(int32_t))));
+            build_dofs_blocked_kernel<<<grid_for(nbr * h->ndof * h->res_nc, 256, h->sm_count), 256>>>(
+                h->cell_dofs, r.cell_list, r.ncells, h->ndof, h->ndof, h->res_nc, r.res_dofs_blk);
+        }
         CKC(cka(cudaDeviceSynchronize()));
     }
 #undef CKC

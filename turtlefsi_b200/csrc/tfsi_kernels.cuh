@@ -639,39 +639,74 @@ template <int G, bool BIH> struct ResCfg {
     static constexpr int NGROUPS = (BIH ? 3 : 2) * G;            // P2 row groups (field, comp): phi, psi (, beta)
     static constexpr int FS = NGROUPS * (G + 1) + 1;             // flux items per point (+ gamma); odd in all cases
     static __host__ __device__ size_t off_coef(int nq, int nc) { return sizeof(double) * (size_t)nq * nc * FS; }
-    static __host__ __device__ size_t off_dofs(int nq, int nc) { return off_coef(nq, nc) + 2 * sizeof(double) * (size_t)NDOF * nc; }
+    static __host__ __device__ size_t off_geo(int nq, int nc) { return off_coef(nq, nc) + 2 * sizeof(double) * (size_t)NDOF * nc; }
+    static __host__ __device__ size_t off_dofs(int nq, int nc) { return off_geo(nq, nc) + sizeof(double) * (size_t)(G * G + 1) * nc; }
     static __host__ __device__ size_t bytes(int nq, int nc) { return off_dofs(nq, nc) + sizeof(int32_t) * (size_t)NDOF * nc; }
 };
 
+// Residual b = -F. NC cells per CTA, 8 threads per cell:
+//   NC = 32: 8 warps, one CTA per SM;  NC = 16: 4 warps, TWO CTAs per SM (242 registers each), so that the
+//   gather / scatter phases of one CTA run under the FP64 phase of the other.
+// gather : dofs from the per-batch blocked array [k][cell] (coalesced), x and x1 gathered in one batch of
+//          independent loads; geometry (K, |det|) staged once per cell
+// phase 0: thread (cell, q) -> per-point fluxes of F = F_lin + F_nonlin (residual_point) -> smem [q][cell][FS]
+// phase 1: warp = row group (field, comp), lane = cell: Z_i = sum_q phi_i f0 + ghat_i . f  (sparse P2 test
+//          functions); with NC = 16 the two half-warps take the even / odd points and are combined by shuffles;
+//          ONE RED per row
 template <int G, bool BIH, int NC>
-__global__ void __launch_bounds__(RES_THREADS, 1) residual_kernel(CellArgs a)
+__global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(CellArgs a)
 {
     typedef ResCfg<G, BIH> R;
     constexpr int N2 = R::N2, N1 = R::N1, NDOF = R::NDOF, FS = R::FS;
+    constexpr int RT = NC * 8, RW = RT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = a.nq;
     double* flux = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + R::off_coef(nq, NC));
     double* coef1 = coef + NDOF * NC;
+    double* sgeo = reinterpret_cast<double*>(smem_raw + R::off_geo(nq, NC));
     int32_t* sdofs = reinterpret_cast<int32_t*>(smem_raw + R::off_dofs(nq, NC));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int idx = threadIdx.x; idx < NDOF * NC; idx += RES_THREADS) {
-        const int c = idx % NC, k = idx / NC;
-        const int64_t ci = (int64_t)blockIdx.x * NC + c;
-        const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
-        const int dof = a.cell_dofs[cell * a.ndof + k];
-        sdofs[idx] = dof;
-        coef[idx] = a.x[dof];
-        coef1[idx] = a.x1[dof];
+    {
+        const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * (NDOF * NC);
+        constexpr int PER = (NDOF * NC + RT - 1) / RT;
+        int dof[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = threadIdx.x + u * RT;
+            dof[u] = (idx < NDOF * NC) ? dblk[idx] : 0;
+        }
+        double xv[PER], x1v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { xv[u] = a.x[dof[u]]; x1v[u] = a.x1[dof[u]]; }
+        if (threadIdx.x < NC) {
+            const int c = threadIdx.x;
+            const int64_t ci = (int64_t)blockIdx.x * NC + c;
+            const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
+            double K[G][G];
+            const double adet = load_geometry<G>(a, cell, K);
+#pragma unroll
+            for (int s = 0; s < G; ++s)
+#pragma unroll
+                for (int t = 0; t < G; ++t) sgeo[(s * G + t) * NC + c] = K[s][t];
+            sgeo[G * G * NC + c] = adet;
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = threadIdx.x + u * RT;
+            if (idx < NDOF * NC) { sdofs[idx] = dof[u]; coef[idx] = xv[u]; coef1[idx] = x1v[u]; }
+        }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < nq * NC; t += RES_THREADS) {       // phase 0
+    for (int t = threadIdx.x; t < nq * NC; t += RT) {                 // phase 0
         const int c = t % NC, q = t / NC;
-        const int64_t ci = (int64_t)blockIdx.x * NC + c;
-        const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
         double K[G][G];
-        const double adet = load_geometry<G>(a, cell, K);
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+#pragma unroll
+            for (int u = 0; u < G; ++u) K[s][u] = sgeo[(s * G + u) * NC + c];
+        const double adet = sgeo[G * G * NC + c];
         double alfa_cell = a.rc.alfa;
         if (a.rc.ext == 1 && a.rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
         auto cf = [&](int k) { return coef[k * NC + c]; };
@@ -698,21 +733,26 @@ __global__ void __launch_bounds__(RES_THREADS, 1) residual_kernel(CellArgs a)
     const bool has_phi = fluid ? (a.rc.ext != 0) : (a.rc.solid_on != 0);
     const bool has_psi = fluid ? (a.rc.fluid_on != 0) : (a.rc.solid_on != 0);
     const bool has_beta = BIH && fluid && a.rc.ext == 2;
-    const int c = lane % NC;                                          // NC is 32 or 16 (half-warps duplicate)
+    constexpr int QS = 32 / NC;                                       // point stride: half-warps split the points
+    const int c = lane % NC, q0 = lane / NC;
     const bool valid = (lane < NC) && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
-    for (int t = warp; t <= R::NGROUPS; t += RES_WARPS) {             // phase 1: row groups, last = gamma
+    for (int t = warp; t <= R::NGROUPS; t += RW) {                    // phase 1: row groups, last = gamma
         if (t < R::NGROUPS) {
             const int fieldg = t / G, cc = t % G;                     // 0 phi (d rows), 1 psi (v rows), 2 beta (w rows)
             if ((fieldg == 0 && !has_phi) || (fieldg == 1 && !has_psi) || (fieldg == 2 && !has_beta)) continue;
             double Z[N2];
 #pragma unroll
             for (int i = 0; i < N2; ++i) Z[i] = 0.0;
-            for (int q = 0; q < nq; ++q) {
+            for (int q = q0; q < nq; q += QS) {
                 const double* src = flux + ((size_t)q * NC + c) * FS + t * (G + 1);
                 double W[G + 1];
 #pragma unroll
                 for (int s = 0; s <= G; ++s) W[s] = src[s];
                 test_p2_sparse<G>(c_tabR, q, W, Z);
+            }
+            if (QS == 2) {
+#pragma unroll
+                for (int i = 0; i < N2; ++i) Z[i] += __shfl_xor_sync(0xffffffffu, Z[i], 16);
             }
             if (valid) {
                 const int row0 = (fieldg == 0 ? 0 : (fieldg == 1 ? G * N2 : 2 * G * N2 + N1)) + cc * N2;
@@ -723,10 +763,14 @@ __global__ void __launch_bounds__(RES_THREADS, 1) residual_kernel(CellArgs a)
             double Zg[N1];
 #pragma unroll
             for (int m = 0; m < N1; ++m) Zg[m] = 0.0;
-            for (int q = 0; q < nq; ++q) {
+            for (int q = q0; q < nq; q += QS) {
                 const double gm = flux[((size_t)q * NC + c) * FS + FS - 1];
 #pragma unroll
                 for (int m = 0; m < N1; ++m) Zg[m] += c_tabR.phi1[q][m] * gm;
+            }
+            if (QS == 2) {
+#pragma unroll
+                for (int m = 0; m < N1; ++m) Zg[m] += __shfl_xor_sync(0xffffffffu, Zg[m], 16);
             }
             if (valid) {
 #pragma unroll

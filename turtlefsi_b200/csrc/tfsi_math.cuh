@@ -615,24 +615,37 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     const double jw = tab.w[q] * adet;
-    // field values and reference gradients at n and n-1
+    // field values and reference gradients at n and n-1. Gradients through the barycentric derivatives of
+    // the P2 basis, which are sparse (vertex i: (4 lambda_i - 1) e_i; edge (a,b): 4 lambda_b e_a + 4 lambda_a e_b):
+    // 16 FMAs + 3 differences per component instead of 30 FMAs; d/dxi_t = d/dlambda_{t+1} - d/dlambda_0.
+    typedef P2Edges<G> E;
     double d[G], v[G], d1[G], v1[G], Gd[G][G], Gv[G][G], Gd1[G][G], Gv1[G][G];
 #pragma unroll
     for (int a = 0; a < G; ++a) {
+        double Ld[G + 1], Lv[G + 1], Ld1[G + 1], Lv1[G + 1];
         d[a] = v[a] = d1[a] = v1[a] = 0;
 #pragma unroll
-        for (int t = 0; t < G; ++t) Gd[a][t] = Gv[a][t] = Gd1[a][t] = Gv1[a][t] = 0;
-#pragma unroll
         for (int j = 0; j < N2; ++j) {
-            double dj = cf(a * N2 + j), vj = cf(G * N2 + a * N2 + j);
-            double d1j = cf1(a * N2 + j), v1j = cf1(G * N2 + a * N2 + j);
-            double ph = tab.phi2[q][j];
-            d[a] += dj * ph; v[a] += vj * ph; d1[a] += d1j * ph; v1[a] += v1j * ph;
-#pragma unroll
-            for (int t = 0; t < G; ++t) {
-                double g = tab.dphi2[q][j][t];
-                Gd[a][t] += dj * g; Gv[a][t] += vj * g; Gd1[a][t] += d1j * g; Gv1[a][t] += v1j * g;
+            const double dj = cf(a * N2 + j), vj = cf(G * N2 + a * N2 + j);
+            const double d1j = cf1(a * N2 + j), v1j = cf1(G * N2 + a * N2 + j);
+            const double ph = tab.phi2[q][j];
+            d[a] = fma(dj, ph, d[a]); v[a] = fma(vj, ph, v[a]); d1[a] = fma(d1j, ph, d1[a]); v1[a] = fma(v1j, ph, v1[a]);
+            if (j <= G) {
+                const double g = tab.d4[q][j];
+                Ld[j] = dj * g; Lv[j] = vj * g; Ld1[j] = d1j * g; Lv1[j] = v1j * g;
+            } else {
+                const int ea = E::a(j - G - 1), eb = E::b(j - G - 1);
+                const double la = tab.l4[q][ea], lb = tab.l4[q][eb];
+                Ld[ea] = fma(dj, lb, Ld[ea]); Ld[eb] = fma(dj, la, Ld[eb]);
+                Lv[ea] = fma(vj, lb, Lv[ea]); Lv[eb] = fma(vj, la, Lv[eb]);
+                Ld1[ea] = fma(d1j, lb, Ld1[ea]); Ld1[eb] = fma(d1j, la, Ld1[eb]);
+                Lv1[ea] = fma(v1j, lb, Lv1[ea]); Lv1[eb] = fma(v1j, la, Lv1[eb]);
             }
+        }
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            Gd[a][t] = Ld[t + 1] - Ld[0]; Gv[a][t] = Lv[t + 1] - Lv[0];
+            Gd1[a][t] = Ld1[t + 1] - Ld1[0]; Gv1[a][t] = Lv1[t + 1] - Lv1[0];
         }
     }
 #pragma unroll
