@@ -638,7 +638,13 @@ template <int G, bool BIH> struct ResCfg {
     static constexpr int NDOF = (BIH ? 3 : 2) * G * N2 + N1;
     static constexpr int NGROUPS = (BIH ? 3 : 2) * G;            // P2 row groups (field, comp): phi, psi (, beta)
     static constexpr int FS = NGROUPS * (G + 1) + 1;             // flux items per point (+ gamma); odd in all cases
-    static __host__ __device__ size_t off_coef(int nq, int nc) { return sizeof(double) * (size_t)nq * nc * FS; }
+    static constexpr int NU = 8;                                 // phase-1 units (warps x point-slices per warp)
+    static constexpr int PR = G * N2 + N1;                       // partial record of a unit: one field's rows + gamma
+    // flux table [q][cell][FS]; re-used for the partial sums [unit][PR][cell] of phase 1
+    static __host__ __device__ size_t off_coef(int nq, int nc) {
+        const size_t a = (size_t)nq * FS, b = (size_t)NU * PR;
+        return sizeof(double) * (a > b ? a : b) * nc;
+    }
     static __host__ __device__ size_t off_geo(int nq, int nc) { return off_coef(nq, nc) + 2 * sizeof(double) * (size_t)NDOF * nc; }
     static __host__ __device__ size_t off_dofs(int nq, int nc) { return off_geo(nq, nc) + sizeof(double) * (size_t)(G * G + 1) * nc; }
     static __host__ __device__ size_t bytes(int nq, int nc) { return off_dofs(nq, nc) + sizeof(int32_t) * (size_t)NDOF * nc; }
@@ -729,53 +735,82 @@ __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(Ce
         dst[FS - 1] = f.gamma;
     }
     __syncthreads();
+    // phase 1: unit u = (warp, point slice of the warp) -> (active field, slice): all G components of the field
+    // share the tabulated test functions; partial sums over the slices go through shared memory
     const bool fluid = a.rc.kind == 0;
     const bool has_phi = fluid ? (a.rc.ext != 0) : (a.rc.solid_on != 0);
     const bool has_psi = fluid ? (a.rc.fluid_on != 0) : (a.rc.solid_on != 0);
     const bool has_beta = BIH && fluid && a.rc.ext == 2;
-    constexpr int QS = 32 / NC;                                       // point stride: half-warps split the points
-    const int c = lane % NC, q0 = lane / NC;
-    const bool valid = (lane < NC) && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
-    for (int t = warp; t <= R::NGROUPS; t += RW) {                    // phase 1: row groups, last = gamma
-        if (t < R::NGROUPS) {
-            const int fieldg = t / G, cc = t % G;                     // 0 phi (d rows), 1 psi (v rows), 2 beta (w rows)
-            if ((fieldg == 0 && !has_phi) || (fieldg == 1 && !has_psi) || (fieldg == 2 && !has_beta)) continue;
-            double Z[N2];
+    const bool has_gamma = fluid && a.rc.fluid_on;
+    const int nfa = (has_phi ? 1 : 0) + (has_psi ? 1 : 0) + (has_beta ? 1 : 0);
+    // k-th active field (0 phi: d rows, 1 psi: v rows, 2 beta: w rows)
+    auto field_of = [&](int k) {
+        int f = 0;
+        if (!has_phi) f = 1;
+        if (k >= 1) f = (has_phi && has_psi) ? 1 : 2;
+        if (k >= 2) f = 2;
+        return f;
+    };
+    constexpr int QS = 32 / NC, NU = R::NU, PR = R::PR;
+    static_assert(RW * QS == NU, "8 units per CTA");
+    if (nfa > 0) {
+        const int c = lane % NC, u = warp * QS + lane / NC;
+        const int nsl = NU / nfa, fi = u % nfa, sl = u / nfa;
+        const bool active = sl < nsl;
+        const int fld = field_of(fi);
+        double Z[G][N2], Zg[N1];
 #pragma unroll
-            for (int i = 0; i < N2; ++i) Z[i] = 0.0;
-            for (int q = q0; q < nq; q += QS) {
-                const double* src = flux + ((size_t)q * NC + c) * FS + t * (G + 1);
-                double W[G + 1];
+        for (int cc = 0; cc < G; ++cc)
 #pragma unroll
-                for (int s = 0; s <= G; ++s) W[s] = src[s];
-                test_p2_sparse<G>(c_tabR, q, W, Z);
+            for (int i = 0; i < N2; ++i) Z[cc][i] = 0.0;
+#pragma unroll
+        for (int m = 0; m < N1; ++m) Zg[m] = 0.0;
+        if (active) {
+            for (int q = sl; q < nq; q += nsl) {
+                const double* src = flux + ((size_t)q * NC + c) * FS;
+                double W[G][G + 1];
+#pragma unroll
+                for (int cc = 0; cc < G; ++cc)
+#pragma unroll
+                    for (int s = 0; s <= G; ++s) W[cc][s] = src[(fld * G + cc) * (G + 1) + s];
+                const double gm = src[FS - 1];
+#pragma unroll
+                for (int cc = 0; cc < G; ++cc) test_p2_sparse<G>(c_tabR, q, W[cc], Z[cc]);
+                if (fi == 0) {
+#pragma unroll
+                    for (int m = 0; m < N1; ++m) Zg[m] = fma(c_tabR.phi1[q][m], gm, Zg[m]);
+                }
             }
-            if (QS == 2) {
+        }
+        __syncthreads();                                              // the flux table is dead: re-use it
+        double* part = flux;
+        if (active) {
 #pragma unroll
-                for (int i = 0; i < N2; ++i) Z[i] += __shfl_xor_sync(0xffffffffu, Z[i], 16);
+            for (int cc = 0; cc < G; ++cc)
+#pragma unroll
+                for (int i = 0; i < N2; ++i) part[((size_t)u * PR + cc * N2 + i) * NC + c] = Z[cc][i];
+            if (fi == 0) {
+#pragma unroll
+                for (int m = 0; m < N1; ++m) part[((size_t)u * PR + G * N2 + m) * NC + c] = Zg[m];
             }
-            if (valid) {
-                const int row0 = (fieldg == 0 ? 0 : (fieldg == 1 ? G * N2 : 2 * G * N2 + N1)) + cc * N2;
-#pragma unroll
-                for (int i = 0; i < N2; ++i) atomicAdd(a.out + sdofs[(row0 + i) * NC + c], -Z[i]);
+        }
+        __syncthreads();
+        const int nout = nfa * G * N2 + (has_gamma ? N1 : 0);
+        for (int o = threadIdx.x; o < nout * NC; o += RT) {
+            const int cc = o % NC, r = o / NC;
+            if ((int64_t)blockIdx.x * NC + cc >= a.ncell_region) continue;
+            int k, rr, row;
+            if (r < nfa * G * N2) {
+                k = r / (G * N2); rr = r % (G * N2);
+                const int f = field_of(k);
+                row = (f == 0 ? 0 : (f == 1 ? G * N2 : 2 * G * N2 + N1)) + rr;
+            } else {
+                k = 0; rr = G * N2 + (r - nfa * G * N2);
+                row = 2 * G * N2 + (r - nfa * G * N2);
             }
-        } else if (fluid && a.rc.fluid_on) {
-            double Zg[N1];
-#pragma unroll
-            for (int m = 0; m < N1; ++m) Zg[m] = 0.0;
-            for (int q = q0; q < nq; q += QS) {
-                const double gm = flux[((size_t)q * NC + c) * FS + FS - 1];
-#pragma unroll
-                for (int m = 0; m < N1; ++m) Zg[m] += c_tabR.phi1[q][m] * gm;
-            }
-            if (QS == 2) {
-#pragma unroll
-                for (int m = 0; m < N1; ++m) Zg[m] += __shfl_xor_sync(0xffffffffu, Zg[m], 16);
-            }
-            if (valid) {
-#pragma unroll
-                for (int m = 0; m < N1; ++m) atomicAdd(a.out + sdofs[(2 * G * N2 + m) * NC + c], -Zg[m]);
-            }
+            double sum = 0.0;
+            for (int s2 = 0; s2 < nsl; ++s2) sum += part[((size_t)(s2 * nfa + k) * PR + rr) * NC + cc];
+            atomicAdd(a.out + sdofs[row * NC + cc], -sum);
         }
     }
 }
