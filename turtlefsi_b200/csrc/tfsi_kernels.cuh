@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
         if (t >= NTASK) break;
         if (t < NBIG) {
             const int grp = t % NGRP, r = t / NGRP;
-            const int fld = r / (2 * G), ca = (r >> 1) % G, half = r & 1;
+            // half-major order: the warps that run concurrently execute the same code variant (the two
+            // half-block variants do not fit the instruction cache together: 14.44 -> 14.06 ms)
+            const int half = r / (2 * G), fld = (r / G) & 1, ca = r % G;
             const int c = grp * CPW + cw;
             const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
             const double* basec = base + (size_t)c * STRIDE;
