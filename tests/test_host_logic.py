@@ -112,3 +112,31 @@ def test_biharmonic_facet_operator_matches_oracle():
         assert abs(A - B).max() < 1e-14 * abs(B).max()
         # antisymmetric coupling: rows(w) x cols(d) = - rows(d) x cols(w) transposed positions
         assert abs(A).sum() > 0
+
+
+def test_surface_traction_3d_constant_stress():
+    """3-D drag/lift functional (common.py:63-81 sigma * n over marked facets): for a linear velocity
+    v = A x, constant p and d = 0 the stress is constant, so the traction on a planar face is
+    sigma n * area and the traction over the closed boundary vanishes."""
+    from turtlefsi_b200.boundary import Facets, interpolate, surface_traction
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = box_mesh(3)
+    space = MixedSpace(mesh)
+    A = np.array([[0.3, -1.2, 0.5], [0.7, 0.1, -0.4], [-0.9, 0.6, 0.2]])
+    mu, p0 = 0.37, 2.5
+    x = np.zeros(space.num_dofs)
+    interpolate(space, mesh, x, 1, lambda X: X @ A.T)
+    interpolate(space, mesh, x, 2, lambda X: np.full(len(X), p0))
+    sig = mu * (A + A.T) - p0 * np.eye(3)
+    facets = Facets(mesh)
+    allb = np.nonzero(facets.on_boundary)[0]
+    assert np.abs(surface_traction(mesh, space, facets, x, mu, allb)).max() < 1e-13
+    face = np.nonzero(facets.on_boundary & (np.abs(facets.midpoints[:, 0] - 1.0) < 1e-12))[0]
+    assert np.allclose(surface_traction(mesh, space, facets, x, mu, face), sig @ np.array([1.0, 0, 0]), rtol=0, atol=1e-13)
+    # with a deformation d = B x the stress stays constant: sigma = mu (A F^-1 + F^-T A^T) - p I
+    B = 0.05 * np.array([[1.0, 0.2, 0], [0, -0.5, 0.3], [0.1, 0, 0.4]])
+    interpolate(space, mesh, x, 0, lambda X: X @ B.T)
+    H = A @ np.linalg.inv(np.eye(3) + B)
+    sig = mu * (H + H.T) - p0 * np.eye(3)
+    assert np.allclose(surface_traction(mesh, space, facets, x, mu, face), sig @ np.array([1.0, 0, 0]), rtol=0, atol=1e-13)

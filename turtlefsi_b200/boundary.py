@@ -192,36 +192,24 @@ def _gauss_legendre_01(n):
     return 0.5 * (x + 1.0), 0.5 * w
 
 
-def surface_traction(mesh, space, facets, x, mu_f, facet_ids, npts=6):
+def surface_traction(mesh, space, facets, x, mu_f, facet_ids, degree=10):
     """sum over the given facets of  int sigma(v, p, d, mu_f) * n  dS  (vector [g]), evaluated on
     the "+" cell (cell0) with its outward normal; sigma = mu (grad v F^-1 + F^-T grad v^T) - p I
-    (turtleFSI/modules/common.py:63-81). 2-D only needs a 1-D rule; 3-D uses a triangle rule."""
+    (turtleFSI/modules/common.py:63-81; the drag/lift functionals of TF_fsi.py:229-233, TF_cfd.py:129-131).
+    Facet rule: Gauss-Legendre on edges, the FIAT triangle rule on faces, exact to `degree`."""
     g = mesh.gdim
-    if g != 2:
-        raise NotImplementedError("surface functionals are implemented for 2-D benchmarks")
-    s, w = _gauss_legendre_01(npts)
+    bary, fw = _facet_rule(g, degree)
     total = np.zeros(g)
     ref_vertices = np.vstack([np.zeros(g), np.eye(g)])
+    n2 = space.n2
     for f in facet_ids:
         c = facets.cell0[f]
         k = facets.local0[f]
-        vloc = [v for v in range(g + 1) if v != k]
-        cv = mesh.cells[c]
-        X = mesh.coords[cv]
-        Jg = (X[1:] - X[0]).T
-        K = np.linalg.inv(Jg)
-        a, b = X[vloc[0]], X[vloc[1]]
-        length = np.linalg.norm(b - a)
-        t = (b - a) / length
-        nrm = np.array([t[1], -t[0]])
-        if np.dot(nrm, X[k] - a) > 0:
-            nrm = -nrm
-        ra, rb = ref_vertices[vloc[0]], ref_vertices[vloc[1]]
-        pts = ra[None, :] + s[:, None] * (rb - ra)[None, :]
-        phi2, dphi2, phi1 = tabulate(g, pts)
-        dofs = space.cell_dofs[c]
-        n2 = space.n2
-        u = x[dofs]
+        vloc, meas, nrm = _facet_frame(mesh, c, k)
+        X = mesh.coords[mesh.cells[c]]
+        K = np.linalg.inv((X[1:] - X[0]).T)
+        phi2, dphi2, phi1 = tabulate(g, bary @ ref_vertices[vloc])
+        u = x[space.cell_dofs[c]]
         dco = u[:g * n2].reshape(g, n2)
         vco = u[g * n2:2 * g * n2].reshape(g, n2)
         pco = u[2 * g * n2:2 * g * n2 + g + 1]
@@ -233,7 +221,7 @@ def surface_traction(mesh, space, facets, x, mu_f, facet_ids, npts=6):
         Fi = np.linalg.inv(F)
         H = Gv @ Fi
         sig = mu_f * (H + np.swapaxes(H, 1, 2)) - p[:, None, None] * np.eye(g)
-        total += np.einsum('q,qab,b->a', w * length, sig, nrm)
+        total += np.einsum('q,qab,b->a', fw * meas, sig, nrm)
     return total
 
 
