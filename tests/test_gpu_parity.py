@@ -148,6 +148,17 @@ def test_host_entry_matches_device_calls(tube_params):
     assert np.abs(A2.cpu().numpy() - A.cpu().numpy()).max() < 1e-12 * scale     # atomic order only
     assert np.abs(bh - b.cpu().numpy()).max() < 1e-12 * np.abs(bh).max()
     assert abs(ss - float((bh ** 2).sum())) < 1e-10 * ss
+    # the same through the bitmap-compressed A_pre stream, and with the Jacobian re-used (A untouched)
+    asm.compress_A_pre(A_pre)
+    A3 = asm.new_matrix()
+    bh3 = np.zeros(space.num_dofs)
+    asm.newton_assemble_host(x, x1, g, A_pre, A3, bh3, recompute=True)
+    assert np.abs(A3.cpu().numpy() - A.cpu().numpy()).max() < 1e-12 * scale
+    A3.fill_(7.0)
+    bh4 = np.zeros(space.num_dofs)
+    ss4 = asm.newton_assemble_host(x, x1, g, A_pre, A3, bh4, recompute=False)
+    assert float(A3.min()) == 7.0 and float(A3.max()) == 7.0
+    assert np.abs(bh4 - bh).max() < 1e-12 * np.abs(bh).max() and abs(ss4 / ss - 1) < 1e-12
 
 
 def test_partitioned_assembly_owned_rows_equal_global(tube_params):
@@ -198,6 +209,59 @@ def test_partitioned_assembly_owned_rows_equal_global(tube_params):
         assert np.abs(b[owned] - gb[to_global[owned]]).max() < 1e-12 * np.abs(gb).max()
         covered += int(sel.sum())
     assert covered == GM.shape[0]
+
+
+def test_rcb_partitioned_assembly_owned_rows_equal_global(tube_params):
+    """general-mesh partition (recursive coordinate bisection, partition_rcb.py), ranks emulated on one GPU:
+    owned rows of each rank's local CUDA assembly == rows of the single-domain CUDA assembly, and the halo
+    pack/unpack kernels move the ghost values."""
+    import scipy.sparse as sp
+    import torch
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.mesh import synthetic_state, tube_mesh
+    from turtlefsi_b200.partition_rcb import RankView, rcb_partition
+    from turtlefsi_b200.space import MixedSpace
+    common, regions = tube_params
+    mesh = tube_mesh(4)
+    world = 3
+    gs = MixedSpace(mesh)
+    part = rcb_partition(mesh, world)
+    xg, x1g = synthetic_state(mesh, gs, 2024, h=0.5), synthetic_state(mesh, gs, 2025, h=0.5)
+
+    def assemble(m, space, x, x1):
+        asm = FSIAssembler(m, space, regions, common["dt"], common["theta"], hmin=mesh.hmin())
+        xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+        A = asm.assemble_jacobian(xd, x1d, asm.assemble_A_pre(xd, x1d))
+        b = asm.assemble_residual(xd, x1d)
+        M = sp.csr_matrix((A.cpu().numpy(), asm.colidx.cpu().numpy(), asm.rowptr.cpu().numpy()), shape=(space.num_dofs,) * 2)
+        return asm, M, b.cpu().numpy()
+    _, GA, gb = assemble(mesh, gs, xg, x1g)
+    scale, covered = abs(GA).max(), 0
+    views = [RankView(mesh, r, world, cell_part=part, gspace=gs) for r in range(world)]
+    for v in views:
+        asm, A, b = assemble(v.mesh, v.space, v.scatter_global(xg), v.scatter_global(x1g))
+        own = np.nonzero(v.dof_owned)[0]
+        Ao = A[own].tocoo()
+        lifted = sp.csr_matrix((Ao.data, (v.dof_global[own][Ao.row], v.dof_global[Ao.col])), shape=GA.shape)
+        rows = np.zeros(gs.num_dofs)
+        rows[v.dof_global[own]] = 1.0
+        assert abs(lifted - sp.diags(rows) @ GA).max() < 1e-12 * scale
+        assert np.abs(b[own] - gb[v.dof_global[own]]).max() < 1e-12 * np.abs(gb).max()
+        covered += len(own)
+        # halo kernels: pack what the peers need / unpack into the ghosts (the transport itself is NCCL)
+        send, recv = v.halo_lists(views)
+        xl = torch.as_tensor(v.scatter_global(xg)).cuda()
+        for p_, idx in send.items():
+            buf = torch.empty(len(idx), dtype=torch.float64, device="cuda")
+            it = torch.as_tensor(idx).cuda()
+            asm._check(asm.lib.tfsi_halo_pack(asm.h, xl.data_ptr(), it.data_ptr(), len(idx), buf.data_ptr(), None))
+            assert np.array_equal(buf.cpu().numpy(), xg[v.dof_global[idx]])
+        for p_, idx in recv.items():
+            buf = torch.as_tensor(xg[v.dof_global[idx]] + 1.0).cuda()
+            it = torch.as_tensor(idx).cuda()
+            asm._check(asm.lib.tfsi_halo_unpack(asm.h, xl.data_ptr(), it.data_ptr(), len(idx), buf.data_ptr(), None))
+            assert np.array_equal(xl.cpu().numpy()[idx], xg[v.dof_global[idx]] + 1.0)
+    assert covered == gs.num_dofs
 
 
 @pytest.mark.parametrize("gdim", [2, 3])
@@ -331,3 +395,61 @@ def test_abi_error_behaviour(tube_params):
     far = np.array([0], dtype=np.int32), np.array([space.num_dofs - 1], dtype=np.int32), np.array([1.0])
     with pytest.raises(RuntimeError, match="outside the CSR pattern"):
         asm.set_facet_operator(*far)
+
+
+RCB_NCCL_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from turtlefsi_b200.assembler import FSIAssembler
+from turtlefsi_b200.mesh import tube_mesh, synthetic_state
+from turtlefsi_b200.partition_rcb import HaloExchangeRCB, RankView
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+world = dist.get_world_size()
+regions = [dict(marker=1, kind="fluid", rho=1025.0, mu=3.5e-3),
+           dict(marker=2, kind="solid", rho=1000.0, mu=344827.5862068966, lambda_=3103448.2758620703)]
+mesh = tube_mesh(6)
+view = RankView(mesh, rank, world)
+asm = FSIAssembler(view.mesh, view.space, regions, 1e-3, 0.501, hmin=mesh.hmin())
+xg = synthetic_state(mesh, view.gspace, 2024, h=0.3)
+truth = view.scatter_global(xg)
+x = torch.as_tensor(truth.copy()).cuda()
+x[torch.as_tensor(np.nonzero(~view.dof_owned)[0]).cuda()] = -1.0          # poison the ghosts
+halo = HaloExchangeRCB(asm, *view.halo_lists(), rank)
+halo.exchange(x)
+torch.cuda.synchronize()
+assert np.array_equal(x.cpu().numpy(), truth), "NCCL halo exchange did not restore the ghost values"
+# residual norm over owned dofs + all-reduce == norm of the single-domain residual (computed on rank 0)
+x1 = torch.as_tensor(view.scatter_global(synthetic_state(mesh, view.gspace, 2025, h=0.3))).cuda()
+b = asm.assemble_residual(x, x1)
+ss = (b[torch.as_tensor(view.dof_owned).cuda()] ** 2).sum().reshape(1)
+dist.all_reduce(ss)
+if rank == 0:
+    from turtlefsi_b200.space import MixedSpace
+    g = FSIAssembler(mesh, view.gspace, regions, 1e-3, 0.501)
+    gb = g.assemble_residual(torch.as_tensor(xg).cuda(), torch.as_tensor(synthetic_state(mesh, view.gspace, 2025, h=0.3)).cuda())
+    ref = float((gb ** 2).sum())
+    assert abs(ss.item() / ref - 1) < 1e-12, (ss.item(), ref)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_rcb_two_gpu_nccl_halo_and_norm(tmp_path):
+    """needs two GPUs (skipped on a single-GPU box): RankView + HaloExchangeRCB over NCCL, distributed norm."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "rcb_nccl_worker.py"
+    script.write_text(RCB_NCCL_WORKER % root)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29619", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
