@@ -3,6 +3,8 @@ the Taylor-Green vortex (turtleFSI/problems/TaylorGreen2D.py: analytic u, p :134
 the ORACLE and the reference's Newton loop. The discrete solution converges to the analytic one at
 the Taylor-Hood rates, which pins the fluid forms N1-N5 (fluid.py:32-52), the theta scheme and the
 time-dependent Dirichlet data independently of any FEniCS output."""
+import os
+
 import numpy as np
 
 
@@ -129,3 +131,26 @@ def test_facet_builders_match_the_oracle_closed_forms():
         vol = np.abs(np.linalg.det(Xc[:, 1:] - Xc[:, :1])).sum() / (2 if g == 2 else 6)
         for a in range(g):
             assert abs(l[space.node_dof(1, a)] @ X[:, a] - vol) < 1e-13
+
+
+def test_checkpoint_and_restart_continue_the_run(tmp_path):
+    """problems/__init__.py:183-219, 361-381 + monolithic.py:44-50, 160-162: a run stopped after 4 steps and
+    restarted from its checkpoint ends where the uninterrupted 7-step run ends (to the Newton tolerance: the
+    restart re-assembles the Jacobian on its first step, newtonsolver.py:63)."""
+    full = _run(8, T=0.06)
+    folder = str(tmp_path / "tg")
+    first = _run(8, T=0.03, results_folder=folder, checkpoint_step=1)
+    assert len(first["error_v_list"]) == 4 and os.path.exists(os.path.join(folder, "Checkpoint", "checkpoint_fields.npy"))
+    again = _run(8, T=0.06, restart_folder=folder)
+    assert again["first_step_num"] == 3 and abs(again["t"] - full["t"]) < 1e-12 and len(again["error_v_list"]) == 3
+    a, b = np.asarray(again["dvp_"]["n"]), np.asarray(full["dvp_"]["n"])
+    assert np.abs(a - b).max() < 1e-8 * np.abs(b).max()
+    assert abs(again["error_v_list"][-1] / full["error_v_list"][-1] - 1) < 1e-7
+    # the first Newton iteration of the restarted run rebuilds the Jacobian (counter == first_step_num)
+    assert again["residual_history"][0][:2] == (3, 0)
+    bad = np.load(os.path.join(folder, "Checkpoint", "checkpoint_fields.npy"))
+    bad[5] = np.nan
+    np.save(os.path.join(folder, "Checkpoint", "checkpoint_fields.npy"), bad)
+    import pytest
+    with pytest.raises(ValueError, match="Nan values"):
+        _run(8, T=0.06, restart_folder=folder)

@@ -64,6 +64,15 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
     default_variables = copy.deepcopy(_defaults)
     default_variables.update(mod.set_problem_parameters(default_variables=default_variables) or {})   # monolithic.py:35
     default_variables.update(overrides or {})                                                        # CLI: :38-43
+    if default_variables.get("restart_folder") is not None:                                          # :44-50
+        import json
+        import os
+        rf = str(default_variables["restart_folder"])
+        rf = rf if "Checkpoint" in rf else os.path.join(rf, "Checkpoint")
+        with open(os.path.join(rf, "default_variables.json")) as f:
+            default_variables.update(json.load(f))                    # previous settings, incl. t and counter
+        default_variables.update({k: v for k, v in (overrides or {}).items() if k in ("T", "verbose", "checkpoint_step")})
+        default_variables["restart_folder"] = rf
     ns.update(default_variables)
     ns["default_variables"] = default_variables
     ns.setdefault("results_folder", None)
@@ -86,6 +95,13 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
     solver = importlib.import_module("turtlefsi_b200.modules." + ns["solver"])                        # :153
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
+    # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them
+    from .problems import checkpoint, start_from_checkpoint
+    if ns.get("restart_folder") is not None:
+        start_from_checkpoint(**ns)
+    if ns.get("results_folder") is not None:
+        import os
+        ns.setdefault("checkpoint_folder", os.path.join(str(ns["results_folder"]), "Checkpoint"))
     ns.setdefault("residual_history", [])
     t, T, dt = ns["t"], ns["T"], ns["dt"]
     counter = ns["counter"]
@@ -103,6 +119,9 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
         tmp = mod.post_solve(**ns)
         if tmp is not None:
             ns.update(tmp)
+        if ns.get("checkpoint_folder") is not None and counter % ns["checkpoint_step"] == 0:               # :193-195
+            ns.update(t=t, counter=counter)
+            checkpoint(**ns)
         counter += 1
         if max_steps is not None and counter >= max_steps:
             stop = True

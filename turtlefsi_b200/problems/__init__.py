@@ -1,6 +1,11 @@
 """turtleFSI/problems/__init__.py counterpart: `default_variables` (same keys and values:
-reference :41-117) and the default problem-file hooks (reference :465-523). I/O (XDMF,
-checkpoints, kill/pause files) is out of scope of this repository."""
+reference :41-117), the default problem-file hooks (reference :465-523) and checkpoint / restart
+(reference :183-219, :361-381) with numpy files instead of XDMF/HDF5. Visualisation output and the
+kill/pause files are out of scope of this repository."""
+import json
+import os
+
+import numpy as np
 
 _compiler_parameters = dict({"quadrature_degree": 4, "optimize": True})   # problems/__init__.py:16-17
 
@@ -49,3 +54,31 @@ def post_solve(**namespace):
 
 def finished(**namespace):
     pass
+
+
+def checkpoint(dvp_, default_variables, checkpoint_folder, assembler, **namespace):
+    """reference :183-219: store the current parameters (only keys of default_variables, e.g. t and counter) and
+    the fields of the LAST time level (d1, v1, p1, (w1) = dvp_["n-1"] after the state rotation). Written to a
+    temporary file first, then moved, so that an existing checkpoint is never left corrupted."""
+    default_variables.update((k, namespace[k]) for k in (default_variables.keys() & namespace.keys()))
+    os.makedirs(checkpoint_folder, exist_ok=True)
+    x1 = assembler.to_host(dvp_["n-1"])                      # gathered global vector (collective under torchrun)
+    if getattr(assembler, "rank", 0) != 0:
+        return
+    keep = {k: v for k, v in default_variables.items() if isinstance(v, (int, float, str, bool, list, type(None)))}
+    keep["restart_folder"] = None if keep.get("restart_folder") is None else str(keep["restart_folder"])
+    with open(os.path.join(checkpoint_folder, "default_variables.json"), "w") as f:
+        json.dump(keep, f)
+    tmp = os.path.join(checkpoint_folder, "tmp_fields.npy")
+    np.save(tmp, np.asarray(x1, dtype=np.float64))
+    os.replace(tmp, os.path.join(checkpoint_folder, "checkpoint_fields.npy"))
+
+
+def start_from_checkpoint(dvp_, restart_folder, assembler, **namespace):
+    """reference :361-381: both time levels n and n-1 start from the stored fields."""
+    x1 = np.load(os.path.join(restart_folder, "checkpoint_fields.npy"))
+    if np.isnan(x1).any():
+        raise ValueError("Nan values detected in the checkpoint fields. Stopping simulation.")
+    xd = assembler.to_device(x1)
+    assembler.copy(dvp_["n-1"], xd)
+    assembler.copy(dvp_["n"], xd)
