@@ -313,9 +313,9 @@ def main():
                        "MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_cell": flops_fluid, "cells_per_step": n_fluid, "launches_per_step": kf_n // max(args.steps, 1),
         "ms_per_step": kf_avg_ms,
-        "traffic": 15474.0 * n_fluid,
-        "traffic_note": "bytes per launch = 15.47 KB/cell x fluid cells; per-cell figure from ncu --set full of the same "
-                        "kernel at 6*32^3 (profiles/r1_jac_kernels_raw.csv: dram read 969 MB + write 737 MB for 110263 "
+        "traffic": 15209.0 * n_fluid,
+        "traffic_note": "bytes per launch = 15.21 KB/cell x fluid cells; per-cell figure from ncu --set full of the same "
+                        "kernel at 6*32^3 (profiles/r1_jac_kernels_raw.csv: dram read 969.4 MB + write 707.6 MB for 110263 "
                         "fluid cells); 218 kFLOP/cell -> 14 FLOP/B, above the 5.6 FLOP/B ridge: FP64-bound",
         "hbm": {"achieved": alg_bytes_step / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak,
