@@ -166,6 +166,10 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
                               const double* g_host, const double* Apre_vals, double* A_vals,
                               double* b_host, double* out_sumsq_b, int32_t recompute_jacobian);
 
+/* y = A x on the handle's CSR pattern (device arrays): residual check / iterative refinement around the
+ * linear solve  up_sol.solve(dvp_res.vector(), b)  newtonsolver.py:93 — the solve itself stays outside. */
+int tfsi_csr_matvec(tfsi_handle* h, const double* A_vals, const double* x, double* y, void* stream);
+
 /* Halo update of the Newton iterate before an assembly (multi-GPU): packs x[send_idx] into
  * send_buf and unpacks recv_buf into x[recv_idx]; the NCCL send/recv between the two is
  * issued by the host language (torch.distributed) on the same stream. */

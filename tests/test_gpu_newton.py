@@ -193,3 +193,33 @@ def test_robin_validation_and_inner_pressure_match_oracle():
     assert np.allclose(np.array(ns["probe_v"]), np.array(ref["probe_v"]), rtol=1e-7, atol=1e-12)
     assert np.allclose(np.array(ns["probe_d"]), np.array(ref["probe_d"]), rtol=1e-6, atol=1e-14)
     assert np.abs(np.array(ns["probe_d"])[-1] - np.array(base["probe_d"])[-1]).max() > 1e-8   # the load acts
+
+
+def test_tf_fsi_with_the_device_refactorisation_lu():
+    """the linear solve on the device with the reference's re-use protocol — analysis and pivoting
+    once on the host, numeric re-factorisation (cusolverRf) at every re-assembly, solve-only on re-use; every solve
+    is residual-checked (tfsi_csr_matvec) and refined. Same Newton histories and goldens as with the host LU."""
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.linear_solver import DeviceRfLU
+    made = {}
+
+    def make_asm(mesh, space, regions, ns):
+        return FSIAssembler(mesh, space, regions, ns["dt"], ns["theta"], fluid=ns["fluid"], solid=ns["solid"],
+                            extrapolation=ns["extrapolation"], extrapolation_sub_type=ns["extrapolation_sub_type"],
+                            quad_degree_jacobian=ns["compiler_parameters"]["quadrature_degree"], quad_degree_residual=10,
+                            gravity=ns["gravity"])
+
+    def make_solver(a):
+        made["lu"] = DeviceRfLU(a)
+        return made["lu"]
+    ns = monolithic.run("TF_fsi", make_asm, make_solver, overrides=dict(T=0.05, dt=0.01, theta=0.51, verbose=False))
+    hist, gold = _fixtures()
+    _compare(ns, hist["tf_fsi_biharmonic_default"], ("drag", "lift", "dis_x"))
+    g = gold["TF_fsi"]
+    assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-10 and abs(ns["lift_list"][-1] / g["lift"] - 1) < 1e-7
+    lu = made["lu"]
+    iters = len(ns["residual_history"])
+    assert lu.solves == iters and lu.last_relative_residual < 1e-11
+    assert lu.host_analyses <= 3 < iters                    # pivoting is NOT redone per iteration ...
+    assert lu.refactorizations >= iters                     # ... the numeric factorisation is (TF_fsi: recompute = 1)

@@ -185,6 +185,12 @@ class FSIAssembler:
     def set_facet_load_scale(self, scale):
         self._check(self.lib.tfsi_set_facet_load_scale(self.h, float(scale)))
 
+    def matvec(self, A, x, out=None):
+        """y = A x on the CSR pattern (residual check around the linear solve)."""
+        out = self.new_vector() if out is None else out
+        self._check(self.lib.tfsi_csr_matvec(self.h, _ptr(A), _ptr(x), _ptr(out), self._stream()))
+        return out
+
     def compress_A_pre(self, A_pre):
         """register the non-zeros of A_pre so that A := A_pre costs a zero-fill + sparse overwrite."""
         self._check(self.lib.tfsi_compress_A_pre(self.h, _ptr(A_pre), self._stream()))

@@ -717,6 +717,14 @@ int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream) 
     return 0;
 }
 
+int tfsi_csr_matvec(tfsi_handle* h, const double* A, const double* x, double* y, void* stream) {
+    if (!h || !A || !x || !y) return fail(h, TFSI_ERR_ARG, "null argument");
+    csr_matvec_kernel<<<grid_for(h->N * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->colidx, A, x, y, h->N);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
 int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out, void* stream) {
     if (!h || !v || !out) return fail(h, TFSI_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -906,6 +906,22 @@ __global__ void ident_zeros_kernel(const int64_t* rowptr, const int64_t* diagpos
     }
 }
 
+// y = A x on the handle's CSR pattern, one warp per row (residual check / refinement of the linear solve)
+__global__ void csr_matvec_kernel(const int64_t* rowptr, const int32_t* colidx, const double* A, const double* x,
+                                  double* y, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = wid; r < n; r += nw) {
+        double s = 0.0;
+        for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) s = fma(A[k], x[colidx[k]], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = s;
+    }
+}
+
 __global__ void bc_matrix_kernel(const int64_t* rowptr, const int64_t* diagpos, const int32_t* bc, int64_t nbc, double* A)
 {
     const int lane = threadIdx.x & 31;

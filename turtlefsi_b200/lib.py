@@ -13,7 +13,7 @@ EXPORTS = [
     "tfsi_assemble_A_pre", "tfsi_assemble_jacobian", "tfsi_assemble_residual", "tfsi_ident_zeros",
     "tfsi_set_bc_dofs", "tfsi_apply_bc_matrix", "tfsi_apply_bc_rhs", "tfsi_apply_bc_vec",
     "tfsi_sumsq", "tfsi_newton_assemble_host", "tfsi_halo_pack", "tfsi_halo_unpack",
-    "tfsi_launch_count", "tfsi_probe_fp64_peak", "tfsi_expand_node_pattern", "tfsi_set_profiling", "tfsi_kernel_time", "tfsi_compress_A_pre", "tfsi_compressed_nnz", "tfsi_set_facet_operator", "tfsi_set_facet_operator_prev", "tfsi_set_facet_load", "tfsi_set_facet_load_scale",
+    "tfsi_launch_count", "tfsi_probe_fp64_peak", "tfsi_expand_node_pattern", "tfsi_set_profiling", "tfsi_kernel_time", "tfsi_compress_A_pre", "tfsi_compressed_nnz", "tfsi_set_facet_operator", "tfsi_set_facet_operator_prev", "tfsi_set_facet_load", "tfsi_set_facet_load_scale", "tfsi_csr_matvec",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
     lib.tfsi_set_facet_operator_prev.argtypes = [vp, vp, vp, vp, i64]
     lib.tfsi_set_facet_load.argtypes = [vp, vp, vp, i64]
     lib.tfsi_set_facet_load_scale.argtypes = [vp, C.c_double]
+    lib.tfsi_csr_matvec.argtypes = [vp, vp, vp, vp, vp]
     lib.tfsi_compress_A_pre.argtypes = [vp, vp, vp]
     lib.tfsi_compressed_nnz.argtypes = [vp]
     lib.tfsi_compressed_nnz.restype = i64
