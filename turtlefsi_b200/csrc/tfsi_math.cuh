@@ -473,8 +473,9 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
     for (int s = 0; s <= G; ++s) {
         double x = 0.0;
         if ((s == 0 && (MODE & 2)) || (s > 0 && (MODE & 4))) {
+            x = C[s][1];                                  // not 0.0 + C: `0.0 + x` is a real DADD (signed zero)
 #pragma unroll
-            for (int t = 1; t <= G; ++t) x += C[s][t];
+            for (int t = 2; t <= G; ++t) x += C[s][t];
         }
         Cs[s] = x;
     }
@@ -515,8 +516,9 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
         // ---- stage 2: Z_ij += sum_s T_is W_s
         double Wsum = 0.0;
         if (MODE & 4) {
+            Wsum = W[1];
 #pragma unroll
-            for (int s = 1; s <= G; ++s) Wsum += W[s];
+            for (int s = 2; s <= G; ++s) Wsum += W[s];
         }
 #pragma unroll
         for (int i = 0; i < N2; ++i) {
@@ -543,9 +545,9 @@ TFSI_HD void test_p2_sparse(const Tab& tab, int q, const double (&W)[G + 1], dou
 {
     constexpr int N2 = Dim<G>::N2;
     typedef P2Edges<G> E;
-    double Wsum = 0.0;
+    double Wsum = W[1];
 #pragma unroll
-    for (int s = 1; s <= G; ++s) Wsum += W[s];
+    for (int s = 2; s <= G; ++s) Wsum += W[s];
 #pragma unroll
     for (int i = 0; i < N2; ++i) {
         double z = fma(tab.phi2[q][i], W[0], Z[i]);
