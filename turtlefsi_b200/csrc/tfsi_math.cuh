@@ -479,11 +479,10 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
         }
         Cs[s] = x;
     }
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
+    // stage 1 of column jj + 1 is written BEFORE stage 2 of column jj: with only 3 warps per scheduler the FP64
+    // pipe needs several independent FMAs per warp, and the stage-2 chains of a column all wait for its W
+    auto stage1 = [&](int jj, double (&W)[G + 1]) {
         const int j = HalfCols<G, HALF>::col(jj);
-        double W[G + 1];
-        // ---- stage 1: W_s = sum_t C'_st U_jt
         if (j == 0) {
             const double D = tab.d4[q][0];
             W[0] = 0.0;
@@ -513,28 +512,45 @@ TFSI_HD void block_p2p2(const Tab& tab, int q, const double (&C)[G + 1][G + 1],
                 for (int s = 1; s <= G; ++s) W[s] = (MODE & 4) ? La * C[s][eb] + Lb * C[s][ea] : 0.0;
             }
         }
-        // ---- stage 2: Z_ij += sum_s T_is W_s
+    };
+    auto stage2 = [&](int jj, const double (&W)[G + 1]) {
         double Wsum = 0.0;
         if (MODE & 4) {
             Wsum = W[1];
 #pragma unroll
             for (int s = 2; s <= G; ++s) Wsum += W[s];
         }
+        // one FMA per term (`z += a*b + c*d` would cost DMUL + DFMA + DADD), written breadth-first over the rows
+        // so that the FMAs of one dependency chain are a whole pass apart
+        if (MODE & 3) {
 #pragma unroll
-        for (int i = 0; i < N2; ++i) {
-            // one FMA per term, accumulated in sequence: `z += a*b + c*d` would cost DMUL + DFMA + DADD
-            double z = Z[i][jj];
-            if (MODE & 3) z = fma(tab.phi2[q][i], W[0], z);
-            if (MODE & 4) {
-                if (i == 0) z = fma(-tab.d4[q][0], Wsum, z);
-                else if (i <= G) z = fma(tab.d4[q][i], W[i], z);
-                else {
-                    const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
-                    if (ea == 0) { z = fma(tab.l4[q][0], W[eb], z); z = fma(-tab.l4[q][eb], Wsum, z); }
-                    else { z = fma(tab.l4[q][ea], W[eb], z); z = fma(tab.l4[q][eb], W[ea], z); }
-                }
+            for (int i = 0; i < N2; ++i) Z[i][jj] = fma(tab.phi2[q][i], W[0], Z[i][jj]);
+        }
+        if (MODE & 4) {
+#pragma unroll
+            for (int i = 0; i < N2; ++i) {
+                if (i == 0) Z[i][jj] = fma(-tab.d4[q][0], Wsum, Z[i][jj]);
+                else if (i <= G) Z[i][jj] = fma(tab.d4[q][i], W[i], Z[i][jj]);
+                else Z[i][jj] = fma(tab.l4[q][E::a(i - G - 1)], W[E::b(i - G - 1)], Z[i][jj]);
             }
-            Z[i][jj] = z;
+#pragma unroll
+            for (int i = G + 1; i < N2; ++i) {
+                const int ea = E::a(i - G - 1), eb = E::b(i - G - 1);
+                if (ea == 0) Z[i][jj] = fma(-tab.l4[q][eb], Wsum, Z[i][jj]);
+                else Z[i][jj] = fma(tab.l4[q][eb], W[ea], Z[i][jj]);
+            }
+        }
+    };
+    double Wa[G + 1], Wb[G + 1];
+    stage1(0, Wa);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        if (jj % 2 == 0) {
+            if (jj + 1 < NJ) stage1(jj + 1, Wb);
+            stage2(jj, Wa);
+        } else {
+            if (jj + 1 < NJ) stage1(jj + 1, Wa);
+            stage2(jj, Wb);
         }
     }
 }
