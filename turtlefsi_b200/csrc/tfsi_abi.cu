@@ -111,6 +111,9 @@ int upload(tfsi_handle* h, T** dst, const T* src, size_t n) {
 
 int bind_tables(tfsi_handle* h, cudaStream_t st) {
     if (g_tab_owner == h->id) return 0;
+    // the tabulations live in __constant__ memory shared by all handles of the process: kernels of the previous
+    // owner may still be in flight on another stream, so the (rare) change of owner waits for the device
+    if (g_tab_owner != 0) CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpyToSymbolAsync(c_tabJ, &h->tabJ, sizeof h->tabJ, 0, cudaMemcpyHostToDevice, st));
     CK(h, cudaMemcpyToSymbolAsync(c_tabR, &h->tabR, sizeof h->tabR, 0, cudaMemcpyHostToDevice, st));
     g_tab_owner = h->id;
