@@ -234,3 +234,49 @@ def test_rcb_halo_exchange_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("gdim,world", [(2, 3), (3, 4)])
+def test_rcb_partition_on_unstructured_delaunay_meshes(gdim, world):
+    """arbitrary (Delaunay) meshes: ownership, halo pairing, and owned rows of the partitioned oracle assembly
+    equal to the single-domain rows."""
+    import scipy.sparse as sp
+    from scipy.spatial import Delaunay
+    from oracle.backend import OracleAssembler
+    from tests.conftest import TUBE_PARAMS, TUBE_REGIONS
+    from turtlefsi_b200.mesh import Mesh, synthetic_state
+    rng = np.random.default_rng(5 + gdim)
+    pts = rng.uniform(0, 1, size=(70 if gdim == 2 else 45, gdim))
+    tri = Delaunay(pts)
+    cells = np.sort(tri.simplices, axis=1).astype(np.int32)
+    X = pts[cells]
+    vol = np.abs(np.linalg.det(X[:, 1:] - X[:, :1]))
+    cells = cells[vol > 1e-6]                                                # drop degenerate slivers
+    cen = pts[cells].mean(axis=1)
+    mesh = Mesh(pts, cells, np.where(cen[:, 0] < 0.5, 1, 2).astype(np.int32))
+    part, gs, views = _rcb_views(mesh, world)
+    owned = np.zeros(gs.num_dofs, dtype=int)
+    for v in views:
+        owned[v.dof_global[v.dof_owned]] += 1
+    assert (owned == 1).all()
+    lists = [v.halo_lists() for v in views]
+    for r, v in enumerate(views):
+        for p, idx in lists[r][0].items():
+            assert np.array_equal(v.dof_global[idx], views[p].dof_global[lists[p][1][r]])
+    common = dict(TUBE_PARAMS, hmin=mesh.hmin())
+    degJ, degR = (5, 10) if gdim == 2 else (4, 6)
+    xg, x1g = synthetic_state(mesh, gs, 21, h=0.05), synthetic_state(mesh, gs, 22, h=0.05)
+    G = OracleAssembler(mesh, gs, TUBE_REGIONS, common, degJ, degR, use_c_port=True)
+    GA = sp.csr_matrix((G.assemble_jacobian(xg, x1g, G.assemble_A_pre(xg, x1g)), G.colidx, G.rowptr), shape=(gs.num_dofs,) * 2)
+    gb = G.assemble_residual(xg, x1g)
+    for v in views:
+        L = OracleAssembler(v.mesh, v.space, TUBE_REGIONS, common, degJ, degR, use_c_port=True)
+        x, x1 = v.scatter_global(xg), v.scatter_global(x1g)
+        A = sp.csr_matrix((L.assemble_jacobian(x, x1, L.assemble_A_pre(x, x1)), L.colidx, L.rowptr), shape=(v.space.num_dofs,) * 2)
+        own = np.nonzero(v.dof_owned)[0]
+        Ao = A[own].tocoo()
+        lifted = sp.csr_matrix((Ao.data, (v.dof_global[own][Ao.row], v.dof_global[Ao.col])), shape=GA.shape)
+        rows = np.zeros(gs.num_dofs)
+        rows[v.dof_global[own]] = 1.0
+        assert abs(lifted - sp.diags(rows) @ GA).max() < 1e-12 * abs(GA).max()
+        assert np.abs(L.assemble_residual(x, x1)[own] - gb[v.dof_global[own]]).max() < 1e-12 * np.abs(gb).max()
