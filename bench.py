@@ -342,8 +342,9 @@ def main():
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3,
-                "what": "tfsi_newton_assemble_host: H2D x,x1,g (pinned) -> Jacobian+ident_zeros+BC rows, residual+BC "
-                        "-> D2H b + ||b||^2; A stays in HBM for the device LU"},
+                "what": "tfsi_newton_assemble_host, every copy inside the timed region: H2D x,x1,g (pinned; A := A_pre "
+                        "runs under it) -> residual+BC -> Jacobian kernels+ident_zeros+BC rows (D2H b + ||b||^2 run "
+                        "under them); A stays in HBM for the device LU"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "breakdown_ms": {"jacobian_step": ms_step, "jac_fluid_kernel": kf_avg_ms, "jac_solid_kernel": ks_avg_ms,
