@@ -94,8 +94,7 @@ class DirichletBC:
             for a, b in itertools.combinations(range(g), 2):
                 for lo, hi in zip(np.minimum(fv[:, a], fv[:, b]), np.maximum(fv[:, a], fv[:, b])):
                     pairs.add((int(lo), int(hi)))
-            ek = {(int(a), int(b)): i for i, (a, b) in enumerate(space.edge_vertices)} if not hasattr(space, "_edge_lookup") else space._edge_lookup
-            space._edge_lookup = ek
+            ek = space.edge_lookup()
             eids = np.array(sorted(ek[p] for p in pairs), dtype=np.int64)
             nodes.append(space.edge_node[eids])
         nodes = np.concatenate(nodes)

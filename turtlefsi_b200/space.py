@@ -113,6 +113,12 @@ class MixedSpace:
             return self.node_base[self.vertex_node] + 2 * g
         return 2 * g * self.num_nodes + np.arange(self.num_vertices, dtype=np.int64)
 
+    def edge_lookup(self):
+        """{(lower vertex, higher vertex): edge id}, built once."""
+        if getattr(self, "_edge_lookup", None) is None:
+            self._edge_lookup = {(int(a), int(b)): i for i, (a, b) in enumerate(self.edge_vertices)}
+        return self._edge_lookup
+
     def node_coords(self, mesh):
         X = np.zeros((self.num_nodes, self.gdim))
         X[self.vertex_node] = mesh.coords
