@@ -453,3 +453,25 @@ def test_rcb_two_gpu_nccl_halo_and_norm(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_free_stream_is_preserved_on_a_moving_mesh_cuda(gdim):
+    """size-independent property through the C-ABI: uniform velocity + constant pressure on a moving mesh leave the
+    interior momentum / continuity rows of the residual at round-off (see tests/test_known_answers.py)."""
+    import torch
+    from tests.helpers import square_mesh
+    from tests.test_known_answers import _free_stream_state, _interior_flow_rows
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = square_mesh(6) if gdim == 2 else box_mesh(5)
+    mesh.markers[:] = 1
+    space = MixedSpace(mesh)
+    regions = [dict(marker=1, kind="fluid", rho=1025.0, mu=3.5e-3)]
+    x, x1 = _free_stream_state(mesh, space, 31)
+    asm = FSIAssembler(mesh, space, regions, 1e-3, 0.501, quad_degree_residual=10 if gdim == 2 else 6)
+    b = asm.assemble_residual(torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()).cpu().numpy()
+    rows = _interior_flow_rows(mesh, space)
+    assert len(rows) > 20 and np.abs(b).max() > 1e-3
+    assert np.abs(b[rows]).max() < 1e-12 * np.abs(b).max()

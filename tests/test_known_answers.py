@@ -6,6 +6,7 @@ time-dependent Dirichlet data independently of any FEniCS output."""
 import os
 
 import numpy as np
+import pytest
 
 
 def _run(N, **over):
@@ -154,3 +155,60 @@ def test_checkpoint_and_restart_continue_the_run(tmp_path):
     import pytest
     with pytest.raises(ValueError, match="Nan values"):
         _run(8, T=0.06, restart_folder=folder)
+
+
+def _free_stream_state(mesh, space, seed):
+    """moving mesh (d != d1, both smooth, det F > 0), uniform velocity at both time levels, constant pressure"""
+    from turtlefsi_b200.mesh import synthetic_state
+    g = mesh.gdim
+    x, x1 = synthetic_state(mesh, space, seed, h=0.3), synthetic_state(mesh, space, seed + 1, h=0.3)
+    vel = np.array([0.3, -0.2, 0.5])[:g]
+    for xx in (x, x1):
+        for a in range(g):
+            xx[space.node_dof(1, a)] = vel[a]
+    x[space.vertex_dof_p()] = 7.0
+    x1[space.vertex_dof_p()] = -3.0
+    return x, x1
+
+
+def _interior_flow_rows(mesh, space):
+    from turtlefsi_b200.boundary import Facets
+    f = Facets(mesh)
+    bverts = np.unique(f.vertices[f.on_boundary])
+    on_b = np.zeros(space.num_nodes, dtype=bool)
+    on_b[space.vertex_node[bverts]] = True
+    ev = space.edge_vertices
+    isb = np.zeros(mesh.num_vertices, dtype=bool)
+    isb[bverts] = True
+    on_b[space.edge_node] = isb[ev[:, 0]] & isb[ev[:, 1]]        # conservative: edges between boundary vertices
+    inner = ~on_b
+    rows = [space.node_dof(1, a)[inner] for a in range(mesh.gdim)]
+    vin = np.setdiff1d(np.arange(mesh.num_vertices), bverts)
+    rows.append(np.asarray(space.vertex_dof_p())[vin])
+    return np.concatenate(rows)
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_free_stream_is_preserved_on_a_moving_mesh(gdim):
+    """ALE consistency (a size-independent property of fluid.py:32-56): a uniform velocity with constant pressure
+    solves the equations on ANY moving mesh — N1, N2, N6, L1, L2 vanish with grad v = 0 and v = v1, N5 is
+    tr(adj(F) grad v) = 0, and -p adj(F)^T : grad psi integrates to zero for interior test functions (Piola
+    identity). The momentum and continuity residual rows of interior nodes are therefore zero to round-off."""
+    from oracle.backend import OracleAssembler
+    from tests.conftest import TUBE_PARAMS
+    from tests.helpers import square_mesh
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = square_mesh(6) if gdim == 2 else box_mesh(3)
+    mesh.markers[:] = 1
+    space = MixedSpace(mesh)
+    regions = [dict(marker=1, kind="fluid", rho=1025.0, mu=3.5e-3)]
+    x, x1 = _free_stream_state(mesh, space, 31)
+    rows = _interior_flow_rows(mesh, space)
+    assert len(rows) > 20
+    for use_c in (True, False):
+        ora = OracleAssembler(mesh, space, regions, dict(TUBE_PARAMS), 4, 10 if gdim == 2 else 6, use_c_port=use_c)
+        b = ora.assemble_residual(x, x1)
+        scale = np.abs(b).max()
+        assert scale > 0.1                                     # boundary rows carry the pressure load, d rows the lifting
+        assert np.abs(b[rows]).max() < 1e-12 * scale
