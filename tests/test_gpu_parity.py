@@ -475,3 +475,39 @@ def test_free_stream_is_preserved_on_a_moving_mesh_cuda(gdim):
     rows = _interior_flow_rows(mesh, space)
     assert len(rows) > 20 and np.abs(b).max() > 1e-3
     assert np.abs(b[rows]).max() < 1e-12 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_solid_residual_and_jacobian_are_objective_cuda(gdim):
+    """rigid rotation of any size at rest: the solid residual vanishes (E = 0), and the non-linear Jacobian block
+    psi x delta d annihilates infinitesimal rigid motions of the rotated body (delta d = W R x, W skew)."""
+    import torch
+    from tests.helpers import square_mesh
+    from tests.test_known_answers import _rigid_rotation_state
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.boundary import interpolate
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = square_mesh(5) if gdim == 2 else box_mesh(4)
+    mesh.markers[:] = 2
+    space = MixedSpace(mesh)
+    regions = [dict(marker=2, kind="solid", rho=1000.0, mu=344827.5862068966, lambda_=3103448.2758620703)]
+    x, x1 = _rigid_rotation_state(mesh, space)
+    asm = FSIAssembler(mesh, space, regions, 1e-3, 0.501, quad_degree_residual=10 if gdim == 2 else 6)
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    b = asm.assemble_residual(xd, x1d).cpu().numpy()
+    assert np.abs(b).max() < 1e-12 * 3103448.0
+    # J_nl (psi x delta d) applied to an infinitesimal rotation of the CURRENT configuration: delta d = W (x + d)
+    W = np.array([[0.0, -1.0], [1.0, 0.0]]) if gdim == 2 else np.array([[0.0, -0.3, 0.2], [0.3, 0.0, -0.5], [-0.2, 0.5, 0.0]])
+    X = space.node_coords(mesh)
+    cur = X + np.stack([x[space.node_dof(0, a)] for a in range(gdim)], axis=1)
+    dd = np.zeros(space.num_dofs)
+    interp = cur @ W.T
+    for a in range(gdim):
+        dd[space.node_dof(0, a)] = interp[:, a]
+    A = asm.assemble_jacobian(xd, x1d, None)
+    y = asm.matvec(A, torch.as_tensor(dd).cuda()).cpu().numpy()
+    stretch = np.zeros(space.num_dofs)
+    stretch[space.node_dof(0, 0)] = cur[:, 0]
+    ys = asm.matvec(A, torch.as_tensor(stretch).cuda()).cpu().numpy()
+    assert np.abs(ys).max() > 1.0 and np.abs(y).max() < 1e-11 * np.abs(ys).max()

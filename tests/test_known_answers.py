@@ -212,3 +212,45 @@ def test_free_stream_is_preserved_on_a_moving_mesh(gdim):
         scale = np.abs(b).max()
         assert scale > 0.1                                     # boundary rows carry the pressure load, d rows the lifting
         assert np.abs(b[rows]).max() < 1e-12 * scale
+
+
+def _rigid_rotation_state(mesh, space):
+    """d = (R - I) x + c for a LARGE rotation R, the same at both time levels, zero velocity"""
+    from turtlefsi_b200.boundary import interpolate
+    g = mesh.gdim
+    if g == 2:
+        t = 0.9
+        R = np.array([[np.cos(t), -np.sin(t)], [np.sin(t), np.cos(t)]])
+    else:
+        a, b = 0.7, -1.1
+        Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+        R = Rz @ Rx
+    x = np.zeros(space.num_dofs)
+    interpolate(space, mesh, x, 0, lambda X: X @ (R - np.eye(g)).T + 0.3)
+    return x, x.copy()
+
+
+@pytest.mark.parametrize("gdim", [2, 3])
+def test_solid_residual_is_objective(gdim):
+    """St.Venant-Kirchhoff stress (common.py:104-109) depends on E = (F^T F - I)/2 only: a rigid rotation of any
+    size (F = R) at rest gives E = 0, P = 0 — the whole solid residual (solid.py:41-43, 62-63) vanishes."""
+    from oracle.backend import OracleAssembler
+    from tests.conftest import TUBE_PARAMS
+    from tests.helpers import square_mesh
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = square_mesh(5) if gdim == 2 else box_mesh(3)
+    mesh.markers[:] = 2
+    space = MixedSpace(mesh)
+    regions = [dict(marker=2, kind="solid", rho=1000.0, mu=344827.5862068966, lambda_=3103448.2758620703)]
+    x, x1 = _rigid_rotation_state(mesh, space)
+    for use_c in (True, False):
+        ora = OracleAssembler(mesh, space, regions, dict(TUBE_PARAMS), 4, 10 if gdim == 2 else 6, use_c_port=use_c)
+        b = ora.assemble_residual(x, x1)
+        # scale: the stress a 1 % stretch would produce on one cell face
+        assert np.abs(b).max() < 1e-12 * 3103448.0
+        # ... and a stretch is NOT free
+        xs = x.copy()
+        xs[space.node_dof(0, 0)] *= 1.01
+        assert np.abs(ora.assemble_residual(xs, xs.copy())).max() > 1.0
