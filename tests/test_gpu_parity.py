@@ -511,3 +511,22 @@ def test_solid_residual_and_jacobian_are_objective_cuda(gdim):
     stretch[space.node_dof(0, 0)] = cur[:, 0]
     ys = asm.matvec(A, torch.as_tensor(stretch).cuda()).cpu().numpy()
     assert np.abs(ys).max() > 1.0 and np.abs(y).max() < 1e-11 * np.abs(ys).max()
+
+
+def test_translation_of_the_displacement_changes_nothing_cuda(tube_params):
+    """only grad d and d - d1 enter the forms: a rigid translation added to d at both time levels leaves the CUDA
+    residual and Jacobian unchanged (up to the order of the atomic additions)."""
+    import torch
+    from turtlefsi_b200.assembler import FSIAssembler
+    common, regions = tube_params
+    mesh, space, x, x1 = _setup(3, False, 4)
+    xs, x1s = x.copy(), x1.copy()
+    for a, c in enumerate((0.4, -0.7, 1.3)):
+        xs[space.node_dof(0, a)] += c
+        x1s[space.node_dof(0, a)] += c
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"])
+    t = lambda v: torch.as_tensor(v).cuda()
+    b, bs = asm.assemble_residual(t(x), t(x1)).cpu().numpy(), asm.assemble_residual(t(xs), t(x1s)).cpu().numpy()
+    assert np.abs(b - bs).max() < 1e-12 * np.abs(b).max()
+    A, As = asm.assemble_jacobian(t(x), t(x1), None).cpu().numpy(), asm.assemble_jacobian(t(xs), t(x1s), None).cpu().numpy()
+    assert np.abs(A - As).max() < 1e-12 * np.abs(A).max()

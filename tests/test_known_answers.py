@@ -254,3 +254,24 @@ def test_solid_residual_is_objective(gdim):
         xs = x.copy()
         xs[space.node_dof(0, 0)] *= 1.01
         assert np.abs(ora.assemble_residual(xs, xs.copy())).max() > 1.0
+
+
+def test_translation_of_the_displacement_changes_nothing():
+    """only grad d and d - d1 enter the forms (fluid.py, solid.py, laplace.py): a rigid translation added to d at both
+    time levels leaves residual and Jacobian unchanged (FSI tube, oracle C port)."""
+    from oracle.backend import OracleAssembler
+    from tests.conftest import TUBE_PARAMS, TUBE_REGIONS
+    from turtlefsi_b200.mesh import synthetic_state, tube_mesh
+    from turtlefsi_b200.space import MixedSpace
+    mesh = tube_mesh(3)
+    space = MixedSpace(mesh)
+    x, x1 = synthetic_state(mesh, space, 5, h=0.5), synthetic_state(mesh, space, 6, h=0.5)
+    xs, x1s = x.copy(), x1.copy()
+    for a, c in enumerate((0.4, -0.7, 1.3)):
+        xs[space.node_dof(0, a)] += c
+        x1s[space.node_dof(0, a)] += c
+    ora = OracleAssembler(mesh, space, TUBE_REGIONS, dict(TUBE_PARAMS), 4, 6, use_c_port=True)
+    b, bs = ora.assemble_residual(x, x1), ora.assemble_residual(xs, x1s)
+    assert np.abs(b - bs).max() < 1e-12 * np.abs(b).max()
+    A, As = ora.assemble_jacobian(x, x1), ora.assemble_jacobian(xs, x1s)
+    assert np.abs(A - As).max() < 1e-12 * np.abs(A).max()
