@@ -114,3 +114,19 @@ def test_ident_zeros_hits_exactly_the_empty_rows(big):
     assert np.array_equal(np.sort(rows), expect)
     assert float(A[torch.as_tensor(changed).cuda()].min().item()) == 1.0
     del A, before
+
+
+def test_residual_is_translation_invariant_at_full_size(big):
+    """size-independent property: only grad d and d - d1 enter the forms, so a rigid translation added to d at both
+    time levels leaves the residual of the 2 M-tet FSI tube unchanged (to the order of the atomic additions)."""
+    import torch
+    asm, space = big["asm"], big["space"]
+    xs, x1s = big["xd"].clone(), big["x1d"].clone()
+    for a, c in enumerate((0.4, -0.7, 1.3)):
+        idx = torch.as_tensor(space.node_dof(0, a)).cuda()
+        xs[idx] += c
+        x1s[idx] += c
+    bs = asm.assemble_residual(xs, x1s)
+    torch.cuda.synchronize()
+    scale = float(big["b"].abs().max().item())
+    assert scale > 0 and float((bs - big["b"]).abs().max().item()) < 1e-12 * scale
