@@ -38,6 +38,9 @@ extern "C" {
 #define TFSI_LAPLACE_CONSTANT 0        /* laplace.py:39-40 */
 #define TFSI_LAPLACE_SMALL_CONSTANT 1  /* laplace.py:37-38 */
 #define TFSI_LAPLACE_VOLUME 2          /* laplace.py:35-36 */
+#define TFSI_LAPLACE_VOLUME_CHANGE 3   /* laplace.py:33-34: alfa = 1/J(d^n) in the residual; its Jacobian is part of the
+                                          FROZEN A_pre (newtonsolver.py:26-27): supported for the set-up state d = 0 of
+                                          every shipped problem, where it equals grad(delta d):grad(phi) */
 
 typedef struct tfsi_handle tfsi_handle;
 

@@ -108,18 +108,52 @@ def run_numpy_oracle_elastic():
             "dis_x": [float(v) for v in ns["displacement_x_list"]], "dis_y": [float(v) for v in ns["displacement_y_list"]]}
 
 
+def run_numpy_oracle_volume_change():
+    """test_laplace[volume_change] (tests/test_turtleFSI.py:61-80): alfa = 1/J(d) (laplace.py:33-34) is outside the
+    C port; numpy complex-step oracle, ~2 minutes."""
+    from oracle.backend import OracleAssembler
+    from turtlefsi_b200 import monolithic
+    from turtlefsi_b200.linear_solver import HostLU
+
+    def make_asm(mesh, space, regions, ns):
+        common = dict(dt=ns["dt"], theta=ns["theta"], extrapolation=ns["extrapolation"],
+                      extrapolation_sub_type=ns["extrapolation_sub_type"], fluid=ns["fluid"], solid=ns["solid"],
+                      gravity=ns["gravity"])
+        return OracleAssembler(mesh, space, regions, common, ns["compiler_parameters"]["quadrature_degree"], 10)
+    ns = monolithic.run("TF_fsi", make_asm, lambda a: HostLU(a.rowptr, a.colidx, a.num_dofs),
+                        overrides=dict(T=0.05, dt=0.01, theta=0.51, extrapolation="laplace",
+                                       extrapolation_sub_type="volume_change", verbose=False))
+    return {"problem": "TF_fsi", "overrides": "-e laplace -et volume_change --theta 0.51", "oracle": "numpy complex-step",
+            "residual_history": [[int(c), int(i), float(r), float(rr)] for c, i, r, rr in ns["residual_history"]],
+            "drag": [float(v) for v in ns["drag_list"]], "lift": [float(v) for v in ns["lift_list"]],
+            "dis_x": [float(v) for v in ns["displacement_x_list"]], "dis_y": [float(v) for v in ns["displacement_y_list"]]}
+
+
+SLOW = {"tf_fsi_elastic_numpy_oracle": ("--elastic", run_numpy_oracle_elastic),
+        "tf_fsi_laplace_volume_change_numpy_oracle": ("--volume-change", run_numpy_oracle_volume_change)}
+
+
 if __name__ == "__main__":
+    if "--only-slow" in sys.argv:            # regenerate just the flagged numpy-oracle runs inside the stored file
+        path = os.path.join(HERE, "turek_oracle_histories.json")
+        hist = json.load(open(path))
+        for key, (flag, fn) in SLOW.items():
+            if flag in sys.argv:
+                hist[key] = fn()
+        json.dump(hist, open(path, "w"), indent=1)
+        print("written")
+        sys.exit(0)
     json.dump(GOLDENS, open(os.path.join(HERE, "turek_goldens.json"), "w"), indent=1)
     json.dump(run_oracle_tf_fsi(), open(os.path.join(HERE, "tf_fsi_oracle_history.json"), "w"), indent=1)
     hist = {name: run_oracle(prob, ov) for name, (prob, ov, _) in CASES.items()}
-    if "--elastic" in sys.argv:
-        hist["tf_fsi_elastic_numpy_oracle"] = run_numpy_oracle_elastic()
-    else:   # keep the stored (slow to regenerate) elastic run
-        try:
-            old = json.load(open(os.path.join(HERE, "turek_oracle_histories.json")))
-            if "tf_fsi_elastic_numpy_oracle" in old:
-                hist["tf_fsi_elastic_numpy_oracle"] = old["tf_fsi_elastic_numpy_oracle"]
-        except Exception:
-            pass
+    try:
+        old = json.load(open(os.path.join(HERE, "turek_oracle_histories.json")))
+    except Exception:
+        old = {}
+    for key, (flag, fn) in SLOW.items():     # keep the stored (slow to regenerate) numpy-oracle runs unless asked
+        if flag in sys.argv:
+            hist[key] = fn()
+        elif key in old:
+            hist[key] = old[key]
     json.dump(hist, open(os.path.join(HERE, "turek_oracle_histories.json"), "w"), indent=1)
     print("written")

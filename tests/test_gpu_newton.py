@@ -76,6 +76,17 @@ def test_tf_fsi_other_lifting_variants_hit_reference_goldens(ext, sub):
     assert np.isclose(ns["lift_list"][-1], g["lift"], rtol=1e-4 if ext == "laplace" else 1e-5)
 
 
+def test_tf_fsi_laplace_volume_change():
+    """tests/test_turtleFSI.py:61-80 with "volume_change" (alfa = 1/J(d), laplace.py:33-34): CUDA path vs the stored
+    numpy-oracle run (the C port does not have this variant) and the reference's goldens."""
+    hist, gold = _fixtures()
+    ns = _run_gpu("TF_fsi", theta=0.51, extrapolation="laplace", extrapolation_sub_type="volume_change")
+    _compare(ns, hist["tf_fsi_laplace_volume_change_numpy_oracle"], ("drag", "lift", "dis_x"))
+    g = gold["TF_fsi"]
+    assert np.isclose(ns["displacement_x_list"][-1], g["dis_x"]) and np.isclose(ns["displacement_y_list"][-1], g["dis_y"])
+    assert np.isclose(ns["drag_list"][-1], g["drag"]) and np.isclose(ns["lift_list"][-1], g["lift"], rtol=1e-4)
+
+
 def test_tf_cfd():
     hist, gold = _fixtures()
     ns = _run_gpu("TF_cfd", theta=0.5)

@@ -380,7 +380,11 @@ def test_abi_error_behaviour(tube_params):
         FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="elastic", pattern=(rp, ci))
     with pytest.raises(RuntimeError, match="Could not find extrapolation method"):
         FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="laplace",
-                     extrapolation_sub_type="volume_change", pattern=(rp, ci))
+                     extrapolation_sub_type="volume_chnage", pattern=(rp, ci))
+    vc = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="laplace",
+                      extrapolation_sub_type="volume_change", pattern=(rp, ci))
+    with pytest.raises(RuntimeError, match="set-up state d = 0"):      # frozen A_pre of 1/J(d): d = 0 only
+        vc.assemble_A_pre(torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda())
     # (c) a 15-point Jacobian rule does not fit the shared-memory budget in 3-D: error at assembly
     asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], quad_degree_jacobian=5, pattern=(rp, ci))
     xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()

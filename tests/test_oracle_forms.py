@@ -154,6 +154,19 @@ def test_kernel_math_matches_oracle(emul, g, bih, deg, amp):
                            1, 1, 2 if bih else 1, 0, C.c_double(0.0), C.c_double(0.0), C.c_int64(len(Xs)),
                            _dp(Xs), _dp(us), _dp(u1s), sp.ndof_cell, _dp(Fe))
         assert np.abs(Fe - (Rl + Rn)).max() < 1e-13 * np.abs(Rl + Rn).max()
+        if not bih and kind == 0:
+            # every laplace sub-type of the residual (laplace.py:33-40), incl. "volume_change" alfa = 1/J(d)
+            for code, sub in ((1, "small_constant"), (2, "volume"), (3, "volume_change")):
+                prm2 = oa.region_params(dict(common, extrapolation_sub_type=sub, hmin=0.37), reg)
+                Rl2, Rn2 = cf.residual(reg["kind"], Xs, us, u1s, prm2)
+                Fe2 = np.zeros_like(Rl2)
+                emul.emul_residual(g, len(wts), _dp(pts), _dp(wts), kind, C.c_double(reg["rho"]), C.c_double(reg["mu"]),
+                                   C.c_double(reg.get("lambda_", 0.0)), C.c_double(common["dt"]), C.c_double(common["theta"]),
+                                   1, 1, 1, code, C.c_double(0.37), C.c_double(0.0), C.c_int64(len(Xs)),
+                                   _dp(Xs), _dp(us), _dp(u1s), sp.ndof_cell, _dp(Fe2))
+                assert np.abs(Fe2 - (Rl2 + Rn2)).max() < 1e-13 * np.abs(Rl2 + Rn2).max(), sub
+                nd = g * (6 if g == 2 else 10)                          # the d rows carry the lifting term
+                assert np.abs(Fe2[:, :nd] - Fe[:, :nd]).max() > 1e-3 * np.abs(Fe[:, :nd]).max()
 
 
 @pytest.mark.parametrize("g,n", [(3, 3), (2, 6)])

@@ -106,6 +106,16 @@ def test_stored_elastic_oracle_run_matches_reference_golden():
     assert abs(f["lift"][-1] / g["lift"] - 1) < 1e-8 and abs(f["dis_y"][-1] / g["dis_y"] - 1) < 1e-7
 
 
+def test_stored_volume_change_oracle_run_matches_reference_golden():
+    """test_laplace[volume_change] (tests/test_turtleFSI.py:61-80): alfa = 1/J(d) lives in the numpy oracle (not in
+    the C port); its 2-minute run is stored by `make_goldens.py --only-slow --volume-change` and checked here with
+    the reference's own tolerances (np.isclose; lift rtol 1e-4, :80)."""
+    f, g = _histories()["tf_fsi_laplace_volume_change_numpy_oracle"], _goldens()["TF_fsi"]
+    assert np.isclose(f["dis_x"][-1], g["dis_x"]) and np.isclose(f["dis_y"][-1], g["dis_y"])
+    assert np.isclose(f["drag"][-1], g["drag"]) and np.isclose(f["lift"][-1], g["lift"], rtol=1e-4)
+    assert abs(f["drag"][-1] / g["drag"] - 1) < 1e-7
+
+
 def test_plaza_refinement_properties():
     from turtlefsi_b200.mesh import read_dolfin_xml, refine
     m = read_dolfin_xml(os.path.join(HERE, "golden", "meshes", "TF_cfd.xml.gz"))

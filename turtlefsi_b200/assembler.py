@@ -17,7 +17,7 @@ from . import lib as _lib
 from .quadrature import default_rule
 
 EXT_CODES = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2}
-LAPLACE_SUB = {"constant": 0, "small_constant": 1, "volume": 2}
+LAPLACE_SUB = {"constant": 0, "small_constant": 1, "volume": 2, "volume_change": 3}
 
 
 def _ptr(t):
@@ -49,6 +49,7 @@ class FSIAssembler:
             raise RuntimeError("extrapolation '%s' is not available on the B200 path" % extrapolation)
         if extrapolation == "laplace" and extrapolation_sub_type not in LAPLACE_SUB:
             raise RuntimeError("Could not find extrapolation method {}".format(extrapolation_sub_type))
+        self._volume_change = extrapolation == "laplace" and extrapolation_sub_type == "volume_change"
         if quad_degree_residual is None:
             # assemble(-F) uses the global form-compiler degree; "auto" estimates
             # 10 in 2-D; every 3-D problem file sets 6 (problem_aneu.py:12)
@@ -157,6 +158,11 @@ class FSIAssembler:
 
     # ------------------------------------------------------------------------------------
     def assemble_A_pre(self, x, x1, out=None):
+        if self._volume_change:
+            # d(1/J(d) grad d : grad phi) is frozen in A_pre at the set-up state; the kernel holds its value for d = 0
+            dd = torch.as_tensor(self.space.sub_dofs(0), device=self.device)
+            if float(x[dd].abs().max()) != 0.0:
+                raise RuntimeError("laplace 'volume_change': A_pre is available for the set-up state d = 0 only")
         out = self.new_matrix() if out is None else out
         self._check(self.lib.tfsi_assemble_A_pre(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
         return out

@@ -116,7 +116,7 @@ struct RegionConst {
     int kind;              // 0 fluid, 1 solid
     int fluid_on, solid_on;
     int ext;               // 0 none, 1 laplace, 2 biharmonic
-    int ext_sub;           // laplace: 0 constant, 1 small_constant, 2 volume
+    int ext_sub;           // laplace: 0 constant, 1 small_constant, 2 volume, 3 volume_change
     int pad_;
 };
 
@@ -738,6 +738,11 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
             f.gamma = jw * J * trH;                                                  // N5
         }
         if (rc.ext == 1) {                       // laplace.py:45  alfa grad d : grad phi
+            double al = alfa_cell;
+            if (rc.ext_sub == 3) {               // laplace.py:33-34 "volume_change": alfa = 1 / J(d^n), pointwise
+                double Fi_[G][G];
+                al = 1.0 / inv<G>(F, Fi_);
+            }
 #pragma unroll
             for (int a = 0; a < G; ++a)
 #pragma unroll
@@ -750,7 +755,7 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
                         for (int t = 0; t < G; ++t) gdab += Gd[a][t] * K[t][b];
                         x += K[s][b] * gdab;
                     }
-                    f.phi_grad[a][s] = jw * alfa_cell * x;
+                    f.phi_grad[a][s] = jw * al * x;
                 }
         } else if (rc.ext == 2) {                // biharmonic.py:35-36
             double w[G], Gw[G][G];
