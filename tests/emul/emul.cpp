@@ -118,7 +118,8 @@ void res_cell(const QuadTab<MAXQ_R>& tab, const RegionConst& rc, const double* X
     const bool bih = ndof > 2 * G * N2 + N1;
     for (int q = 0; q < tab.nq; ++q) {
         PointFlux<G> f;
-        residual_point<G>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        if (rc.ext == 1 && rc.ext_sub == 3) residual_point<G, true>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        else residual_point<G>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         for (int c = 0; c < G; ++c)
             for (int i = 0; i < N2; ++i) {
                 double zp = tab.phi2[q][i] * f.psi_val[c], zd = tab.phi2[q][i] * f.phi_val[c], zb = tab.phi2[q][i] * f.beta_val[c];

@@ -278,11 +278,11 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
     return 0;
 }
 
-template <int G, bool BIH, int NC>
+template <int G, bool BIH, int NC, bool VC>
 int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
     typedef ResCfg<G, BIH> R;
     const size_t smem = R::bytes(h->tabR.nq, NC);
-    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const RegionConst& rc = r.rc;
@@ -291,7 +291,7 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
         a.dofs_blk = r.res_dofs_blk;
         KernelTimer kt(h, 2, st);
-        residual_kernel<G, BIH, NC><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
+        residual_kernel<G, BIH, NC, VC><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
     }
@@ -316,8 +316,12 @@ int residual_nc(const tfsi_handle* h) {
 
 template <int G, bool BIH>
 int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
-    if (h->res_nc == 32) return launch_residual_nc<G, BIH, 32>(h, x, x1, b, st);
-    if (h->res_nc == 16) return launch_residual_nc<G, BIH, 16>(h, x, x1, b, st);
+    if (!BIH && h->ext == TFSI_EXT_LAPLACE && h->ext_sub == TFSI_LAPLACE_VOLUME_CHANGE) {      // alfa = 1/J(d)
+        if (h->res_nc == 32) return launch_residual_nc<G, false, 32, true>(h, x, x1, b, st);
+        if (h->res_nc == 16) return launch_residual_nc<G, false, 16, true>(h, x, x1, b, st);
+    }
+    if (h->res_nc == 32) return launch_residual_nc<G, BIH, 32, false>(h, x, x1, b, st);
+    if (h->res_nc == 16) return launch_residual_nc<G, BIH, 16, false>(h, x, x1, b, st);
     return fail(h, TFSI_ERR_UNSUPPORTED, "residual rule with %d points does not fit in shared memory", h->tabR.nq);
 }
 

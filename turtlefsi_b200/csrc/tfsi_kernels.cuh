@@ -661,7 +661,7 @@ template <int G, bool BIH> struct ResCfg {
 // phase 1: warp = row group (field, comp), lane = cell: Z_i = sum_q phi_i f0 + ghat_i . f  (sparse P2 test
 //          functions); with NC = 16 the two half-warps take the even / odd points and are combined by shuffles;
 //          ONE RED per row
-template <int G, bool BIH, int NC>
+template <int G, bool BIH, int NC, bool VC>
 __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(CellArgs a)
 {
     typedef ResCfg<G, BIH> R;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(Ce
         auto cf = [&](int k) { return coef[k * NC + c]; };
         auto cf1 = [&](int k) { return coef1[k * NC + c]; };
         PointFlux<G> f;
-        residual_point<G>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
+        residual_point<G, VC>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
         double* dst = flux + ((size_t)q * NC + c) * FS;
 #pragma unroll
         for (int cc = 0; cc < G; ++cc) {

@@ -626,7 +626,9 @@ template <int G> struct PointFlux {
     double gamma;                        // pressure-test rows
 };
 
-template <int G, class Tab, class CF, class CF1>
+// VC: laplace "volume_change" (alfa = 1/J(d^n), laplace.py:33-34) compiled in; a template flag so that the default
+// instantiation keeps its register allocation
+template <int G, bool VC = false, class Tab, class CF, class CF1>
 TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], double adet,
                             const RegionConst& rc, double alfa_cell, CF cf, CF1 cf1,
                             PointFlux<G>& f)
@@ -739,7 +741,7 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
         }
         if (rc.ext == 1) {                       // laplace.py:45  alfa grad d : grad phi
             double al = alfa_cell;
-            if (rc.ext_sub == 3) {               // laplace.py:33-34 "volume_change": alfa = 1 / J(d^n), pointwise
+            if (VC) {                            // laplace.py:33-34 "volume_change": alfa = 1 / J(d^n), pointwise
                 double Fi_[G][G];
                 al = 1.0 / inv<G>(F, Fi_);
             }
