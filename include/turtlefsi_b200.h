@@ -34,13 +34,16 @@ extern "C" {
 #define TFSI_EXT_NONE 0        /* modules/no_extrapolation.py */
 #define TFSI_EXT_LAPLACE 1     /* modules/laplace.py          */
 #define TFSI_EXT_BIHARMONIC 2  /* modules/biharmonic.py (cell terms) */
+#define TFSI_EXT_ELASTIC 3     /* modules/elastic.py:18-27: J S_linear(d) F^-T : grad(phi), E = 1/CellVolume, nu = 0.25;
+                                  non-linear in d but part of F_fluid_linear: the residual uses the current state,
+                                  its Jacobian is FROZEN in A_pre at the set-up state (newtonsolver.py:26-27) */
 
 #define TFSI_LAPLACE_CONSTANT 0        /* laplace.py:39-40 */
 #define TFSI_LAPLACE_SMALL_CONSTANT 1  /* laplace.py:37-38 */
 #define TFSI_LAPLACE_VOLUME 2          /* laplace.py:35-36 */
 #define TFSI_LAPLACE_VOLUME_CHANGE 3   /* laplace.py:33-34: alfa = 1/J(d^n) in the residual; its Jacobian is part of the
-                                          FROZEN A_pre (newtonsolver.py:26-27): supported for the set-up state d = 0 of
-                                          every shipped problem, where it equals grad(delta d):grad(phi) */
+                                          FROZEN A_pre (newtonsolver.py:26-27), evaluated at the state handed to
+                                          tfsi_assemble_A_pre (d = 0 in every shipped problem, any state supported) */
 
 typedef struct tfsi_handle tfsi_handle;
 
@@ -88,6 +91,13 @@ typedef struct {
     const double* qpts_residual;
     const double* qwts_residual;
     int32_t verify_pattern;   /* 1: check that every cell block fits the CSR pattern    */
+    int32_t borrow_pattern;   /* 1: rowptr / colidx are DEVICE arrays that stay valid (and unchanged) for the life of
+                                 the handle (or until tfsi_release_pattern): no second copy of the 4 B/entry column
+                                 array is made                                                                       */
+    int32_t deterministic;    /* 1: colour-ordered scatter (north_star design point 3): the cells of every region are
+                                 split into colour classes (no two cells of a class share a mesh vertex), one launch
+                                 per class in a fixed order => every CSR entry / residual row receives its additions
+                                 in the same order in every run: bitwise reproducible results                        */
 } tfsi_problem;
 
 /* newtonsolver.py:13-31 (solver_setup): uploads mesh, dofmap, pattern; builds scatter maps. */
@@ -108,6 +118,12 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
  * A_vals [nnz] is overwritten with J_nonlinear(x, x1) + A_pre (A_pre may be NULL = 0). */
 int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1,
                            const double* Apre_vals, double* A_vals, void* stream);
+
+/* The same in two halves, for callers that overlap the halo exchange of the iterate with the x-independent half:
+ * phase 1 = the initialisation A := A_pre only (x, x1 unused, may be NULL), phase 2 = the cell kernels only
+ * (A += J_nonlinear(x, x1)). phase 1 followed by phase 2 on one stream == tfsi_assemble_jacobian. */
+int tfsi_assemble_jacobian_phase(tfsi_handle* h, const double* x, const double* x1,
+                                 const double* Apre_vals, double* A_vals, void* stream, int32_t phase);
 
 /* Fixed LINEAR facet terms of the forms as a sparse operator A_f in COO form (HOST or DEVICE arrays,
  * duplicates are summed): the exterior-facet terms of the biharmonic lifting with
@@ -137,6 +153,29 @@ int tfsi_set_facet_load_scale(tfsi_handle* h, double scale);
  * caller must call it again (or tfsi_assemble_A_pre, which invalidates it) if it changes A_pre. */
 int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre_vals, void* stream);
 int64_t tfsi_compressed_nnz(const tfsi_handle* h);
+/* Pass this as `Apre_vals` to use the registered compressed copy whatever became of the dense array (the caller
+ * may free it: at 6.3 M tets per GPU the dense A_pre would cost 77 GB). A_pre is IMMUTABLE once compressed: after
+ * editing the dense values call tfsi_compress_A_pre again or tfsi_invalidate_A_pre (then the dense pointer is read). */
+#define TFSI_APRE_COMPRESSED ((const double*)(uintptr_t)1)
+int tfsi_invalidate_A_pre(tfsi_handle* h);
+
+/* A = Matrix(A_pre)                                          newtonsolver.py:28
+ * Declares A_vals as the solver's PERSISTENT matrix: it is set to A_pre now (needs tfsi_compress_A_pre), and from
+ * then on tfsi_assemble_jacobian(..., A_vals) re-initialises only the rows that the non-linear forms scatter into
+ * (velocity and pressure rows of active regions: ~half of the entries); all other rows keep what the library left
+ * there — A_pre, or the unit rows written by tfsi_ident_zeros / tfsi_apply_bc_matrix, which are idempotent. The caller
+ * must not write to A_vals itself while it is bound. tfsi_set_bc_dofs, tfsi_compress_A_pre, tfsi_invalidate_A_pre
+ * make the next assembly a full one. */
+int tfsi_bind_matrix(tfsi_handle* h, double* A_vals, void* stream);
+int tfsi_unbind_matrix(tfsi_handle* h);
+/* entries rewritten by an assembly into the bound matrix (reporting) */
+int64_t tfsi_bound_init_entries(const tfsi_handle* h);
+
+/* Frees / forgets the column array (12 GB at 2 M tets) once set-up is complete: afterwards tfsi_assemble_A_pre,
+ * tfsi_set_facet_operator and tfsi_csr_matvec fail with TFSI_ERR_UNSUPPORTED; the hot path does not need it. */
+int tfsi_release_pattern(tfsi_handle* h);
+/* colour classes per region when created with deterministic = 1 (0 otherwise) */
+int32_t tfsi_num_colours(const tfsi_handle* h);
 
 /* b = assemble(-F)                                          newtonsolver.py:86-88 */
 int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b,
@@ -152,9 +191,10 @@ int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc_dofs, int64_t n);
 /* [bc.apply(A) for bc in bcs]            newtonsolver.py:82  zero rows, unit diagonal */
 int tfsi_apply_bc_matrix(tfsi_handle* h, double* A_vals, void* stream);
 /* [bc.apply(b, x) for bc in bcs]         newtonsolver.py:91  b_i = g_i - x_i ; g [n] values */
-int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, void* stream);
+int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, int64_t n, void* stream);
 /* [bc.apply(x) for bc in bcs]            newtonsolver.py:98  x_i = g_i */
-int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream);
+int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, int64_t n, void* stream);
+/* (n = length of g: must equal the size of the set given to tfsi_set_bc_dofs, else TFSI_ERR_ARG) */
 
 /* b.norm('l2') / norm(dvp_res, 'l2')     newtonsolver.py:105-106 ; synchronises, writes the
  * SUM OF SQUARES to *out_sumsq (caller takes sqrt, after an all-reduce when distributed). */
@@ -163,11 +203,13 @@ int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out_sumsq, vo
 /* Host-buffer variants (reference-facing end-to-end call): x, x1 HOST [N]; b_host HOST [N];
  * A_vals stays on the device (consumer is the device sparse LU).  Includes H2D of x, x1, the
  * Jacobian (+A_pre, ident_zeros, BC rows) and residual (+BC) assembly, and D2H of b.
- * g_host: BC values [nbc] or NULL. Synchronous: ordered after the work queued on the legacy default
- * stream, runs on two internal streams (copies under kernels), returns when b_host and A_vals are final. */
+ * g_host: BC values [nbc] or NULL. x1_host may be NULL: the previous time level uploaded by the last call is
+ * re-used (it changes once per time step, not per Newton iteration). Synchronous: ordered after the work queued on
+ * `stream` (the stream on which the caller produced A_pre / A), runs on two internal streams (copies under
+ * kernels), returns when b_host and A_vals are final. */
 int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host,
                               const double* g_host, const double* Apre_vals, double* A_vals,
-                              double* b_host, double* out_sumsq_b, int32_t recompute_jacobian);
+                              double* b_host, double* out_sumsq_b, int32_t recompute_jacobian, void* stream);
 
 /* y = A x on the handle's CSR pattern (device arrays): residual check / iterative refinement around the
  * linear solve  up_sol.solve(dvp_res.vector(), b)  newtonsolver.py:93 — the solve itself stays outside. */

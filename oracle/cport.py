@@ -20,7 +20,41 @@ def build():
     return _PATH
 
 
+_native = None
+
+
+def build_native():
+    """-march=native build for the TIMED CPU baseline, compiled on the machine that runs it (the portable
+    liboracle_assemble.so travels to the GPU box with the repo snapshot; a binary tuned for this container's CPU must
+    not). Falls back to the portable build when the compiler is missing."""
+    global _native
+    if _native is not None:
+        return _native
+    import hashlib
+    import tempfile
+    try:
+        flags = open("/proc/cpuinfo").read().split("flags", 1)[1].split("\n", 1)[0]
+    except Exception:
+        flags = "unknown"
+    src = os.path.join(_HERE, "c", "oracle_assemble.c")
+    tag = hashlib.sha1((flags + open(src).read()).encode()).hexdigest()[:12]
+    out = os.path.join(tempfile.gettempdir(), "tfsi_oracle_native_%s.so" % tag)
+    if not os.path.exists(out):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        tmp = out + ".%d.tmp" % os.getpid()
+        res = subprocess.run([cc, "-O3", "-march=native", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", tmp, src, "-lm"],
+                             capture_output=True)
+        if res.returncode != 0:
+            build()
+            return _PATH
+        os.replace(tmp, out)
+    _native = out
+    return out
+
+
 def load():
+    if _native is not None:
+        return C.CDLL(_native)
     if not os.path.exists(_PATH):
         build()
     return C.CDLL(_PATH)

@@ -112,13 +112,14 @@ void res_cell(const QuadTab<MAXQ_R>& tab, const RegionConst& rc, const double* X
     double K[G][G];
     double adet = cell_geometry<G>(X, K);
     double alfa_cell = rc.alfa;
-    if (rc.ext == 1 && rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
+    if ((rc.ext == 1 && rc.ext_sub == 2) || rc.ext == 3) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
     auto cf = [&](int k) { return u[k]; };
     auto cf1 = [&](int k) { return u1[k]; };
     const bool bih = ndof > 2 * G * N2 + N1;
     for (int q = 0; q < tab.nq; ++q) {
         PointFlux<G> f;
-        if (rc.ext == 1 && rc.ext_sub == 3) residual_point<G, true>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        if (rc.ext == 1 && rc.ext_sub == 3) residual_point<G, LIFT_VOLUME_CHANGE>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        else if (rc.ext == 3) residual_point<G, LIFT_ELASTIC>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         else residual_point<G>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         for (int c = 0; c < G; ++c)
             for (int i = 0; i < N2; ++i) {
@@ -136,9 +137,68 @@ void res_cell(const QuadTab<MAXQ_R>& tab, const RegionConst& rc, const double* X
     }
 }
 
+// phi x delta d block of the frozen non-linear lifting Jacobian (lin_jacobian_kernel, gen_kind 1 | 2) of one cell
+template <int G>
+void lift_cell(const QuadTab<MAXQ_J>& tab, int gen_kind, const double* Xp, const double* u, int ndof, double* Ae)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = HalfCols<G, 0>::NJ;
+    double X[G + 1][G];
+    for (int v = 0; v <= G; ++v) for (int c = 0; c < G; ++c) X[v][c] = Xp[v * G + c];
+    double K[G][G];
+    const double adet = cell_geometry<G>(X, K);
+    const double Ey = 1.0 / (adet / (G == 2 ? 2.0 : 6.0)), nu = 0.25;
+    const double a_lam = nu * Ey / ((1.0 + nu) * (1.0 - 2.0 * nu)), a_mu = Ey / (2.0 * (1.0 + nu));
+    for (int ca = 0; ca < G; ++ca)
+        for (int cb = 0; cb < G; ++cb)
+            for (int half = 0; half < 2; ++half) {
+                double Z[N2][NJ];
+                memset(Z, 0, sizeof Z);
+                for (int q = 0; q < tab.nq; ++q) {
+                    const double jw = tab.w[q] * adet;
+                    double Gp[G][G];
+                    for (int aa = 0; aa < G; ++aa) {
+                        double Gd[G] = {};
+                        for (int j = 0; j < N2; ++j) for (int t = 0; t < G; ++t) Gd[t] += u[aa * N2 + j] * tab.dphi2[q][j][t];
+                        for (int b = 0; b < G; ++b) { double sacc = 0; for (int t = 0; t < G; ++t) sacc += Gd[t] * K[t][b]; Gp[aa][b] = sacc; }
+                    }
+                    double D[G][G][G][G];
+                    lift_flux_derivative<G>(gen_kind, Gp, a_mu, a_lam, D);
+                    double C[G + 1][G + 1];
+                    C[0][0] = 0.0;
+                    for (int s = 0; s < G; ++s) {
+                        C[0][1 + s] = 0; C[1 + s][0] = 0;
+                        for (int t = 0; t < G; ++t) {
+                            double z = 0;
+                            for (int s2 = 0; s2 < G; ++s2) for (int t2 = 0; t2 < G; ++t2) z += K[s][s2] * D[ca][s2][cb][t2] * K[t][t2];
+                            C[1 + s][1 + t] = jw * z;
+                        }
+                    }
+                    if (half == 0) block_p2p2<G, 0, 5>(tab, q, C, Z); else block_p2p2<G, 1, 5>(tab, q, C, Z);
+                }
+                for (int i = 0; i < N2; ++i) for (int jj = 0; jj < NJ; ++jj) {
+                    int j = half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj);
+                    Ae[(ca * N2 + i) * ndof + cb * N2 + j] += Z[i][jj];
+                }
+            }
+}
+
 }  // namespace
 
 extern "C" {
+
+// Ae[nc][ndof][ndof] += phi x delta d block of the non-linear lifting (gen_kind 1 volume_change, 2 elastic) at state u
+int emul_lifting_jacobian(int g, int nq, const double* pts, const double* wts, int gen_kind, int64_t nc, const double* X,
+                          const double* u, int ndof, double* Ae)
+{
+    QuadTab<MAXQ_J> tab;
+    if (tabulate<MAXQ_J>(g, nq, pts, wts, tab)) return -1;
+    for (int64_t c = 0; c < nc; ++c) {
+        if (g == 3) lift_cell<3>(tab, gen_kind, X + c * 12, u + c * ndof, ndof, Ae + c * ndof * ndof);
+        else lift_cell<2>(tab, gen_kind, X + c * 6, u + c * ndof, ndof, Ae + c * ndof * ndof);
+    }
+    return 0;
+}
 
 // Ae[nc][ndof][ndof] += element matrices of J_nonlinear ; X[nc][(g+1)*g], u/u1[nc][ndof]
 int emul_jacobian(int g, int nq, const double* pts, const double* wts, int kind, double rho, double mu,

@@ -32,8 +32,6 @@ def big():
 
 def test_random_rows_against_oracle(big):
     import torch
-    from oracle.forms import CellForms
-    from oracle.assembly import region_params
     mesh, space, asm = big["mesh"], big["space"], big["asm"]
     assert mesh.num_cells == 6 * big["n"] ** 3
     common = dict(dt=bench_const("DT"), theta=bench_const("THETA"), extrapolation="laplace", extrapolation_sub_type="constant")
@@ -43,39 +41,14 @@ def test_random_rows_against_oracle(big):
     r = np.hypot(X[:, 0], X[:, 1])
     picks = np.concatenate([rng.choice(np.nonzero(r < 0.6)[0], 6), rng.choice(np.nonzero(r > 0.9)[0], 6),
                             rng.choice(np.nonzero(np.abs(r - 0.8) < 0.02)[0], 6)])
-    cfJ, cfR = CellForms(3, False, 4), CellForms(3, False, 6)
+    from oracle.spotcheck import check_nodes
     rowptr = asm.rowptr
-    worst_A = worst_b = 0.0
-    for node in picks:
-        cells = np.nonzero((space.cell_nodes == node).any(axis=1))[0]
-        cd = space.cell_dofs[cells].astype(np.int64)
-        Xc = mesh.coords[mesh.cells[cells]]
-        rows = np.arange(space.node_base[node], space.node_base[node] + space.node_ncomp[node])
-        ref_rows = {int(rw): {} for rw in rows}
-        ref_b = {int(rw): 0.0 for rw in rows}
-        for reg in regions:
-            sel = mesh.markers[cells] == reg["marker"]
-            if not sel.any():
-                continue
-            prm = region_params(common, reg)
-            Je = cfJ.jacobian(reg["kind"], Xc[sel], big["x"][cd[sel]], big["x1"][cd[sel]], prm, "all")
-            Rl, Rn = cfR.residual(reg["kind"], Xc[sel], big["x"][cd[sel]], big["x1"][cd[sel]], prm)
-            for ci, dofs in enumerate(cd[sel]):
-                for li, rw in enumerate(dofs):
-                    if int(rw) in ref_rows:
-                        ref_b[int(rw)] -= (Rl + Rn)[ci, li]
-                        acc = ref_rows[int(rw)]
-                        for lj, cl in enumerate(dofs):
-                            acc[int(cl)] = acc.get(int(cl), 0.0) + Je[ci, li, lj]
-        for rw in rows:
-            lo, hi = int(rowptr[rw].item()), int(rowptr[rw + 1].item())
-            cols = asm.colidx[lo:hi].cpu().numpy()
-            vals = big["A"][lo:hi].cpu().numpy()
-            ref = np.array([ref_rows[int(rw)].get(int(c), 0.0) for c in cols])
-            assert set(ref_rows[int(rw)]) <= set(int(c) for c in cols)
-            scale = max(np.abs(ref).max(), 1e-300)
-            worst_A = max(worst_A, np.abs(vals - ref).max() / scale)
-            worst_b = max(worst_b, abs(big["b"][rw].item() - ref_b[int(rw)]))
+
+    def get_row(rw):
+        lo, hi = int(rowptr[rw].item()), int(rowptr[rw + 1].item())
+        return asm.colidx[lo:hi].cpu().numpy(), big["A"][lo:hi].cpu().numpy()
+    worst_A, worst_b, _ = check_nodes(mesh, space, regions, common, big["x"], big["x1"], picks, get_row,
+                                      lambda rw: big["b"][rw].item())
     bscale = float(big["b"].abs().max().item())
     assert worst_A < 1e-12, worst_A
     assert worst_b < 1e-12 * bscale, (worst_b, bscale)

@@ -375,21 +375,25 @@ def test_abi_error_behaviour(tube_params):
     ci2 = np.delete(ci, k)
     with pytest.raises(RuntimeError, match="CSR pattern"):
         FSIAssembler(mesh, space, regions, common["dt"], common["theta"], pattern=(rp2, ci2))
-    # (b) forms outside the kernels' scope are refused, not approximated
+    # (b) unknown lifting names are refused, with the reference's own message for the laplace sub-type (laplace.py:42)
     with pytest.raises(RuntimeError, match="not available on the B200 path"):
-        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="elastic", pattern=(rp, ci))
+        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="plastic", pattern=(rp, ci))
     with pytest.raises(RuntimeError, match="Could not find extrapolation method"):
         FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="laplace",
                      extrapolation_sub_type="volume_chnage", pattern=(rp, ci))
-    vc = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], extrapolation="laplace",
-                      extrapolation_sub_type="volume_change", pattern=(rp, ci))
-    with pytest.raises(RuntimeError, match="set-up state d = 0"):      # frozen A_pre of 1/J(d): d = 0 only
-        vc.assemble_A_pre(torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda())
-    # (c) a 15-point Jacobian rule does not fit the shared-memory budget in 3-D: error at assembly
-    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], quad_degree_jacobian=5, pattern=(rp, ci))
+    # (c) a quadrature rule beyond the table sizes of the kernels: error at creation
+    with pytest.raises(RuntimeError, match="quadrature rule too large"):
+        FSIAssembler(mesh, space, regions, common["dt"], common["theta"], quad_degree_jacobian=8, pattern=(rp, ci))
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], pattern=(rp, ci))
     xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
-    with pytest.raises(RuntimeError, match="shared memory"):
-        asm.assemble_jacobian(xd, x1d, None)
+    # (c2) BC value arrays must match the registered dof set; the compressed-A_pre sentinel needs a registered copy
+    asm.set_bc_dofs(np.array([0, 1, 2], dtype=np.int32))
+    with pytest.raises(RuntimeError, match="BC values"):
+        asm.apply_bc_vec(xd.clone(), torch.zeros(2, dtype=torch.float64, device="cuda"))
+    with pytest.raises(RuntimeError, match="no compressed A_pre"):
+        asm.assemble_jacobian(xd, x1d, "compressed")
+    with pytest.raises(RuntimeError, match="needs a compressed A_pre"):
+        asm.bind_matrix(asm.new_matrix())
     # (d) null pointers
     lib = L.load()
     assert lib.tfsi_assemble_residual(asm.h, None, None, None, None) == -1

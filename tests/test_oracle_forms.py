@@ -169,6 +169,44 @@ def test_kernel_math_matches_oracle(emul, g, bih, deg, amp):
                 assert np.abs(Fe2[:, :nd] - Fe[:, :nd]).max() > 1e-3 * np.abs(Fe[:, :nd]).max()
 
 
+@pytest.mark.parametrize("g,deg,amp", [(3, 4, 0.5), (3, 4, 3.0), (2, 5, 2.0)])
+def test_nonlinear_lifting_math_matches_oracle(emul, g, deg, amp):
+    """elastic lifting (elastic.py:18-27) and laplace "volume_change" (laplace.py:33-34): residual fluxes and the
+    phi x delta d block of the FROZEN A_pre (newtonsolver.py:26-27) at a NON-ZERO set-up state, host-compiled kernel
+    mathematics vs the complex-step oracle."""
+    mesh, sp, x, x1 = _case(g, False, amp)
+    pts, wts = map(np.ascontiguousarray, ft.quadrature(g, deg))
+    cf = CellForms(g, False, deg)
+    X = np.ascontiguousarray(mesh.coords[mesh.cells])
+    u, u1 = np.ascontiguousarray(x[sp.cell_dofs]), np.ascontiguousarray(x1[sp.cell_dofs])
+    reg = TUBE_REGIONS[0]
+    sel = mesh.markers == reg["marker"]
+    Xs, us, u1s = map(np.ascontiguousarray, (X[sel], u[sel], u1[sel]))
+    nd = g * (6 if g == 2 else 10)
+    for ext, sub, ext_code, sub_code, gen_kind in (("elastic", "constant", 3, 0, 2), ("laplace", "volume_change", 1, 3, 1)):
+        common = dict(TUBE_PARAMS, extrapolation=ext, extrapolation_sub_type=sub)
+        prm = oa.region_params(common, reg)
+        Rl, Rn = cf.residual("fluid", Xs, us, u1s, prm)
+        Fe = np.zeros_like(Rl)
+        emul.emul_residual(g, len(wts), _dp(pts), _dp(wts), 0, C.c_double(reg["rho"]), C.c_double(reg["mu"]),
+                           C.c_double(0.0), C.c_double(common["dt"]), C.c_double(common["theta"]),
+                           1, 1, ext_code, sub_code, C.c_double(0.0), C.c_double(0.0), C.c_int64(len(Xs)),
+                           _dp(Xs), _dp(us), _dp(u1s), sp.ndof_cell, _dp(Fe))
+        assert np.abs(Fe - (Rl + Rn)).max() < 1e-13 * np.abs(Rl + Rn).max(), ext
+        Jl = cf.jacobian("fluid", Xs, us, u1s, prm, "lin")[:, :nd, :nd]
+        Ae = np.zeros((len(Xs), sp.ndof_cell, sp.ndof_cell))
+        rc = emul.emul_lifting_jacobian(g, len(wts), _dp(pts), _dp(wts), gen_kind, C.c_int64(len(Xs)), _dp(Xs), _dp(us),
+                                        sp.ndof_cell, _dp(Ae))
+        assert rc == 0
+        scale = np.abs(Jl).max(axis=2, keepdims=True)
+        assert (np.abs(Ae[:, :nd, :nd] - Jl) / scale).max() < 1e-11, ext
+        # the state matters: the block at d = 0 differs
+        Ae0 = np.zeros_like(Ae)
+        emul.emul_lifting_jacobian(g, len(wts), _dp(pts), _dp(wts), gen_kind, C.c_int64(len(Xs)), _dp(Xs), _dp(0 * us),
+                                   sp.ndof_cell, _dp(Ae0))
+        assert np.abs(Ae0 - Ae).max() > 1e-4 * np.abs(Ae).max()
+
+
 @pytest.mark.parametrize("g,n", [(3, 3), (2, 6)])
 def test_c_port_matches_numpy_oracle(g, n):
     mesh = tube_mesh(n) if g == 3 else square_mesh(n)

@@ -16,7 +16,7 @@ import torch
 from . import lib as _lib
 from .quadrature import default_rule
 
-EXT_CODES = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2}
+EXT_CODES = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2, "elastic": 3}
 LAPLACE_SUB = {"constant": 0, "small_constant": 1, "volume": 2, "volume_change": 3}
 
 
@@ -38,7 +38,7 @@ class FSIAssembler:
     def __init__(self, mesh, space, regions, dt, theta, fluid="fluid", solid="solid",
                  extrapolation="laplace", extrapolation_sub_type="constant",
                  quad_degree_jacobian=4, quad_degree_residual=None, gravity=None,
-                 pattern=None, device=None, verify_pattern=1, hmin=None):
+                 pattern=None, device=None, verify_pattern=1, hmin=None, deterministic=False):
         if not torch.cuda.is_available():
             raise RuntimeError("turtlefsi_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -49,7 +49,6 @@ class FSIAssembler:
             raise RuntimeError("extrapolation '%s' is not available on the B200 path" % extrapolation)
         if extrapolation == "laplace" and extrapolation_sub_type not in LAPLACE_SUB:
             raise RuntimeError("Could not find extrapolation method {}".format(extrapolation_sub_type))
-        self._volume_change = extrapolation == "laplace" and extrapolation_sub_type == "volume_change"
         if quad_degree_residual is None:
             # assemble(-F) uses the global form-compiler degree; "auto" estimates
             # 10 in 2-D; every 3-D problem file sets 6 (problem_aneu.py:12)
@@ -98,6 +97,8 @@ class FSIAssembler:
         p.nq_jacobian, p.qpts_jacobian, p.qwts_jacobian = len(self.qJ[1]), self.qJ[0].ctypes.data, self.qJ[1].ctypes.data
         p.nq_residual, p.qpts_residual, p.qwts_residual = len(self.qR[1]), self.qR[0].ctypes.data, self.qR[1].ctypes.data
         p.verify_pattern = int(verify_pattern)
+        p.borrow_pattern = 1          # self.rowptr / self.colidx live as long as the handle: no second copy in HBM
+        p.deterministic = int(bool(deterministic))
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             rc = self.lib.tfsi_create(C.byref(p), C.byref(h))
@@ -105,11 +106,21 @@ class FSIAssembler:
             raise RuntimeError("tfsi_create failed (%d): %s" % (rc, self.lib.tfsi_last_error(None).decode()))
         self.h = h
         self.bc_dofs = None
+        self.num_colours = int(self.lib.tfsi_num_colours(self.h))
 
     # ------------------------------------------------------------------------------------
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError("turtlefsi_b200 (%d): %s" % (rc, self.lib.tfsi_last_error(self.h).decode()))
+
+    def _apre(self, A_pre):
+        """A_pre argument of the C call: a tensor, None, or the string "compressed" (= TFSI_APRE_COMPRESSED: the copy
+        registered by compress_A_pre, whatever became of the dense array)."""
+        if isinstance(A_pre, str):
+            if A_pre != "compressed":
+                raise ValueError(A_pre)
+            return C.c_void_p(_lib.APRE_COMPRESSED)
+        return _ptr(A_pre)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -158,11 +169,6 @@ class FSIAssembler:
 
     # ------------------------------------------------------------------------------------
     def assemble_A_pre(self, x, x1, out=None):
-        if self._volume_change:
-            # d(1/J(d) grad d : grad phi) is frozen in A_pre at the set-up state; the kernel holds its value for d = 0
-            dd = torch.as_tensor(self.space.sub_dofs(0), device=self.device)
-            if float(x[dd].abs().max()) != 0.0:
-                raise RuntimeError("laplace 'volume_change': A_pre is available for the set-up state d = 0 only")
         out = self.new_matrix() if out is None else out
         self._check(self.lib.tfsi_assemble_A_pre(self.h, _ptr(x), _ptr(x1), _ptr(out), self._stream()))
         return out
@@ -202,9 +208,35 @@ class FSIAssembler:
         self._check(self.lib.tfsi_compress_A_pre(self.h, _ptr(A_pre), self._stream()))
         return int(self.lib.tfsi_compressed_nnz(self.h))
 
-    def assemble_jacobian(self, x, x1, A_pre=None, out=None):
+    def invalidate_A_pre(self):
+        """forget the compressed copy (A_pre was edited): the dense array is read again."""
+        self._check(self.lib.tfsi_invalidate_A_pre(self.h))
+
+    def bind_matrix(self, A):
+        """A = Matrix(A_pre) (newtonsolver.py:28): A becomes the persistent solver matrix; later assemblies into it
+        rewrite only the rows the non-linear forms touch."""
+        self._check(self.lib.tfsi_bind_matrix(self.h, _ptr(A), self._stream()))
+        self._bound = A            # keep the tensor alive: the handle holds its address
+        return int(self.lib.tfsi_bound_init_entries(self.h))
+
+    def unbind_matrix(self):
+        self._check(self.lib.tfsi_unbind_matrix(self.h))
+        self._bound = None
+
+    def release_pattern(self):
+        """drop the column array after set-up (A_pre assembled, facet operators set): the hot path does not read it."""
+        self._check(self.lib.tfsi_release_pattern(self.h))
+        self.colidx = None
+
+    def assemble_jacobian(self, x, x1, A_pre=None, out=None, phase=0):
+        """A := A_pre + J_nl(x, x1). phase 1 / 2: only the x-independent initialisation / only the cell kernels
+        (a caller that exchanges halos runs phase 1 under the transfer)."""
         out = self.new_matrix() if out is None else out
-        self._check(self.lib.tfsi_assemble_jacobian(self.h, _ptr(x), _ptr(x1), _ptr(A_pre), _ptr(out), self._stream()))
+        if phase:
+            self._check(self.lib.tfsi_assemble_jacobian_phase(self.h, _ptr(x), _ptr(x1), self._apre(A_pre), _ptr(out),
+                                                              self._stream(), int(phase)))
+        else:
+            self._check(self.lib.tfsi_assemble_jacobian(self.h, _ptr(x), _ptr(x1), self._apre(A_pre), _ptr(out), self._stream()))
         return out
 
     def assemble_residual(self, x, x1, out=None):
@@ -224,10 +256,10 @@ class FSIAssembler:
         self._check(self.lib.tfsi_apply_bc_matrix(self.h, _ptr(A), self._stream()))
 
     def apply_bc_rhs(self, b, x, g):
-        self._check(self.lib.tfsi_apply_bc_rhs(self.h, _ptr(b), _ptr(x), _ptr(g), self._stream()))
+        self._check(self.lib.tfsi_apply_bc_rhs(self.h, _ptr(b), _ptr(x), _ptr(g), 0 if g is None else len(g), self._stream()))
 
     def apply_bc_vec(self, x, g):
-        self._check(self.lib.tfsi_apply_bc_vec(self.h, _ptr(x), _ptr(g), self._stream()))
+        self._check(self.lib.tfsi_apply_bc_vec(self.h, _ptr(x), _ptr(g), 0 if g is None else len(g), self._stream()))
 
     def sumsq(self, v):
         out = C.c_double(0.0)
@@ -238,11 +270,12 @@ class FSIAssembler:
         return float(np.sqrt(self.sumsq(v)))
 
     def newton_assemble_host(self, x_host, x1_host, g_host, A_pre, A, b_host, recompute=True):
-        """reference-facing end-to-end call with HOST vectors (pinned torch tensors or numpy)."""
+        """reference-facing end-to-end call with HOST vectors (pinned torch tensors or numpy). x1_host=None re-uses
+        the previous time level uploaded by the last call (it changes once per time step)."""
         ss = C.c_double(0.0)
         self._check(self.lib.tfsi_newton_assemble_host(
-            self.h, _ptr(x_host), _ptr(x1_host), _ptr(g_host), _ptr(A_pre), _ptr(A), _ptr(b_host),
-            C.byref(ss), int(bool(recompute))))
+            self.h, _ptr(x_host), _ptr(x1_host), _ptr(g_host), self._apre(A_pre), _ptr(A), _ptr(b_host),
+            C.byref(ss), int(bool(recompute)), self._stream()))
         return ss.value
 
 

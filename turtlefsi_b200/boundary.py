@@ -172,18 +172,43 @@ def l2_norm(mesh, space, x, field):
     return float(np.sqrt(total))
 
 
+class BCPlan:
+    """index plan of a BC list, built once: sorted unique dofs and, for each, the position of the LAST BC
+    entry that sets it (DOLFIN applies the list sequentially, later BCs win: newtonsolver.py:82,91,98).
+    Per time step only values() of the BC objects is evaluated."""
+
+    def __init__(self, bcs):
+        self.bcs = list(bcs)
+        cat = [np.asarray(d, dtype=np.int64) for bc in self.bcs for d in bc.dofs]
+        self.sizes = [len(d) for d in cat]
+        alld = np.concatenate(cat) if cat else np.zeros(0, dtype=np.int64)
+        # last occurrence of every dof: first occurrence in the reversed list
+        udofs, first_rev = np.unique(alld[::-1], return_index=True)
+        self.dofs = udofs.astype(np.int32)
+        self.pick = (len(alld) - 1 - first_rev).astype(np.int64)
+
+    def matches(self, bcs):
+        """True when `bcs` has the same objects-with-same-dof-arrays structure (cheap check per step)."""
+        bcs = list(bcs)
+        if len(bcs) != len(self.bcs):
+            return False
+        sizes = [len(d) for bc in bcs for d in bc.dofs]
+        if sizes != self.sizes:
+            return False
+        return all(a is b or all(np.array_equal(x, y) for x, y in zip(a.dofs, b.dofs)) for a, b in zip(bcs, self.bcs))
+
+    def values(self, bcs=None):
+        bcs = self.bcs if bcs is None else bcs
+        cat = [np.asarray(v, dtype=np.float64) for bc in bcs for v in bc.values()]
+        allv = np.concatenate(cat) if cat else np.zeros(0)
+        return allv[self.pick]
+
+
 def flatten_bcs(bcs):
-    """(dofs int32 [n], values [n]) in list order, later BCs win on shared dofs (DOLFIN applies
+    """(dofs int32 [n] ascending, values [n]) in list order, later BCs win on shared dofs (DOLFIN applies
     the list sequentially: newtonsolver.py:82,91,98)."""
-    table = {}
-    for bc in bcs:
-        for d, v in zip(bc.dofs, bc.values()):
-            for i, x in zip(d, v):
-                table[int(i)] = float(x)
-    dofs = np.fromiter(table.keys(), dtype=np.int64, count=len(table))
-    vals = np.fromiter(table.values(), dtype=np.float64, count=len(table))
-    order = np.argsort(dofs)
-    return dofs[order].astype(np.int32), vals[order]
+    plan = BCPlan(bcs)
+    return plan.dofs, plan.values()
 
 
 def _gauss_legendre_01(n):

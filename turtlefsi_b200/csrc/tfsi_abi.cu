@@ -23,6 +23,7 @@ thread_local std::string g_create_error;
 struct Region {
     RegionConst rc;
     int32_t marker;
+    int32_t colour;       // colour class (deterministic mode), else 0
     int64_t ncells;
     int32_t* cell_list;   // device
     uint16_t* rank_blk;   // device, per CTA batch (Jacobian kernels)
@@ -31,36 +32,27 @@ struct Region {
     size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
 };
 
-// One kernel launch of the Jacobian assembly: a slice of one region's cell list. `init_end` is
-// the end (in CSR entries) of the rows that may be touched by this and all earlier segments; A is
-// initialised (A := A_pre or 0) up to there on the copy stream before the segment starts, so the
-// HBM-bound initialisation overlaps with the FP64-bound kernels of earlier segments.
-struct Segment {
-    int region;
-    int64_t first, count;
-    int64_t init_end;
-};
-constexpr int JAC_CHUNKS = 8;
-
 }  // namespace
 
 struct tfsi_handle {
-    int gdim, biharmonic, ndof, ndof_pad, n2, n1;
+    int dev;                  // CUDA device the handle lives on (every entry switches to it)
+    int gdim, biharmonic, ndof, n2, n1;
     int64_t nv, nc, N, nnz;
     double *coords;
-    int32_t *cell_vertices, *cell_dofs, *colidx, *bc_dofs;
-    int64_t *rowptr, *diagpos;
-    uint16_t* rank;
-    double* scratch;          // 1 double (sumsq)
+    int32_t *cell_vertices, *cell_dofs, *bc_dofs;
+    const int32_t* colidx;    // owned copy, or the caller's array (borrow_pattern)
+    const int64_t* rowptr;
+    int own_pattern;
+    int64_t* diagpos;
+    double* scratch;          // 1 double (sumsq) + error counters
     int res_nc;               // cells per residual CTA (32 | 16 | 0 = unsupported rule)
-    double *hx, *hx1, *hb, *hg;   // device staging for the _host entry
+    double *hx, *hx1, *hb, *hg;   // device staging for the _host entry (allocated at its first use)
+    int hx1_valid;
     int64_t nbc;
     std::vector<Region> regions;
-    std::vector<Segment> segments;
-    cudaStream_t copy_stream, main_stream;   // copy_stream: A_pre chunks / host-entry H2D+D2H; main_stream: host-entry kernels
+    int ncolours;
+    cudaStream_t copy_stream, main_stream;   // host entry: copy_stream = H2D / D2H, main_stream = kernels
     cudaEvent_t ev_entry, ev_in, ev_b;
-    cudaEvent_t ev_begin, ev_seg[2 * JAC_CHUNKS * 8];
-    int n_ev;
     QuadTab<MAXQ_J> tabJ;
     QuadTab<MAXQ_R> tabR;
     int fluid_on, solid_on, ext, ext_sub;
@@ -74,6 +66,8 @@ struct tfsi_handle {
     // compressed copy of A_pre (tfsi_compress_A_pre)
     const double* cpre_src;
     uint32_t* cpre_bitmap; int64_t* cpre_base; double* cpre_val; int64_t cpre_nnz, cpre_words;
+    // persistent matrix (tfsi_bind_matrix): word mask of the rows J_nl scatters into
+    double* bound_A; int bound_dirty; uint32_t* tmask; int64_t bound_entries;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
@@ -82,7 +76,7 @@ struct tfsi_handle {
 namespace {
 
 int g_next_id = 1;
-int g_tab_owner = 0;     // id of the handle whose tables sit in constant memory
+int g_tab_owner[64] = {0};     // per device: id of the handle whose tables sit in constant memory
 
 int fail(tfsi_handle* h, int code, const char* fmt, ...) {
     char buf[512];
@@ -102,6 +96,15 @@ int fail(tfsi_handle* h, int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                       \
     } while (0)
 
+// every ABI entry runs on the handle's device, whatever the caller's current device is
+struct DeviceGuard {
+    int prev; bool switched;
+    explicit DeviceGuard(const tfsi_handle* h) : prev(-1), switched(false) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->dev) { cudaSetDevice(h->dev); switched = true; }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 template <class T>
 int upload(tfsi_handle* h, T** dst, const T* src, size_t n) {
     CK(h, cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
@@ -110,21 +113,22 @@ int upload(tfsi_handle* h, T** dst, const T* src, size_t n) {
 }
 
 int bind_tables(tfsi_handle* h, cudaStream_t st) {
-    if (g_tab_owner == h->id) return 0;
-    // the tabulations live in __constant__ memory shared by all handles of the process: kernels of the previous
+    int& owner = g_tab_owner[h->dev & 63];
+    if (owner == h->id) return 0;
+    // the tabulations live in __constant__ memory shared by all handles on this device: kernels of the previous
     // owner may still be in flight on another stream, so the (rare) change of owner waits for the device
-    if (g_tab_owner != 0) CK(h, cudaDeviceSynchronize());
+    if (owner != 0) CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpyToSymbolAsync(c_tabJ, &h->tabJ, sizeof h->tabJ, 0, cudaMemcpyHostToDevice, st));
     CK(h, cudaMemcpyToSymbolAsync(c_tabR, &h->tabR, sizeof h->tabR, 0, cudaMemcpyHostToDevice, st));
-    g_tab_owner = h->id;
+    owner = h->id;
     return 0;
 }
 
 CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* x, const double* x1, double* out) {
     CellArgs a;
     a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
-    a.rank = h->rank; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.rank_blk = r.rank_blk; a.dofs_blk = r.dofs_blk;
-    a.ncell_region = r.ncells; a.ndof = h->ndof; a.ndof_pad = h->ndof_pad; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
+    a.colidx = h->colidx; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.rank_blk = r.rank_blk; a.dofs_blk = r.dofs_blk;
+    a.ncell_region = r.ncells; a.ndof = h->ndof; a.q0 = 0; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
     return a;
 }
 
@@ -141,101 +145,85 @@ int grid_for(int64_t n, int block, int sm) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm * 16));
 }
 
+// largest chunk of quadrature points whose per-point table fits the shared memory of one CTA
+template <class SM> int max_points(int nq) {
+    int m = nq;
+    while (m > 1 && SM::bytes(m) > 227 * 1024) --m;
+    return m;
+}
+
+// J_nl of one region: one launch per chunk of the quadrature rule (the REDs of the chunks add up). The rule of the
+// headline config (Keast 14-point, 3-D) runs in one launch of the compile-time-sized instantiation.
 template <int G>
-int launch_jacobian_segment(tfsi_handle* h, const Segment& sg, const double* x, const double* x1, double* A, cudaStream_t st) {
-    const Region& r = h->regions[sg.region];
-    CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, A);
-    a.cell_list = r.cell_list + sg.first;
-    a.ncell_region = sg.count;
-    {
-        const int nc_ = (r.rc.kind == TFSI_KIND_FLUID) ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
-        a.rank_blk = r.rank_blk + (size_t)(sg.first / nc_) * r.rank_blk_elems;
-        a.dofs_blk = r.dofs_blk + (size_t)(sg.first / nc_) * r.dofs_blk_elems;
-    }
+int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, const double* x1, double* A, cudaStream_t st) {
+    const int nq = h->tabJ.nq;
+    CellArgs a = cell_args(h, r, nq, x, x1, A);
     const bool is_fluid = r.rc.kind == TFSI_KIND_FLUID;
     const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
-    const int grid = (int)((sg.count + ncta - 1) / ncta);
-    if (r.rc.kind == TFSI_KIND_FLUID) {
-        KernelTimer kt(h, 0, st);
-        size_t smem = FluidJac<G>::SM::bytes(a.nq);
-        if (smem > 227 * 1024)
-            return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian rule with %d points needs %zu B of shared memory", a.nq, smem);
-        // compile-time quadrature size for the rule of the headline config (Keast 14-point)
-        if (G == 3 && a.nq == 14) {
-            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_fluid_kernel<G, 14><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
+    const int grid = (int)((r.ncells + ncta - 1) / ncta);
+    const int chunk = is_fluid ? max_points<typename FluidJac<G>::SM>(nq) : max_points<typename SolidJac<G>::SM>(nq);
+    const int nchunk = (nq + chunk - 1) / chunk;
+    for (int c = 0; c < nchunk; ++c) {
+        a.q0 = (int)((int64_t)nq * c / nchunk);
+        a.nq = (int)((int64_t)nq * (c + 1) / nchunk) - a.q0;           // balanced chunks, each <= chunk
+        KernelTimer kt(h, is_fluid ? 0 : 1, st);
+        if (is_fluid) {
+            const size_t smem = FluidJac<G>::SM::bytes(a.nq);
+            if (smem > 227 * 1024)
+                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
+            if (G == 3 && nq == 14) {
+                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_fluid_kernel<G, 14><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
+            } else {
+                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
+            }
         } else {
-            CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
+            const size_t smem = SolidJac<G>::SM::bytes(a.nq);
+            if (G == 3 && nq == 14) {
+                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
+            } else {
+                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jac_solid_kernel<G, 0><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
+            }
         }
-    } else {
-        KernelTimer kt(h, 1, st);
-        size_t smem = SolidJac<G>::SM::bytes(a.nq);
-        if (G == 3 && a.nq == 14) {
-            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
-        } else {
-            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G, 0><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
-        }
+        h->launches++;
+        CK(h, cudaGetLastError());
     }
-    h->launches++;
-    CK(h, cudaGetLastError());
     return 0;
 }
 
-// A := (A_pre | 0) + J_nl, initialisation pipelined with the segment kernels (see Segment).
+// A := (A_pre | 0) + J_nl.
 // phase 0: everything; 1: only the x-independent initialisation A := A_pre; 2: only the cell kernels
 // (the host entry runs phase 1 under the H2D copy of x)
 int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st, int phase = 0) {
-    const bool use_compressed = Apre && Apre == h->cpre_src && h->segments.size() <= h->regions.size();
-    if (use_compressed || phase != 0) {
-        // A := A_pre as zero-fill + sparse overwrite (one kernel, whole matrix), then the cell kernels
-        if (phase != 2) {
-            if (use_compressed) {
-                bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
-                    h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A);
-                CK(h, cudaGetLastError());
-            } else if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (Apre == TFSI_APRE_COMPRESSED && !h->cpre_bitmap)
+        return fail(h, TFSI_ERR_ARG, "TFSI_APRE_COMPRESSED given but no compressed A_pre is registered (tfsi_compress_A_pre)");
+    const bool use_compressed = h->cpre_bitmap && Apre && (Apre == TFSI_APRE_COMPRESSED || Apre == h->cpre_src);
+    if (phase != 2) {
+        // A := A_pre streamed ONCE from the bitmap-compressed copy (zero-fill + packed non-zeros); into the bound
+        // matrix only the rows that the cell kernels scatter into are rewritten
+        if (use_compressed) {
+            const bool partial = A == h->bound_A && h->tmask && !h->bound_dirty;
+            bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
+                h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A, partial ? h->tmask : nullptr);
+            CK(h, cudaGetLastError());
+            if (A == h->bound_A) h->bound_dirty = 0;
+        } else {
+            if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
             else CK(h, cudaMemsetAsync(A, 0, (size_t)h->nnz * sizeof(double), st));
-            h->launches++;
+            if (A == h->bound_A) h->bound_dirty = 1;      // not A_pre-initialised by the compressed copy
         }
-        if (phase == 1) return 0;
-        for (const Segment& sg : h->segments) {
-            const Region& r = h->regions[sg.region];
-            if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
-            int rc = h->gdim == 3 ? launch_jacobian_segment<3>(h, sg, x, x1, A, st) : launch_jacobian_segment<2>(h, sg, x, x1, A, st);
-            if (rc) return rc;
-        }
-        return 0;
-    }
-    CK(h, cudaEventRecord(h->ev_begin, st));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_begin, 0));
-    auto init = [&](int64_t lo, int64_t hi) -> int {
-        if (hi <= lo) return 0;
-        if (Apre) CK(h, cudaMemcpyAsync(A + lo, Apre + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, h->copy_stream));
-        else CK(h, cudaMemsetAsync(A + lo, 0, (size_t)(hi - lo) * sizeof(double), h->copy_stream));
         h->launches++;
-        return 0;
-    };
-    int64_t done = 0;
-    int ev = 0;
-    for (const Segment& sg : h->segments) {
-        if (sg.init_end > done) {
-            if (int rc = init(done, sg.init_end)) return rc;
-            done = sg.init_end;
-            CK(h, cudaEventRecord(h->ev_seg[ev], h->copy_stream));
-            CK(h, cudaStreamWaitEvent(st, h->ev_seg[ev], 0));
-            ev++;
-        }
-        const Region& r = h->regions[sg.region];
+    }
+    if (phase == 1) return 0;
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
         if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
-        int rc = h->gdim == 3 ? launch_jacobian_segment<3>(h, sg, x, x1, A, st) : launch_jacobian_segment<2>(h, sg, x, x1, A, st);
+        int rc = h->gdim == 3 ? launch_jacobian_region<3>(h, r, x, x1, A, st) : launch_jacobian_region<2>(h, r, x, x1, A, st);
         if (rc) return rc;
     }
-    if (int rc = init(done, h->nnz)) return rc;
-    CK(h, cudaEventRecord(h->ev_seg[ev], h->copy_stream));
-    CK(h, cudaStreamWaitEvent(st, h->ev_seg[ev], 0));
     return 0;
 }
 
@@ -250,15 +238,22 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
         la.nblk = 0;
         auto add = [&](int to, int tr, int mk, double cm, double ck, int per_vol) {
             LinBlock b; b.test_off = to; b.trial_off = tr; b.mass_kind = mk; b.cm = cm; b.ck = ck;
-            b.ck_per_volume = per_vol; b.pad_ = 0; b.pad2_ = 0;
+            b.ck_per_volume = per_vol; b.pad_ = 0; b.gen_kind = 0;
             la.blk[la.nblk++] = b;
         };
         const RegionConst& rc = r.rc;
         if (rc.kind == TFSI_KIND_FLUID) {
             if (rc.fluid_on) add(off_v, off_v, 2, rc.c1lin, 0.0, 0);                  // fluid.py:33
-            if (rc.ext == TFSI_EXT_LAPLACE)                                             // laplace.py:45
+            if (rc.ext == TFSI_EXT_LAPLACE && rc.ext_sub == TFSI_LAPLACE_VOLUME_CHANGE) {  // laplace.py:33-34, frozen at x
+                add(off_d, off_d, 0, 0.0, 0.0, 0);
+                la.blk[la.nblk - 1].gen_kind = 1;
+            } else if (rc.ext == TFSI_EXT_LAPLACE)                                      // laplace.py:45
                 add(off_d, off_d, 0, 0.0, rc.ext_sub == TFSI_LAPLACE_VOLUME ? 1.0 : rc.alfa,
                     rc.ext_sub == TFSI_LAPLACE_VOLUME);
+            if (rc.ext == TFSI_EXT_ELASTIC) {                                           // elastic.py:24-25, frozen at x
+                add(off_d, off_d, 0, 0.0, 0.0, 0);
+                la.blk[la.nblk - 1].gen_kind = 2;
+            }
             if (rc.ext == TFSI_EXT_BIHARMONIC) {                                        // biharmonic.py:35-36
                 add(off_w, off_w, 1, rc.alfa, 0.0, 0);
                 add(off_w, off_d, 0, 0.0, -rc.alfa, 0);
@@ -278,11 +273,11 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
     return 0;
 }
 
-template <int G, bool BIH, int NC, bool VC>
+template <int G, bool BIH, int NC, int LIFT>
 int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
     typedef ResCfg<G, BIH> R;
     const size_t smem = R::bytes(h->tabR.nq, NC);
-    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const RegionConst& rc = r.rc;
@@ -291,7 +286,7 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
         a.dofs_blk = r.res_dofs_blk;
         KernelTimer kt(h, 2, st);
-        residual_kernel<G, BIH, NC, VC><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
+        residual_kernel<G, BIH, NC, LIFT><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
     }
@@ -317,11 +312,15 @@ int residual_nc(const tfsi_handle* h) {
 template <int G, bool BIH>
 int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
     if (!BIH && h->ext == TFSI_EXT_LAPLACE && h->ext_sub == TFSI_LAPLACE_VOLUME_CHANGE) {      // alfa = 1/J(d)
-        if (h->res_nc == 32) return launch_residual_nc<G, false, 32, true>(h, x, x1, b, st);
-        if (h->res_nc == 16) return launch_residual_nc<G, false, 16, true>(h, x, x1, b, st);
+        if (h->res_nc == 32) return launch_residual_nc<G, false, 32, LIFT_VOLUME_CHANGE>(h, x, x1, b, st);
+        if (h->res_nc == 16) return launch_residual_nc<G, false, 16, LIFT_VOLUME_CHANGE>(h, x, x1, b, st);
     }
-    if (h->res_nc == 32) return launch_residual_nc<G, BIH, 32, false>(h, x, x1, b, st);
-    if (h->res_nc == 16) return launch_residual_nc<G, BIH, 16, false>(h, x, x1, b, st);
+    if (!BIH && h->ext == TFSI_EXT_ELASTIC) {                                                   // elastic.py
+        if (h->res_nc == 32) return launch_residual_nc<G, false, 32, LIFT_ELASTIC>(h, x, x1, b, st);
+        if (h->res_nc == 16) return launch_residual_nc<G, false, 16, LIFT_ELASTIC>(h, x, x1, b, st);
+    }
+    if (h->res_nc == 32) return launch_residual_nc<G, BIH, 32, LIFT_DEFAULT>(h, x, x1, b, st);
+    if (h->res_nc == 16) return launch_residual_nc<G, BIH, 16, LIFT_DEFAULT>(h, x, x1, b, st);
     return fail(h, TFSI_ERR_UNSUPPORTED, "residual rule with %d points does not fit in shared memory", h->tabR.nq);
 }
 
@@ -341,23 +340,57 @@ int64_t tfsi_launch_count(const tfsi_handle* h) { return h ? h->launches : -1; }
 
 void tfsi_destroy(tfsi_handle* h) {
     if (!h) return;
-    cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs); cudaFree(h->colidx);
-    cudaFree(h->rowptr); cudaFree(h->diagpos); cudaFree(h->rank); cudaFree(h->bc_dofs); cudaFree(h->scratch);
+    DeviceGuard dg(h);
+    cudaFree(h->coords); cudaFree(h->cell_vertices); cudaFree(h->cell_dofs);
+    if (h->own_pattern) { cudaFree((void*)h->colidx); cudaFree((void*)h->rowptr); }
+    cudaFree(h->diagpos); cudaFree(h->bc_dofs); cudaFree(h->scratch);
     cudaFree(h->hx); cudaFree(h->hx1); cudaFree(h->hb); cudaFree(h->hg);
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals); cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
-    cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
+    cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val); cudaFree(h->tmask);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
-    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
-    for (int i = 0; i < h->n_ev; ++i) cudaEventDestroy(h->ev_seg[i]);
-    if (g_tab_owner == h->id) g_tab_owner = 0;
+    for (auto& v : h->ev) for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (g_tab_owner[h->dev & 63] == h->id) g_tab_owner[h->dev & 63] = 0;
     delete h;
 }
+
+namespace {
+
+// Greedy colouring of the cells of one region: two cells conflict when they share a mesh VERTEX (then, and only
+// then, they share P2 nodes / CSR entries). A cell takes the least-used colour that none of its vertices has seen
+// (balanced classes: every class is one kernel launch); a new colour is opened when all are taken.
+// Returns the colour of every listed cell; ncol = number of classes.
+std::vector<int> colour_cells(const int32_t* cell_vertices, int nvpc, int64_t nv, const std::vector<int32_t>& list, int& ncol) {
+    constexpr int W = 4;                                    // up to 256 colours
+    std::vector<uint64_t> vmask((size_t)nv * W, 0);
+    std::vector<int64_t> used;
+    std::vector<int> colour(list.size(), 0);
+    for (size_t k = 0; k < list.size(); ++k) {
+        const int32_t* v = cell_vertices + (size_t)list[k] * nvpc;
+        uint64_t forb[W] = {0, 0, 0, 0};
+        for (int i = 0; i < nvpc; ++i) for (int w = 0; w < W; ++w) forb[w] |= vmask[(size_t)v[i] * W + w];
+        int best = -1;
+        for (int c = 0; c < (int)used.size(); ++c)
+            if (!((forb[c >> 6] >> (c & 63)) & 1ull) && (best < 0 || used[c] < used[best])) best = c;
+        if (best < 0) {
+            if ((int)used.size() >= 64 * W) { ncol = -1; return colour; }
+            best = (int)used.size();
+            used.push_back(0);
+        }
+        used[best]++;
+        colour[k] = best;
+        for (int i = 0; i < nvpc; ++i) vmask[(size_t)v[i] * W + (best >> 6)] |= 1ull << (best & 63);
+    }
+    ncol = (int)used.size();
+    return colour;
+}
+
+}  // namespace
 
 int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     if (!p || !out) return fail(nullptr, TFSI_ERR_ARG, "null argument");
@@ -372,24 +405,27 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->gdim = g; h->biharmonic = p->biharmonic ? 1 : 0;
     h->n1 = g + 1; h->n2 = (g == 2) ? 6 : 10;
     h->ndof = (h->biharmonic ? 3 : 2) * g * h->n2 + h->n1;
-    h->ndof_pad = (h->ndof + 7) & ~7;
     h->nv = p->num_vertices; h->nc = p->num_cells; h->N = p->num_dofs;
-    h->coords = nullptr; h->cell_vertices = h->cell_dofs = h->colidx = h->bc_dofs = nullptr;
-    h->rowptr = h->diagpos = nullptr; h->rank = nullptr; h->scratch = nullptr;
-    h->hx = h->hx1 = h->hb = h->hg = nullptr;
-    h->nbc = 0; h->launches = 0; h->profiling = 0;
-    h->copy_stream = h->main_stream = nullptr; h->ev_begin = h->ev_entry = h->ev_in = h->ev_b = nullptr; h->n_ev = 0;
+    h->coords = nullptr; h->cell_vertices = h->cell_dofs = h->bc_dofs = nullptr;
+    h->colidx = nullptr; h->rowptr = nullptr; h->own_pattern = 1;
+    h->diagpos = nullptr; h->scratch = nullptr;
+    h->hx = h->hx1 = h->hb = h->hg = nullptr; h->hx1_valid = 0;
+    h->nbc = 0; h->launches = 0; h->profiling = 0; h->ncolours = 0;
+    h->copy_stream = h->main_stream = nullptr; h->ev_entry = h->ev_in = h->ev_b = nullptr;
     h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
     h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
     h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0; h->fl_scale = 1.0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
+    h->bound_A = nullptr; h->bound_dirty = 0; h->tmask = nullptr; h->bound_entries = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (h->ext < 0 || h->ext > TFSI_EXT_ELASTIC) { delete h; return fail(nullptr, TFSI_ERR_ARG, "unknown extrapolation code %d", h->ext); }
+    h->dev = 0;
+    cudaGetDevice(&h->dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
 
 #define CKC(call) do { int rc_ = (call); if (rc_) { g_create_error = h->err; tfsi_destroy(h); return rc_; } } while (0)
+    auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
     if (tabulate<MAXQ_J>(g, p->nq_jacobian, p->qpts_jacobian, p->qwts_jacobian, h->tabJ) ||
         tabulate<MAXQ_R>(g, p->nq_residual, p->qpts_residual, p->qwts_residual, h->tabR)) {
         tfsi_destroy(h);
@@ -398,93 +434,84 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     CKC(upload(h, &h->coords, p->coords, (size_t)h->nv * g));
     CKC(upload(h, &h->cell_vertices, p->cell_vertices, (size_t)h->nc * (g + 1)));
     CKC(upload(h, &h->cell_dofs, p->cell_dofs, (size_t)h->nc * h->ndof));
-    CKC(upload(h, &h->rowptr, p->rowptr, (size_t)h->N + 1));
+    if (p->borrow_pattern) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, p->colidx) != cudaSuccess || pa.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            tfsi_destroy(h);
+            return fail(nullptr, TFSI_ERR_ARG, "borrow_pattern needs DEVICE arrays rowptr / colidx");
+        }
+        h->own_pattern = 0; h->rowptr = p->rowptr; h->colidx = p->colidx;
+    } else {
+        int64_t* rp = nullptr;
+        CKC(upload(h, &rp, p->rowptr, (size_t)h->N + 1));
+        h->rowptr = rp;
+    }
     {
         int64_t nnz = 0;
-        cudaError_t e = cudaMemcpy(&nnz, h->rowptr + h->N, sizeof nnz, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(&nnz, h->rowptr + h->N, sizeof nnz, cudaMemcpyDefault);
         if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "rowptr readback: %s", cudaGetErrorString(e)); }
         h->nnz = nnz;
     }
-    CKC(upload(h, &h->colidx, p->colidx, (size_t)h->nnz));
-    {
-        auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
-        CKC(cka(cudaMalloc((void**)&h->diagpos, (size_t)h->N * sizeof(int64_t))));
-        CKC(cka(cudaMalloc((void**)&h->rank, (size_t)h->nc * h->n2 * h->ndof_pad * sizeof(uint16_t))));
-        CKC(cka(cudaMalloc((void**)&h->scratch, 64)));
-        CKC(cka(cudaMalloc((void**)&h->hx, (size_t)h->N * sizeof(double))));
-        CKC(cka(cudaMalloc((void**)&h->hx1, (size_t)h->N * sizeof(double))));
-        CKC(cka(cudaMalloc((void**)&h->hb, (size_t)h->N * sizeof(double))));
+    if (!p->borrow_pattern) {
+        int32_t* ci = nullptr;
+        CKC(upload(h, &ci, p->colidx, (size_t)h->nnz));
+        h->colidx = ci;
     }
-    // regions: host pass over the markers
+    CKC(cka(cudaMalloc((void**)&h->diagpos, (size_t)h->N * sizeof(int64_t))));
+    CKC(cka(cudaMalloc((void**)&h->scratch, 64)));
+    // regions: host pass over the markers (and, for the colour-ordered scatter, over the cell vertices)
     {
         std::vector<int32_t> marker((size_t)h->nc);
         cudaError_t e = cudaMemcpy(marker.data(), p->cell_marker, (size_t)h->nc * sizeof(int32_t), cudaMemcpyDefault);
         if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "marker copy: %s", cudaGetErrorString(e)); }
+        std::vector<int32_t> cv;
+        if (p->deterministic) {
+            cv.resize((size_t)h->nc * (g + 1));
+            e = cudaMemcpy(cv.data(), p->cell_vertices, cv.size() * sizeof(int32_t), cudaMemcpyDefault);
+            if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "cell copy: %s", cudaGetErrorString(e)); }
+        }
         for (int i = 0; i < p->num_regions; ++i) {
             const tfsi_region& rg = p->regions[i];
             Region r;
-            r.marker = rg.marker;
+            r.marker = rg.marker; r.colour = 0;
             r.rc = make_region_const(rg.kind, rg.rho, rg.mu, rg.lambda, p->dt, p->theta, p->fluid_on, p->solid_on,
                                      p->extrapolation, p->extrapolation_sub_type, p->hmin, p->has_gravity ? p->gravity : 0.0);
+            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
-            r.ncells = (int64_t)list.size();
-            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
-            CKC(upload(h, &r.cell_list, list.data(), list.size()));
-            h->regions.push_back(r);
-        }
-    }
-    // launch segments + initialisation frontier (host pass over the dof map)
-    {
-        std::vector<int32_t> cd((size_t)h->nc * h->ndof);
-        std::vector<int64_t> rp((size_t)h->N + 1);
-        cudaError_t e = cudaMemcpy(cd.data(), h->cell_dofs, cd.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(rp.data(), h->rowptr, rp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "segment planning: %s", cudaGetErrorString(e)); }
-        std::vector<std::vector<int32_t>> lists(h->regions.size());
-        {
-            std::vector<int32_t> marker((size_t)h->nc);
-            cudaMemcpy(marker.data(), p->cell_marker, (size_t)h->nc * sizeof(int32_t), cudaMemcpyDefault);
-            for (int64_t c = 0; c < h->nc; ++c)
-                for (size_t r = 0; r < h->regions.size(); ++r)
-                    if (marker[(size_t)c] == h->regions[r].marker) { lists[r].push_back((int32_t)c); break; }
-        }
-        // measured on B200 (DESIGN.md "what did not work"): overlapping the copy with the cell kernels
-        // slows the kernels by the same amount (their REDs share L2/HBM with the copy), so one
-        // segment per region is used; the pipelined path is kept for finer experiments.
-        const int nch = (getenv("TFSI_JAC_CHUNKS") ? atoi(getenv("TFSI_JAC_CHUNKS")) : 1);
-        int64_t frontier = -1;
-        for (int c = 0; c < nch; ++c)
-            for (size_t r = 0; r < h->regions.size(); ++r) {
-                const int64_t n = (int64_t)lists[r].size();
-                const bool flr = h->regions[r].rc.kind == TFSI_KIND_FLUID;
-                const int ncta = (h->gdim == 3) ? (flr ? FluidCfg<3>::L::NC : SolidCfg<3>::L::NC)
-                                                : (flr ? FluidCfg<2>::L::NC : SolidCfg<2>::L::NC);   // boundaries on CTA batches
-                int64_t lo = (n * c / nch) / ncta * ncta, hi = (c == nch - 1) ? n : (n * (c + 1) / nch) / ncta * ncta;
-                if (hi <= lo) continue;
-                for (int64_t k = lo; k < hi; ++k) {
-                    const int32_t* d = cd.data() + (size_t)lists[r][(size_t)k] * h->ndof;
-                    for (int j = 0; j < h->ndof; ++j) if (d[j] > frontier) frontier = d[j];
-                }
-                Segment sg; sg.region = (int)r; sg.first = lo; sg.count = hi - lo; sg.init_end = rp[(size_t)frontier + 1];
-                h->segments.push_back(sg);
+            if (!p->deterministic) {
+                r.ncells = (int64_t)list.size();
+                CKC(upload(h, &r.cell_list, list.data(), list.size()));
+                h->regions.push_back(r);
+                continue;
             }
-        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming);
-        cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming);
-        h->n_ev = (int)h->segments.size() + 1;
-        if (h->n_ev > 2 * JAC_CHUNKS * 8) { h->n_ev = 0; tfsi_destroy(h); return fail(nullptr, TFSI_ERR_UNSUPPORTED, "too many regions"); }
-        for (int i = 0; i < h->n_ev; ++i) cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming);
+            int ncol = 0;
+            std::vector<int> col = colour_cells(cv.data(), g + 1, h->nv, list, ncol);
+            if (ncol < 0) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_UNSUPPORTED, "more than 256 colour classes"); }
+            h->ncolours = std::max(h->ncolours, ncol);
+            std::vector<std::vector<int32_t>> cls((size_t)ncol);
+            for (size_t k = 0; k < list.size(); ++k) cls[(size_t)col[k]].push_back(list[k]);
+            for (int c = 0; c < ncol; ++c) {
+                Region rcpy = r;
+                rcpy.colour = c;
+                rcpy.ncells = (int64_t)cls[(size_t)c].size();
+                CKC(upload(h, &rcpy.cell_list, cls[(size_t)c].data(), cls[(size_t)c].size()));
+                h->regions.push_back(rcpy);
+            }
+        }
     }
-    // scatter maps
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->main_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming);
+    // pattern checks + diagonal positions
+    int* derr = reinterpret_cast<int*>(h->scratch + 1);
     {
-        int* derr = reinterpret_cast<int*>(h->scratch + 1);
         cudaMemset(derr, 0, sizeof(int));
         const int64_t total = h->nc * h->n2 * h->ndof;
-        build_rank_kernel<<<grid_for(total, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, h->nc, h->n2, h->ndof, h->ndof_pad, derr);
+        check_pattern_kernel<<<grid_for(total, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->nc, h->n2, h->ndof, derr);
         diagpos_kernel<<<grid_for(h->N, 256, h->sm_count), 256>>>(h->rowptr, h->colidx, h->diagpos, h->N, derr);
         int herr = 0;
         cudaError_t e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
@@ -502,14 +529,14 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             CKC(upload(h, &dnol, nol.data(), nol.size()));
             const int64_t tot2 = h->nc * h->ndof * h->ndof;
             const int64_t stride = (p->verify_pattern > 1) ? p->verify_pattern : 1;
-            verify_rank_kernel<<<grid_for(tot2 / stride + 1, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, h->rank, dnol, h->nc, h->n2, h->ndof, h->ndof_pad, stride, derr);
+            verify_rank_kernel<<<grid_for(tot2 / stride + 1, 256, h->sm_count), 256>>>(h->cell_dofs, h->rowptr, h->colidx, dnol, h->nc, h->n2, h->ndof, stride, derr);
             e = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
             cudaFree(dnol);
             if (e != cudaSuccess) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_CUDA, "verify kernel: %s", cudaGetErrorString(e)); }
             if (herr) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_PATTERN, "CSR pattern is not a union of dense cell blocks with node-uniform column sets (%d mismatches)", herr); }
         }
     }
-    // per-CTA-batch blocked copies for the Jacobian kernels (bulk-copy / coalesced staging)
+    // per-CTA-batch scatter ranks and blocked dof copies for the cell kernels (bulk-copy / coalesced staging)
     h->res_nc = residual_nc(h);
     for (Region& r : h->regions) {
         if (r.ncells == 0) continue;
@@ -523,12 +550,11 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         r.rank_blk_elems = rbytes / sizeof(uint16_t);
         r.dofs_blk_elems = (size_t)ncoef * ncta;
         const int64_t nb = (r.ncells + ncta - 1) / ncta;
-        auto cka = [&](cudaError_t e) { if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return TFSI_ERR_CUDA; } return 0; };
         CKC(cka(cudaMalloc((void**)&r.rank_blk, (size_t)nb * rbytes)));
         CKC(cka(cudaMemset(r.rank_blk, 0, (size_t)nb * rbytes)));
         CKC(cka(cudaMalloc((void**)&r.dofs_blk, (size_t)nb * r.dofs_blk_elems * sizeof(int32_t))));
         build_rank_blocked_kernel<<<grid_for(nb * h->n2 * ncols * ncta, 256, h->sm_count), 256>>>(
-            h->rank, r.cell_list, r.ncells, h->n2, h->ndof_pad, ncols, ncta, rks, r.rank_blk_elems, r.rank_blk);
+            h->cell_dofs, h->rowptr, h->colidx, r.cell_list, r.ncells, h->ndof, h->n2, ncols, ncta, rks, r.rank_blk_elems, r.rank_blk, derr);
         build_dofs_blocked_kernel<<<grid_for(nb * ncoef * ncta, 256, h->sm_count), 256>>>(
             h->cell_dofs, r.cell_list, r.ncells, h->ndof, ncoef, ncta, r.dofs_blk);
         if (h->res_nc) {                                     // residual kernel: [ndof][res_nc] per batch
@@ -537,16 +563,34 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             build_dofs_blocked_kernel<<<grid_for(nbr * h->ndof * h->res_nc, 256, h->sm_count), 256>>>(
                 h->cell_dofs, r.cell_list, r.ncells, h->ndof, h->ndof, h->res_nc, r.res_dofs_blk);
         }
+    }
+    {
+        int herr = 0;
         CKC(cka(cudaDeviceSynchronize()));
+        CKC(cka(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost)));
+        if (herr) { tfsi_destroy(h); return fail(nullptr, TFSI_ERR_PATTERN, "%d scatter ranks could not be resolved in the CSR pattern", herr); }
     }
 #undef CKC
     *out = h;
     return TFSI_OK;
 }
 
+int32_t tfsi_num_colours(const tfsi_handle* h) { return h ? h->ncolours : -1; }
+
+int tfsi_release_pattern(tfsi_handle* h) {
+    if (!h) return TFSI_ERR_ARG;
+    DeviceGuard dg(h);
+    CK(h, cudaDeviceSynchronize());
+    if (h->own_pattern) cudaFree((void*)h->colidx);
+    h->colidx = nullptr;
+    return 0;
+}
+
 int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, double* Apre, void* stream) {
     if (!h || !x || !x1 || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
-    if (Apre == h->cpre_src) h->cpre_src = nullptr;     // values change: compressed copy is stale
+    if (!h->colidx) return fail(h, TFSI_ERR_UNSUPPORTED, "the column array was released (tfsi_release_pattern)");
+    DeviceGuard dg(h);
+    if (Apre == h->cpre_src) { h->cpre_src = nullptr; h->bound_dirty = 1; }     // values change: compressed copy is stale
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(Apre, 0, (size_t)h->nnz * sizeof(double), st));
@@ -561,16 +605,28 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
 
 int tfsi_assemble_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, void* stream) {
     if (!h || !x || !x1 || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    DeviceGuard dg(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     return launch_jacobian(h, x, x1, Apre, A, st);
 }
 
+int tfsi_assemble_jacobian_phase(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A,
+                                 void* stream, int32_t phase) {
+    if (!h || !A || phase < 1 || phase > 2 || (phase == 2 && (!x || !x1))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = bind_tables(h, st)) return rc;
+    return launch_jacobian(h, x, x1, Apre, A, st, phase);
+}
+
 int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n) {
     if (!h || n < 0 || (n && (!rows || !cols || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     h->fo_rows = h->fo_cols = nullptr; h->fo_pos = nullptr; h->fo_vals = nullptr; h->fo_n = 0;
     if (n == 0) return 0;
+    if (!h->colidx) return fail(h, TFSI_ERR_UNSUPPORTED, "the column array was released (tfsi_release_pattern)");
     if (int rc = upload(h, &h->fo_rows, rows, (size_t)n)) return rc;
     if (int rc = upload(h, &h->fo_cols, cols, (size_t)n)) return rc;
     if (int rc = upload(h, &h->fo_vals, vals, (size_t)n)) return rc;
@@ -587,6 +643,7 @@ int tfsi_set_facet_operator(tfsi_handle* h, const int32_t* rows, const int32_t* 
 
 int tfsi_set_facet_operator_prev(tfsi_handle* h, const int32_t* rows, const int32_t* cols, const double* vals, int64_t n) {
     if (!h || n < 0 || (n && (!rows || !cols || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
     cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals);
     h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
     if (n == 0) return 0;
@@ -601,6 +658,7 @@ int tfsi_set_facet_operator_prev(tfsi_handle* h, const int32_t* rows, const int3
 
 int tfsi_set_facet_load(tfsi_handle* h, const int32_t* dofs, const double* vals, int64_t n) {
     if (!h || n < 0 || (n && (!dofs || !vals))) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
     cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
     h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0;
     if (n == 0) return 0;
@@ -618,12 +676,23 @@ int tfsi_set_facet_load_scale(tfsi_handle* h, double scale) {
     return 0;
 }
 
-int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
-    if (!h || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
-    cudaStream_t st = (cudaStream_t)stream;
+int tfsi_invalidate_A_pre(tfsi_handle* h) {
+    if (!h) return TFSI_ERR_ARG;
+    DeviceGuard dg(h);
+    CK(h, cudaDeviceSynchronize());
     h->cpre_src = nullptr;
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
-    h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr;
+    h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
+    h->bound_dirty = 1;
+    return 0;
+}
+
+int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
+    if (!h || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
+    DeviceGuard dg(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(h, cudaStreamSynchronize(st));
+    if (int rc = tfsi_invalidate_A_pre(h)) return rc;
     const int64_t nwords = (h->nnz + 31) / 32, ngroups = (nwords + 31) / 32;
     if (ngroups + 1 > INT32_MAX) return fail(h, TFSI_ERR_UNSUPPORTED, "matrix too large for the bitmap scan");
     h->cpre_words = nwords;
@@ -653,8 +722,56 @@ int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
 
 int64_t tfsi_compressed_nnz(const tfsi_handle* h) { return h ? h->cpre_nnz : -1; }
 
+int tfsi_bind_matrix(tfsi_handle* h, double* A, void* stream) {
+    if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (!h->cpre_bitmap) return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix needs a compressed A_pre (tfsi_compress_A_pre)");
+    DeviceGuard dg(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ngroups = (h->cpre_words + 31) / 32;
+    if (!h->tmask) {
+        // rows that J_nl scatters into: velocity + pressure rows of active fluid cells, velocity rows of active solid cells
+        uint8_t* flag = nullptr;
+        CK(h, cudaMalloc((void**)&flag, std::max<size_t>((size_t)h->N, 1)));
+        CK(h, cudaMemsetAsync(flag, 0, (size_t)h->N, st));
+        const int gn2 = h->gdim * h->n2;
+        for (const Region& r : h->regions) {
+            if (r.ncells == 0) continue;
+            const bool fl = r.rc.kind == TFSI_KIND_FLUID;
+            if (fl ? !r.rc.fluid_on : !r.rc.solid_on) continue;
+            const int lo = gn2, hi = fl ? 2 * gn2 + h->n1 : 2 * gn2;
+            mark_rows_kernel<<<grid_for(r.ncells * (hi - lo), 256, h->sm_count), 256, 0, st>>>(h->cell_dofs, r.cell_list, r.ncells, h->ndof, lo, hi, flag);
+        }
+        CK(h, cudaMalloc((void**)&h->tmask, std::max<size_t>((size_t)ngroups, 1) * sizeof(uint32_t)));
+        CK(h, cudaMemsetAsync(h->tmask, 0, (size_t)ngroups * sizeof(uint32_t), st));
+        touched_words_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, st>>>(h->rowptr, flag, h->N, h->tmask);
+        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(h->scratch + 2);
+        CK(h, cudaMemsetAsync(cnt, 0, sizeof *cnt, st));
+        count_pairs_kernel<<<grid_for(ngroups, 256, h->sm_count), 256, 0, st>>>(h->tmask, ngroups, cnt);
+        unsigned long long pairs = 0;
+        CK(h, cudaMemcpyAsync(&pairs, cnt, sizeof pairs, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        cudaFree(flag);
+        h->bound_entries = std::min<int64_t>((int64_t)pairs * 64, h->nnz);
+    }
+    bitmap_stream_kernel<1><<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(
+        h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A, nullptr);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->bound_A = A; h->bound_dirty = 0;
+    return 0;
+}
+
+int tfsi_unbind_matrix(tfsi_handle* h) {
+    if (!h) return TFSI_ERR_ARG;
+    h->bound_A = nullptr; h->bound_dirty = 0;
+    return 0;
+}
+
+int64_t tfsi_bound_init_entries(const tfsi_handle* h) { return h ? h->bound_entries : -1; }
+
 int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, double* b, void* stream) {
     if (!h || !x || !x1 || !b) return fail(h, TFSI_ERR_ARG, "null argument");
+    DeviceGuard dg(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(b, 0, (size_t)h->N * sizeof(double), st));
@@ -679,6 +796,7 @@ int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, do
 
 int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {
     if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
+    DeviceGuard dg(h);
     ident_zeros_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, A, h->N, 3.0e-16);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -687,9 +805,12 @@ int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {
 
 int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc, int64_t n) {
     if (!h || (n && !bc) || n < 0) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
+    CK(h, cudaDeviceSynchronize());
     cudaFree(h->bc_dofs); h->bc_dofs = nullptr;
     cudaFree(h->hg); h->hg = nullptr;
     h->nbc = n;
+    h->bound_dirty = 1;            // unit rows of the previous set may sit in the bound matrix
     if (int rc = upload(h, &h->bc_dofs, bc, (size_t)n)) return rc;
     CK(h, cudaMalloc((void**)&h->hg, std::max<size_t>((size_t)n, 1) * sizeof(double)));
     return 0;
@@ -698,26 +819,31 @@ int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc, int64_t n) {
 int tfsi_apply_bc_matrix(tfsi_handle* h, double* A, void* stream) {
     if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
     if (h->nbc == 0) return 0;
+    DeviceGuard dg(h);
     bc_matrix_kernel<<<grid_for(h->nbc * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->diagpos, h->bc_dofs, h->nbc, A);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
 }
 
-int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, void* stream) {
+int tfsi_apply_bc_rhs(tfsi_handle* h, double* b, const double* x, const double* g, int64_t n, void* stream) {
     if (!h || !b || !x) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (n != h->nbc) return fail(h, TFSI_ERR_ARG, "%lld BC values for a set of %lld dofs (tfsi_set_bc_dofs)", (long long)n, (long long)h->nbc);
     if (h->nbc == 0) return 0;
     if (!g) return fail(h, TFSI_ERR_ARG, "null BC values");
+    DeviceGuard dg(h);
     bc_rhs_kernel<<<grid_for(h->nbc, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->bc_dofs, h->nbc, b, x, g);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
 }
 
-int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream) {
+int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, int64_t n, void* stream) {
     if (!h || !x) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (n != h->nbc) return fail(h, TFSI_ERR_ARG, "%lld BC values for a set of %lld dofs (tfsi_set_bc_dofs)", (long long)n, (long long)h->nbc);
     if (h->nbc == 0) return 0;
     if (!g) return fail(h, TFSI_ERR_ARG, "null BC values");
+    DeviceGuard dg(h);
     bc_vec_kernel<<<grid_for(h->nbc, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->bc_dofs, h->nbc, x, g);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -726,6 +852,8 @@ int tfsi_apply_bc_vec(tfsi_handle* h, double* x, const double* g, void* stream) 
 
 int tfsi_csr_matvec(tfsi_handle* h, const double* A, const double* x, double* y, void* stream) {
     if (!h || !A || !x || !y) return fail(h, TFSI_ERR_ARG, "null argument");
+    if (!h->colidx) return fail(h, TFSI_ERR_UNSUPPORTED, "the column array was released (tfsi_release_pattern)");
+    DeviceGuard dg(h);
     csr_matvec_kernel<<<grid_for(h->N * 32, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(h->rowptr, h->colidx, A, x, y, h->N);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -734,6 +862,7 @@ int tfsi_csr_matvec(tfsi_handle* h, const double* A, const double* x, double* y,
 
 int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out, void* stream) {
     if (!h || !v || !out) return fail(h, TFSI_ERR_ARG, "null argument");
+    DeviceGuard dg(h);
     cudaStream_t st = (cudaStream_t)stream;
     CK(h, cudaMemsetAsync(h->scratch, 0, sizeof(double), st));
     sumsq_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(v, n, h->scratch);
@@ -744,21 +873,29 @@ int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out, void* st
 }
 
 int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host, const double* g_host,
-                              const double* Apre, double* A, double* b_host, double* out_sumsq_b, int32_t recompute) {
-    if (!h || !x_host || !x1_host || !b_host) return fail(h, TFSI_ERR_ARG, "null argument");
+                              const double* Apre, double* A, double* b_host, double* out_sumsq_b, int32_t recompute,
+                              void* stream) {
+    if (!h || !x_host || !b_host) return fail(h, TFSI_ERR_ARG, "null argument");
     if (recompute && !A) return fail(h, TFSI_ERR_ARG, "null A");
+    if (!x1_host && !h->hx1_valid) return fail(h, TFSI_ERR_ARG, "x1_host is NULL but no previous time level was uploaded yet");
+    DeviceGuard dg(h);
+    const size_t nb = (size_t)h->N * sizeof(double);
+    if (!h->hx) {
+        CK(h, cudaMalloc((void**)&h->hx, nb));
+        CK(h, cudaMalloc((void**)&h->hx1, nb));
+        CK(h, cudaMalloc((void**)&h->hb, nb));
+    }
     // Two streams: `io` carries the host<->device copies, `st` the kernels. The x-independent A := A_pre
     // runs under the H2D copy of x; the residual is assembled BEFORE the Jacobian so that its D2H copy
     // and norm run under the Jacobian kernels. Both streams start after everything the caller has
-    // queued on the legacy default stream (A_pre, A are the caller's buffers).
+    // queued on `stream` (A_pre, A are the caller's buffers).
     cudaStream_t st = h->main_stream, io = h->copy_stream;
-    const size_t nb = (size_t)h->N * sizeof(double);
     const bool bcs = h->nbc && g_host;
-    CK(h, cudaEventRecord(h->ev_entry, 0));
+    CK(h, cudaEventRecord(h->ev_entry, (cudaStream_t)stream));
     CK(h, cudaStreamWaitEvent(st, h->ev_entry, 0));
     CK(h, cudaStreamWaitEvent(io, h->ev_entry, 0));
     CK(h, cudaMemcpyAsync(h->hx, x_host, nb, cudaMemcpyHostToDevice, io));
-    CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, io));
+    if (x1_host) { CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, io)); h->hx1_valid = 1; }
     if (bcs) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, io));
     CK(h, cudaEventRecord(h->ev_in, io));
     if (recompute) {
@@ -767,7 +904,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
     }
     CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
     if (int rc = tfsi_assemble_residual(h, h->hx, h->hx1, h->hb, st)) return rc;
-    if (bcs) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, st)) return rc;
+    if (bcs) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, h->nbc, st)) return rc;
     CK(h, cudaEventRecord(h->ev_b, st));
     CK(h, cudaStreamWaitEvent(io, h->ev_b, 0));
     CK(h, cudaMemcpyAsync(b_host, h->hb, nb, cudaMemcpyDeviceToHost, io));
@@ -791,6 +928,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
 int tfsi_halo_pack(tfsi_handle* h, const double* x, const int32_t* idx, int64_t n, double* buf, void* stream) {
     if (!h || !x || (n && (!idx || !buf))) return fail(h, TFSI_ERR_ARG, "null argument");
     if (n == 0) return 0;
+    DeviceGuard dg(h);
     gather_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, idx, n, buf);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -800,6 +938,7 @@ int tfsi_halo_pack(tfsi_handle* h, const double* x, const int32_t* idx, int64_t 
 int tfsi_halo_unpack(tfsi_handle* h, double* x, const int32_t* idx, int64_t n, const double* buf, void* stream) {
     if (!h || !x || (n && (!idx || !buf))) return fail(h, TFSI_ERR_ARG, "null argument");
     if (n == 0) return 0;
+    DeviceGuard dg(h);
     scatter_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, idx, n, buf);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -815,6 +954,7 @@ int tfsi_set_profiling(tfsi_handle* h, int32_t on) {
 
 int tfsi_kernel_time(tfsi_handle* h, int32_t kind, double* total_ms, int64_t* count) {
     if (!h || kind < 0 || kind > 2) return fail(h, TFSI_ERR_ARG, "bad argument");
+    DeviceGuard dg(h);
     double tot = 0;
     for (auto& p : h->ev[kind]) {
         CK(h, cudaEventSynchronize(p.second));

@@ -47,15 +47,16 @@ struct CellArgs {
     const double* coords;          // [nv][G]
     const int32_t* cell_vertices;  // [nc][G+1]
     const int32_t* cell_dofs;      // [nc][ndof]
-    const uint16_t* rank;          // [nc][N2][ndof_pad]
+    const int32_t* colidx;         // [nnz] (set-up kernels only; may be released afterwards)
     const int64_t* rowptr;         // [N+1]
     const int32_t* cell_list;      // cells of this region
     const uint16_t* rank_blk;      // per CTA batch: [N2][NCOLS][RKS] ranks in the shared-memory layout
     const int32_t* dofs_blk;       // per CTA batch: [NCOEF][NC] dofs
     int64_t ncell_region;
     int32_t ndof;                  // dofs per cell (27/39/64/94)
-    int32_t ndof_pad;              // row stride of the rank map (multiple of 8 -> 16-byte rows)
-    int32_t nq;
+    int32_t q0;                    // first point of the quadrature chunk this launch integrates (rules larger than
+                                   // the shared-memory table are integrated in several launches: the REDs add up)
+    int32_t nq;                    // points of the chunk
     RegionConst rc;
     const double* x;
     const double* x1;
@@ -162,11 +163,23 @@ __device__ __forceinline__ void stage_cells(const CellArgs& a, int32_t* scell, d
     }
 }
 
-// set-up kernels: per-CTA-batch copies of the scatter ranks (already in the shared-memory layout, so
-// that staging is ONE bulk copy) and of the cell dofs (so that the gather of the batch is coalesced)
-__global__ void build_rank_blocked_kernel(const uint16_t* rank, const int32_t* cell_list, int64_t ncells,
-                                          int n2, int ndof_pad, int ncols, int nc_cta, int rks, size_t blk_elems,
-                                          uint16_t* out)
+__device__ __forceinline__ int64_t find_col(const int32_t* colidx, int64_t lo, int64_t hi, int32_t col) {
+    while (lo < hi) {                 // first index with colidx >= col
+        int64_t mid = (lo + hi) >> 1;
+        if (colidx[mid] < col) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// set-up kernels: per-CTA-batch scatter ranks (already in the shared-memory layout, so that staging is
+// ONE bulk copy) and per-batch copies of the cell dofs (so that the gather of the batch is coalesced).
+// rank(cell, node I, col j) = position of column cell_dofs[cell][col_map(j)] inside the CSR row of the first dof
+// (d_0) living on node I, found by binary search. err[0] counts misses / overflows (> 65535).
+// The batch's trial columns are the local dofs [0, ncols) (fluid: d, v, p; solid: d).
+__global__ void build_rank_blocked_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
+                                          const int32_t* cell_list, int64_t ncells, int ndof,
+                                          int n2, int ncols, int nc_cta, int rks, size_t blk_elems,
+                                          uint16_t* out, int* err)
 {
     const int64_t nb = (ncells + nc_cta - 1) / nc_cta;
     const int64_t total = nb * n2 * ncols * nc_cta;
@@ -179,7 +192,14 @@ __global__ void build_rank_blocked_kernel(const uint16_t* rank, const int32_t* c
         int64_t idx = b * nc_cta + c;
         if (idx >= ncells) idx = ncells - 1;
         const int64_t cell = cell_list[idx];
-        out[(size_t)b * blk_elems + ((size_t)i * ncols + col) * rks + c] = rank[((size_t)cell * n2 + i) * ndof_pad + col];
+        const int32_t row = cell_dofs[cell * ndof + i];
+        const int32_t cj = cell_dofs[cell * ndof + col];
+        const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+        const int64_t pos = find_col(colidx, lo, hi, cj);
+        uint16_t rk = 0;
+        if (pos >= hi || colidx[pos] != cj || pos - lo > 65535) atomicAdd(err, 1);
+        else rk = (uint16_t)(pos - lo);
+        out[(size_t)b * blk_elems + ((size_t)i * ncols + col) * rks + c] = rk;
     }
 }
 __global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells,
@@ -238,14 +258,14 @@ __device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a,
     for (int i = 0; i < N2; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
-    const int nq = NQ ? NQ : a.nq;
+    const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
 #pragma unroll 1
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return basec[q * QSTR + item]; };
         double C[G + 1][G + 1];
         if (FLD == 0) fluid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
-        block_p2p2<G, HALF, 7>(c_tabJ, q, C, Z);
+        block_p2p2<G, HALF, 7>(c_tabJ, q0 + q, C, Z);
     }
     mbar_wait(mbar, 0);                       // ranks have landed (immediately true after the first task)
     if (valid)
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
     constexpr int JAC_THREADS = FluidJac<G>::THREADS;
     constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, RKS = L::RKS, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nq = NQ ? NQ : a.nq;
+    const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     double* coef1 = coef + NCOEF * NC;
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
         auto cf1 = [&](int k) { return coef1[k * NC + c]; };
         double* dstb = base + ((size_t)q * NC + c) * STRIDE;
         auto out = [&](int item, double v) { dstb[item] = v; };
-        fluid_base<G>(c_tabJ, q, K, adet, a.rc, cf, cf1, out);
+        fluid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, cf1, out);
     }
     __syncthreads();
     if (threadIdx.x == 0) {   // scatter ranks of the batch: one TMA bulk copy into the (now dead) coefficient region;
@@ -367,7 +387,7 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
                     auto bv = [&](int item) { return basec[q * QSTR + item]; };
                     double cc[G];
                     fluid_c_psi_dp<G>(bv, ca, cc);
-                    block_gradp2_p1<G>(c_tabJ, q, cc, Z);
+                    block_gradp2_p1<G>(c_tabJ, q0 + q, cc, Z);
                 }
                 mbar_wait(mbar, 0);
                 if (valid) {
@@ -391,7 +411,7 @@ __global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) ja
                     double cc[G];
                     if (fld == 0) fluid_c_gamma_dd<G>(bv, cb, cc);
                     else fluid_c_gamma_dv<G>(bv, cb, cc);
-                    block_p1_gradp2<G>(c_tabJ, q, cc, Z);
+                    block_p1_gradp2<G>(c_tabJ, q0 + q, cc, Z);
                 }
                 mbar_wait(mbar, 0);
                 if (valid) {
@@ -431,13 +451,13 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
     for (int i = 0; i < N2; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
-    const int nq = NQ ? NQ : a.nq;
+    const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
 #pragma unroll 1
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return basec[q * QSTR + item]; };
         double C[G + 1][G + 1];
         solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
-        block_p2p2<G, HALF, 4>(c_tabJ, q, C, Z);
+        block_p2p2<G, HALF, 4>(c_tabJ, q0 + q, C, Z);
     }
     mbar_wait(mbar, 0);
     if (valid) scatter_p2p2<G, typename SolidJac<G>::L, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(SolidCfg<G>::WARPS * 32, SolidCfg<G>::CTAS) ja
     constexpr int JAC_THREADS = SolidJac<G>::THREADS;
     constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nq = NQ ? NQ : a.nq;
+    const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
     double* base = reinterpret_cast<double*>(smem_raw);
     double* coef = reinterpret_cast<double*>(smem_raw + SM::off_u(nq));
     uint16_t* srank = reinterpret_cast<uint16_t*>(smem_raw + SM::off_u(nq));
@@ -501,7 +521,7 @@ __global__ void __launch_bounds__(SolidCfg<G>::WARPS * 32, SolidCfg<G>::CTAS) ja
         auto cf = [&](int k) { return coef[k * NC + c]; };
         double* dstb = base + ((size_t)q * NC + c) * STRIDE;
         auto out = [&](int item, double v) { dstb[item] = v; };
-        solid_base<G>(c_tabJ, q, K, adet, a.rc, cf, out);
+        solid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, out);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -538,7 +558,8 @@ struct LinBlock {
     int pad_;
     double cm, ck;   // ck multiplies K K^T (already includes alfa for laplace "constant")
     int ck_per_volume;   // laplace "volume": ck / cell volume
-    int pad2_;
+    int gen_kind;        // 0: delta_ab block as above; 1 | 2: full (a, b) coupling through lift_flux_derivative at the set-up
+                         // state d^n (laplace "volume_change" | elastic lifting), frozen in A_pre (newtonsolver.py:26-27)
 };
 constexpr int MAX_LINBLOCKS = 4;
 struct LinArgs {
@@ -576,6 +597,60 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
         }
     double ck = blk.ck;
     if (blk.ck_per_volume) ck /= (adet / (G == 2 ? 2.0 : 6.0));
+    auto scatter = [&](int compa, int compb, const double (&Z)[N2][NJ]) {
+        for (int i = 0; i < N2; ++i) {
+            const int row = dofs[blk.test_off + compa * N2 + i];
+            const int64_t lo = a.rowptr[row], hi = a.rowptr[row + 1];
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const int j = half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj);
+                atomicAdd(a.out + find_col(a.colidx, lo, hi, dofs[blk.trial_off + compb * N2 + j]), Z[i][jj]);
+            }
+        }
+    };
+    if (blk.gen_kind) {
+        // non-linear lifting flux: block (a, b) = sum_q jw ghat_i^T (K D[a][.][b][.] K^T) ghat_j at the set-up state
+        const double Ey = 1.0 / (adet / (G == 2 ? 2.0 : 6.0)), nu = 0.25;
+        const double a_lam = nu * Ey / ((1.0 + nu) * (1.0 - 2.0 * nu)), a_mu = Ey / (2.0 * (1.0 + nu));
+        for (int ca = 0; ca < G; ++ca)
+            for (int cb = 0; cb < G; ++cb) {
+                double Z[N2][NJ];
+                for (int i = 0; i < N2; ++i) for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
+                for (int q = 0; q < a.nq; ++q) {
+                    const double jw = c_tabJ.w[q] * adet;
+                    double Gp[G][G];
+                    for (int aa = 0; aa < G; ++aa) {
+                        double Gd[G];
+                        for (int t = 0; t < G; ++t) Gd[t] = 0;
+                        for (int j = 0; j < N2; ++j) {
+                            const double dj = a.x[dofs[aa * N2 + j]];
+                            for (int t = 0; t < G; ++t) Gd[t] += dj * c_tabJ.dphi2[q][j][t];
+                        }
+                        for (int b = 0; b < G; ++b) {
+                            double sacc = 0;
+                            for (int t = 0; t < G; ++t) sacc += Gd[t] * K[t][b];
+                            Gp[aa][b] = sacc;
+                        }
+                    }
+                    double D[G][G][G][G];
+                    lift_flux_derivative<G>(blk.gen_kind, Gp, a_mu, a_lam, D);
+                    double C[G + 1][G + 1];
+                    C[0][0] = 0.0;
+                    for (int s = 0; s < G; ++s) {
+                        C[0][1 + s] = 0; C[1 + s][0] = 0;
+                        for (int t = 0; t < G; ++t) {
+                            double z = 0;
+                            for (int s2 = 0; s2 < G; ++s2) for (int t2 = 0; t2 < G; ++t2) z += K[s][s2] * D[ca][s2][cb][t2] * K[t][t2];
+                            C[1 + s][1 + t] = jw * z;
+                        }
+                    }
+                    if (half == 0) block_p2p2<G, 0, 5>(c_tabJ, q, C, Z);
+                    else block_p2p2<G, 1, 5>(c_tabJ, q, C, Z);
+                }
+                scatter(ca, cb, Z);
+            }
+        return;
+    }
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -617,15 +692,7 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
         if (half == 0) block_p2p2<G, 0, 5>(c_tabJ, q, C, Z);
         else block_p2p2<G, 1, 5>(c_tabJ, q, C, Z);
     }
-    for (int comp = 0; comp < G; ++comp)
-        for (int i = 0; i < N2; ++i) {
-            const int row = dofs[blk.test_off + comp * N2 + i];
-            double* dst = a.out + a.rowptr[row];
-            const uint16_t* rk = a.rank + ((size_t)cell * N2 + i) * a.ndof_pad + blk.trial_off + comp * N2;
-#pragma unroll
-            for (int jj = 0; jj < NJ; ++jj)
-                atomicAdd(dst + rk[half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj)], Z[i][jj]);
-        }
+    for (int comp = 0; comp < G; ++comp) scatter(comp, comp, Z);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -661,7 +728,7 @@ template <int G, bool BIH> struct ResCfg {
 // phase 1: warp = row group (field, comp), lane = cell: Z_i = sum_q phi_i f0 + ghat_i . f  (sparse P2 test
 //          functions); with NC = 16 the two half-warps take the even / odd points and are combined by shuffles;
 //          ONE RED per row
-template <int G, bool BIH, int NC, bool VC>
+template <int G, bool BIH, int NC, int LIFT>
 __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(CellArgs a)
 {
     typedef ResCfg<G, BIH> R;
@@ -716,11 +783,11 @@ __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(Ce
             for (int u = 0; u < G; ++u) K[s][u] = sgeo[(s * G + u) * NC + c];
         const double adet = sgeo[G * G * NC + c];
         double alfa_cell = a.rc.alfa;
-        if (a.rc.ext == 1 && a.rc.ext_sub == 2) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));
+        if ((a.rc.ext == 1 && a.rc.ext_sub == 2) || a.rc.ext == 3) alfa_cell = 1.0 / (adet / (G == 2 ? 2.0 : 6.0));   // 1 / CellVolume
         auto cf = [&](int k) { return coef[k * NC + c]; };
         auto cf1 = [&](int k) { return coef1[k * NC + c]; };
         PointFlux<G> f;
-        residual_point<G, VC>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
+        residual_point<G, LIFT>(c_tabR, q, K, adet, a.rc, alfa_cell, cf, cf1, f);
         double* dst = flux + ((size_t)q * NC + c) * FS;
 #pragma unroll
         for (int cc = 0; cc < G; ++cc) {
@@ -819,18 +886,10 @@ __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(Ce
 
 // -------------------------------------------------------------------------------------------
 // set-up and vector kernels
-__device__ __forceinline__ int64_t find_col(const int32_t* colidx, int64_t lo, int64_t hi, int32_t col) {
-    while (lo < hi) {                 // first index with colidx >= col
-        int64_t mid = (lo + hi) >> 1;
-        if (colidx[mid] < col) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// rank[cell][node I][j] = position of column cell_dofs[cell][j] inside the CSR row of the first
-// dof (d_0) living on node I.  err[0] counts misses / overflows.
-__global__ void build_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
-                                  uint16_t* rank, int64_t ncells, int n2, int ndof, int ndof_pad, int* err)
+// every dense cell block must lie inside the CSR pattern: entry (row of node I's first dof, column j) for all
+// cells, nodes, local dofs. err[0] counts misses / rows longer than the 16-bit scatter ranks allow.
+__global__ void check_pattern_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
+                                     int64_t ncells, int n2, int ndof, int* err)
 {
     const int64_t total = ncells * n2 * ndof;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -843,16 +902,15 @@ __global__ void build_rank_kernel(const int32_t* cell_dofs, const int64_t* rowpt
         const int32_t col = cell_dofs[cell * ndof + j];
         const int64_t lo = rowptr[row], hi = rowptr[row + 1];
         const int64_t pos = find_col(colidx, lo, hi, col);
-        const size_t o = ((size_t)cell * n2 + i) * ndof_pad + j;
-        if (pos >= hi || colidx[pos] != col || pos - lo > 65535) { atomicAdd(err, 1); rank[o] = 0; }
-        else rank[o] = (uint16_t)(pos - lo);
+        if (pos >= hi || colidx[pos] != col || pos - lo > 65535) atomicAdd(err, 1);
     }
 }
 
-// every row r of the cell (all fields) must see column j at rowptr[r] + rank[node(r)][j]
+// the scatter maps are per NODE: every row r of the cell (all fields) must see column j at the same offset
+// from its row start as the first dof (d_0) of r's node does
 __global__ void verify_rank_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
-                                   const uint16_t* rank, const int32_t* node_of_local, int64_t ncells,
-                                   int n2, int ndof, int ndof_pad, int64_t stride, int* err)
+                                   const int32_t* node_of_local, int64_t ncells,
+                                   int n2, int ndof, int64_t stride, int* err)
 {
     const int64_t total = ncells * ndof * ndof;
     for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; t < total;
@@ -862,8 +920,11 @@ __global__ void verify_rank_kernel(const int32_t* cell_dofs, const int64_t* rowp
         const int r = (int)(cr % ndof);
         const int64_t cell = cr / ndof;
         const int32_t row = cell_dofs[cell * ndof + r];
-        const int64_t pos = rowptr[row] + rank[((size_t)cell * n2 + node_of_local[r]) * ndof_pad + j];
-        if (pos >= rowptr[row + 1] || colidx[pos] != cell_dofs[cell * ndof + j]) atomicAdd(err, 1);
+        const int32_t row0 = cell_dofs[cell * ndof + node_of_local[r]];
+        const int32_t col = cell_dofs[cell * ndof + j];
+        const int64_t off0 = find_col(colidx, rowptr[row0], rowptr[row0 + 1], col) - rowptr[row0];
+        const int64_t pos = rowptr[row] + off0;
+        if (pos >= rowptr[row + 1] || colidx[pos] != col) atomicAdd(err, 1);
     }
 }
 
@@ -1001,10 +1062,13 @@ __global__ void bitmap_build_kernel(const double* vals, int64_t nnz, uint32_t* b
         if (lane == 0) group_cnt[gidx] = c;
     }
 }
-// MODE 0: pack the non-zero values (cval[idx] = vals[k]); MODE 1: expand (A[k] = bit ? cval[idx] : 0)
+// MODE 0: pack the non-zero values (cval[idx] = vals[k]); MODE 1: expand (A[k] = bit ? cval[idx] : 0).
+// MODE 1 with `tmask` (bit w & 31 of tmask[w >> 5] = bitmap word w holds an entry of a row the non-linear kernels
+// scatter into): only those words (in pairs: 64 entries, 512 B) are rewritten — the matrix bound by tfsi_bind_matrix
+// keeps A_pre in all other rows between assemblies.
 template <int MODE>
 __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, const int64_t* group_base, int64_t nnz,
-                                     const double* vals_in, double* cval, double* A)
+                                     const double* vals_in, double* cval, double* A, const uint32_t* tmask = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1012,6 +1076,8 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
     const int64_t ngroups = (nwords + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
     for (int64_t gidx = wid; gidx < ngroups; gidx += nw) {
+        const uint32_t tm = (MODE == 1 && tmask) ? tmask[gidx] : 0xffffffffu;   // warp-uniform
+        if (tm == 0u) continue;
         const int64_t w = gidx * 32 + lane;
         const uint32_t myword = (w < nwords) ? bitmap[w] : 0u;
         int pre = __popc(myword);                         // inclusive scan over lanes -> exclusive
@@ -1025,13 +1091,13 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
                 const uint32_t m = __shfl_sync(0xffffffffu, myword, j);
                 const int start = __shfl_sync(0xffffffffu, pre, j);
                 const int64_t k = (gidx * 32 + j) * 32 + lane;
-                if (k >= nnz) break;
-                if ((m >> lane) & 1u) cval[base + start + __popc(m & lt)] = vals_in[k];
+                if (k < nnz && ((m >> lane) & 1u)) cval[base + start + __popc(m & lt)] = vals_in[k];   // all lanes run every shuffle
             }
         } else {
             // expand: every lane writes two consecutive entries (16-byte stores, 512 B per warp instruction)
 #pragma unroll 4
             for (int j = 0; j < 16; ++j) {
+                if (((tm >> (2 * j)) & 3u) == 0u) continue;                 // warp-uniform: no lane reaches the shuffles
                 const uint32_t mlo = __shfl_sync(0xffffffffu, myword, 2 * j);
                 const uint32_t mhi = __shfl_sync(0xffffffffu, myword, 2 * j + 1);
                 const int start = __shfl_sync(0xffffffffu, pre, 2 * j);
@@ -1049,6 +1115,34 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
             }
         }
     }
+}
+
+// rows that the non-linear Jacobian kernels scatter into: the local dofs [lo, hi) of every cell of a region
+__global__ void mark_rows_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells, int ndof,
+                                 int lo, int hi, uint8_t* flag)
+{
+    const int w = hi - lo;
+    const int64_t total = ncells * w;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        flag[cell_dofs[(int64_t)cell_list[t / w] * ndof + lo + (int)(t % w)]] = 1;
+}
+// word-level mask of the flagged rows (see bitmap_stream_kernel<1>)
+__global__ void touched_words_kernel(const int64_t* rowptr, const uint8_t* flag, int64_t n, uint32_t* tmask)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (!flag[r] || rowptr[r + 1] == rowptr[r]) continue;
+        for (int64_t w = rowptr[r] >> 5; w <= ((rowptr[r + 1] - 1) >> 5); ++w) atomicOr(tmask + (w >> 5), 1u << (w & 31));
+    }
+}
+// number of bitmap word PAIRS that the masked expansion rewrites (reporting only)
+__global__ void count_pairs_kernel(const uint32_t* tmask, int64_t ngroups, unsigned long long* out)
+{
+    unsigned long long c = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t tm = tmask[g];
+        c += __popc((tm | (tm >> 1)) & 0x55555555u);
+    }
+    if (c) atomicAdd(out, c);
 }
 
 // ---- fixed linear facet operator (COO): A_pre += A_f ; b -= A_f x  (biharmonic.py:38-41 ds terms)

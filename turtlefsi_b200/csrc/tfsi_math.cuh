@@ -27,7 +27,8 @@
 
 namespace tfsi {
 
-constexpr int MAXQ_J = 16;   // Jacobian rule: <= 15 points (degree <= 5 in 3-D, <= 6 in 2-D)
+constexpr int MAXQ_J = 32;   // Jacobian rule: <= 32 points (degree <= 6 in 3-D: 24; rules beyond the shared-memory table
+                             // of one launch are integrated in chunks)
 constexpr int MAXQ_R = 64;   // residual rule: 24 (3-D degree 6), 36 (2-D degree 10), 64 (3-D degree 7)
 
 template <int MAXQ>
@@ -115,7 +116,7 @@ struct RegionConst {
     double grav_rho;       // gravity * rho_s (solid.py:65-68), 0 if none
     int kind;              // 0 fluid, 1 solid
     int fluid_on, solid_on;
-    int ext;               // 0 none, 1 laplace, 2 biharmonic
+    int ext;               // 0 none, 1 laplace, 2 biharmonic, 3 elastic
     int ext_sub;           // laplace: 0 constant, 1 small_constant, 2 volume, 3 volume_change
     int pad_;
 };
@@ -626,9 +627,10 @@ template <int G> struct PointFlux {
     double gamma;                        // pressure-test rows
 };
 
-// VC: laplace "volume_change" (alfa = 1/J(d^n), laplace.py:33-34) compiled in; a template flag so that the default
-// instantiation keeps its register allocation
-template <int G, bool VC = false, class Tab, class CF, class CF1>
+// LIFT: 1 = laplace "volume_change" (alfa = 1/J(d^n), laplace.py:33-34), 2 = elastic lifting (elastic.py:18-27)
+// compiled in; a template flag so that the default instantiation keeps its register allocation
+constexpr int LIFT_DEFAULT = 0, LIFT_VOLUME_CHANGE = 1, LIFT_ELASTIC = 2;
+template <int G, int LIFT = 0, class Tab, class CF, class CF1>
 TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], double adet,
                             const RegionConst& rc, double alfa_cell, CF cf, CF1 cf1,
                             PointFlux<G>& f)
@@ -741,7 +743,7 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
         }
         if (rc.ext == 1) {                       // laplace.py:45  alfa grad d : grad phi
             double al = alfa_cell;
-            if (VC) {                            // laplace.py:33-34 "volume_change": alfa = 1 / J(d^n), pointwise
+            if (LIFT == LIFT_VOLUME_CHANGE) {    // laplace.py:33-34 "volume_change": alfa = 1 / J(d^n), pointwise
                 double Fi_[G][G];
                 al = 1.0 / inv<G>(F, Fi_);
             }
@@ -759,6 +761,38 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
                     }
                     f.phi_grad[a][s] = jw * al * x;
                 }
+        } else if (LIFT == LIFT_ELASTIC && rc.ext == 3) {
+            // elastic.py:18-27: J S_linear(d) F^-T : grad(phi);  eps(d) = sym(grad d F^-1) (common.py:56-60),
+            // E = 1 / CellVolume, nu = 0.25; alfa_cell carries E
+            const double nu = 0.25, a_lam = nu * alfa_cell / ((1.0 + nu) * (1.0 - 2.0 * nu)), a_mu = alfa_cell / (2.0 * (1.0 + nu));
+            double Fi[G][G];
+            const double J = inv<G>(F, Fi);
+            double tre = 0, S[G][G];             // grad d F^-1 = I - F^-1
+#pragma unroll
+            for (int a = 0; a < G; ++a) tre += 1.0 - Fi[a][a];
+#pragma unroll
+            for (int a = 0; a < G; ++a)
+#pragma unroll
+                for (int b = 0; b < G; ++b)
+                    S[a][b] = a_mu * (((a == b) ? 2.0 : 0.0) - Fi[a][b] - Fi[b][a]) + ((a == b) ? a_lam * tre : 0.0);
+#pragma unroll
+            for (int a = 0; a < G; ++a) {
+                double P[G];                     // (J S F^-T)[a][b]
+#pragma unroll
+                for (int b = 0; b < G; ++b) {
+                    double x = 0;
+#pragma unroll
+                    for (int c = 0; c < G; ++c) x += S[a][c] * Fi[b][c];
+                    P[b] = J * x;
+                }
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    double x = 0;
+#pragma unroll
+                    for (int b = 0; b < G; ++b) x += K[s][b] * P[b];
+                    f.phi_grad[a][s] = jw * x;
+                }
+            }
         } else if (rc.ext == 2) {                // biharmonic.py:35-36
             double w[G], Gw[G][G];
 #pragma unroll
@@ -841,6 +875,51 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// Derivative of the non-linear mesh-lifting fluxes with respect to grad d, for the FROZEN A_pre (newtonsolver.py:26-27):
+//   D[a][s][b][t] = d P_as / d (grad d)_bt   at the state grad d = Gp (physical gradient)
+//   kind 1  laplace "volume_change":  P = (1/J) grad d                         (laplace.py:33-34,45)
+//   kind 2  elastic:                  P = J S_linear(d) F^-T, S = lam tr(eps) I + 2 mu eps, eps = sym(grad d F^-1)
+//                                                                               (elastic.py:24-25, common.py:56-60,141-145)
+template <int G>
+TFSI_HD void lift_flux_derivative(int kind, const double (&Gp)[G][G], double a_mu, double a_lam, double (&D)[G][G][G][G])
+{
+    double F[G][G], Fi[G][G];
+#pragma unroll
+    for (int a = 0; a < G; ++a)
+#pragma unroll
+        for (int b = 0; b < G; ++b) F[a][b] = Gp[a][b] + ((a == b) ? 1.0 : 0.0);
+    const double J = inv<G>(F, Fi);
+    if (kind == 1) {
+        for (int a = 0; a < G; ++a) for (int s = 0; s < G; ++s) for (int b = 0; b < G; ++b) for (int t = 0; t < G; ++t)
+            D[a][s][b][t] = ((((a == b) && (s == t)) ? 1.0 : 0.0) - Fi[t][b] * Gp[a][s]) / J;
+        return;
+    }
+    double S[G][G], SFt[G][G], tre = 0;
+    for (int a = 0; a < G; ++a) tre += 1.0 - Fi[a][a];
+    for (int a = 0; a < G; ++a) for (int b = 0; b < G; ++b)
+        S[a][b] = a_mu * (((a == b) ? 2.0 : 0.0) - Fi[a][b] - Fi[b][a]) + ((a == b) ? a_lam * tre : 0.0);
+    for (int a = 0; a < G; ++a) for (int s = 0; s < G; ++s) {
+        double x = 0;
+        for (int c = 0; c < G; ++c) x += S[a][c] * Fi[s][c];
+        SFt[a][s] = x;
+    }
+    for (int b = 0; b < G; ++b) for (int t = 0; t < G; ++t) {
+        // delta(grad d) = e_b e_t^T :  delta(grad d F^-1) = F^-1 e_b e_t^T F^-1
+        double trdM = 0;
+        for (int i = 0; i < G; ++i) trdM += Fi[i][b] * Fi[t][i];
+        const double dJ = J * Fi[t][b];
+        for (int a = 0; a < G; ++a) for (int s = 0; s < G; ++s) {
+            double x = 0;                                   // (dS F^-T)[a][s]
+            for (int c = 0; c < G; ++c) {
+                const double dS = a_mu * (Fi[a][b] * Fi[t][c] + Fi[c][b] * Fi[t][a]) + ((a == c) ? a_lam * trdM : 0.0);
+                x += dS * Fi[s][c];
+            }
+            D[a][s][b][t] = dJ * SFt[a][s] + J * x - J * SFt[a][t] * Fi[s][b];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host helpers shared by the ABI and the test harness
 // P2 / P1 tabulation on the UFC reference simplex (vertices then edge midpoints, UFC edge order)
 template <int MAXQ>
@@ -894,6 +973,7 @@ inline RegionConst make_region_const(int kind, double rho, double mu, double lam
         rc.ext = ext; rc.ext_sub = ext_sub;
         if (ext == 1) rc.alfa = (ext_sub == 1) ? 0.01 * hmin * hmin : 1.0;    // laplace.py:37-40
         else if (ext == 2) rc.alfa = 0.01;                                      // biharmonic.py:31
+        else if (ext == 3) rc.alfa = 1.0;                                       // elastic.py:18 (E = alfa / CellVolume)
     } else {
         rc.rho_s_k = rho / k; rc.delta_rho_k = delta * rho / k; rc.delta_rho = delta * rho;
         rc.grav_rho = gravity * rho;

@@ -39,6 +39,7 @@ class DistributedAssembler:
         self._nbc_global = -1
         self._bc_sel = np.zeros(0, dtype=np.int64)
         self._entry_pos = None
+        self.bc_dofs = None
 
     # ---- vectors -------------------------------------------------------------------------------------------
     def new_vector(self):
@@ -125,6 +126,7 @@ class DistributedAssembler:
     # ---- boundary conditions, facet terms (problem files hand over GLOBAL dof numbers) -----------------------
     def set_bc_dofs(self, dofs):
         dofs = np.asarray(dofs, dtype=np.int64)
+        self.bc_dofs = dofs.astype(np.int32)                 # the GLOBAL set (newtonsolver checks it every step)
         self._nbc_global = len(dofs)
         loc = self._glob2loc[dofs]
         self._bc_sel = np.nonzero(loc >= 0)[0]

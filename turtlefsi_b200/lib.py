@@ -14,7 +14,11 @@ EXPORTS = [
     "tfsi_set_bc_dofs", "tfsi_apply_bc_matrix", "tfsi_apply_bc_rhs", "tfsi_apply_bc_vec",
     "tfsi_sumsq", "tfsi_newton_assemble_host", "tfsi_halo_pack", "tfsi_halo_unpack",
     "tfsi_launch_count", "tfsi_probe_fp64_peak", "tfsi_expand_node_pattern", "tfsi_set_profiling", "tfsi_kernel_time", "tfsi_compress_A_pre", "tfsi_compressed_nnz", "tfsi_set_facet_operator", "tfsi_set_facet_operator_prev", "tfsi_set_facet_load", "tfsi_set_facet_load_scale", "tfsi_csr_matvec",
+    "tfsi_invalidate_A_pre", "tfsi_bind_matrix", "tfsi_unbind_matrix", "tfsi_bound_init_entries", "tfsi_release_pattern",
+    "tfsi_num_colours", "tfsi_assemble_jacobian_phase",
 ]
+
+APRE_COMPRESSED = 1     # TFSI_APRE_COMPRESSED sentinel (include/turtlefsi_b200.h)
 
 
 class TfsiRegion(C.Structure):
@@ -35,7 +39,7 @@ class TfsiProblem(C.Structure):
         ("hmin", C.c_double), ("gravity", C.c_double), ("has_gravity", C.c_int32),
         ("nq_jacobian", C.c_int32), ("qpts_jacobian", C.c_void_p), ("qwts_jacobian", C.c_void_p),
         ("nq_residual", C.c_int32), ("qpts_residual", C.c_void_p), ("qwts_residual", C.c_void_p),
-        ("verify_pattern", C.c_int32),
+        ("verify_pattern", C.c_int32), ("borrow_pattern", C.c_int32), ("deterministic", C.c_int32),
     ]
 
 
@@ -82,13 +86,14 @@ def load():
     lib.tfsi_assemble_A_pre.argtypes = [vp, vp, vp, vp, vp]
     lib.tfsi_assemble_jacobian.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.tfsi_assemble_residual.argtypes = [vp, vp, vp, vp, vp]
+    lib.tfsi_assemble_jacobian_phase.argtypes = [vp, vp, vp, vp, vp, vp, i32]
     lib.tfsi_ident_zeros.argtypes = [vp, vp, vp]
     lib.tfsi_set_bc_dofs.argtypes = [vp, vp, i64]
     lib.tfsi_apply_bc_matrix.argtypes = [vp, vp, vp]
-    lib.tfsi_apply_bc_rhs.argtypes = [vp, vp, vp, vp, vp]
-    lib.tfsi_apply_bc_vec.argtypes = [vp, vp, vp, vp]
+    lib.tfsi_apply_bc_rhs.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.tfsi_apply_bc_vec.argtypes = [vp, vp, vp, i64, vp]
     lib.tfsi_sumsq.argtypes = [vp, vp, i64, C.POINTER(dbl), vp]
-    lib.tfsi_newton_assemble_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(dbl), i32]
+    lib.tfsi_newton_assemble_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(dbl), i32, vp]
     lib.tfsi_halo_pack.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.tfsi_halo_unpack.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.tfsi_expand_node_pattern.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -100,6 +105,13 @@ def load():
     lib.tfsi_compress_A_pre.argtypes = [vp, vp, vp]
     lib.tfsi_compressed_nnz.argtypes = [vp]
     lib.tfsi_compressed_nnz.restype = i64
+    lib.tfsi_invalidate_A_pre.argtypes = [vp]
+    lib.tfsi_bind_matrix.argtypes = [vp, vp, vp]
+    lib.tfsi_unbind_matrix.argtypes = [vp]
+    lib.tfsi_bound_init_entries.argtypes = [vp]
+    lib.tfsi_bound_init_entries.restype = i64
+    lib.tfsi_release_pattern.argtypes = [vp]
+    lib.tfsi_num_colours.argtypes = [vp]
     lib.tfsi_set_profiling.argtypes = [vp, i32]
     lib.tfsi_kernel_time.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(i64)]
     lib.tfsi_probe_fp64_peak.argtypes = [C.POINTER(dbl), C.POINTER(dbl)]

@@ -195,8 +195,12 @@ class DeviceRfLU:
                 if it < self.max_refine:
                     x = x + self._rf_solve(r)
                     self.refinements += 1
-            if ok or attempt == 1:
+            if ok:
                 break
+            if attempt == 1:
+                # MUMPS in the reference either solves or raises; never hand Newton an increment that failed its check
+                raise RuntimeError("DeviceRfLU: linear solve did not reach the residual tolerance after re-pivoting "
+                                   "(|b - A x| = %.3e, |b| = %.3e, tol = %.1e)" % (rn, bn, self.tol))
             t1 = time.perf_counter()
             self._host_analysis()                 # static pivots no longer adequate: new pivoting for this matrix
             self._refactor()
@@ -206,3 +210,44 @@ class DeviceRfLU:
         self.solves += 1
         self.last_relative_residual = rn / bn if bn else 0.0
         return x
+
+
+def probe_cudss():
+    """runtime probe for cuDSS, the sparse direct solver BASELINE's north_star names (`dlopen`, no link-time
+    dependency). Returns (ctypes library | None, text). cuDSS is not part of the CUDA toolkit and is NOT in this
+    image; where a deployment has it (LD_LIBRARY_PATH, the nvidia-cudss wheel), the probe finds it and reports its
+    version."""
+    import ctypes as C
+    import glob
+    import os
+    import sys
+    names = ["libcudss.so.0", "libcudss.so"]
+    for base in sys.path:
+        names += sorted(glob.glob(os.path.join(base, "nvidia", "cu*", "lib", "libcudss.so*")))
+        names += sorted(glob.glob(os.path.join(base, "nvidia", "cudss", "lib", "libcudss.so*")))
+    for name in names:
+        try:
+            lib = C.CDLL(name)
+        except OSError:
+            continue
+        ver = []
+        try:
+            for prop in (0, 1, 2):                       # MAJOR_VERSION, MINOR_VERSION, PATCH_LEVEL (libraryPropertyType)
+                v = C.c_int(0)
+                if lib.cudssGetProperty(prop, C.byref(v)) != 0:
+                    raise OSError("cudssGetProperty failed")
+                ver.append(str(v.value))
+        except Exception:
+            ver = ["?"]
+        return lib, "cuDSS %s found (%s)" % (".".join(ver), name)
+    return None, "cuDSS not found by dlopen (libcudss.so[.0], nvidia-cudss wheel paths): not in this image"
+
+
+def make_device_solver(asm, tol=1e-11):
+    """(solver, name, note): the device LU behind the reference's set_operator / solve re-use protocol
+    (newtonsolver.py:51,93). cuDSS is probed at run time; the path that exists and is tested in this image is
+    DeviceRfLU (cusolverRf re-factorisation on the device after a one-off host analysis), so it is what is returned —
+    the probe result is reported so that a deployment with cuDSS sees it named."""
+    _, text = probe_cudss()
+    return DeviceRfLU(asm, tol=tol), "cusolverRf (DeviceRfLU)", text + "; fallback in use: host analysis once (SciPy SuperLU), " \
+        "numeric re-factorisation and solves on the device (cusolverRf), every solve residual-checked"

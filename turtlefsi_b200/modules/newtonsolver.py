@@ -16,27 +16,29 @@ sm_100a kernels (through an assembler object: turtlefsi_b200.assembler.FSIAssemb
 """
 from math import isnan
 
-from ..boundary import flatten_bcs
+from ..boundary import BCPlan
 
 
 def solver_setup(assembler, dvp_, up_sol, bcs, **namespace):
     """Pre-assemble the linear part of the Jacobian (frozen at the state present now, as in the
     reference: SURVEY 8a "frozen-A_pre")."""
-    bc_dofs, bc_vals = flatten_bcs(bcs)
-    assembler.set_bc_dofs(bc_dofs)
+    bc_plan = BCPlan(bcs)                     # dof index maps built once; only values() runs per step
+    assembler.set_bc_dofs(bc_plan.dofs)
     A_pre = assembler.assemble_A_pre(dvp_["n"], dvp_["n-1"])
     if hasattr(assembler, "compress_A_pre"):
         assembler.compress_A_pre(A_pre)           # A_pre is final here (problem files edit the forms before)
     A = assembler.new_matrix()
     assembler.copy(A, A_pre)                  # A = Matrix(A_pre)
+    if hasattr(assembler, "bind_matrix"):
+        assembler.bind_matrix(A)              # persistent solver matrix: re-assemblies rewrite only the rows J_nl touches
     b = None
     F = "F_lin + F_nonlin"                    # descriptor; the forms live in the kernels
-    return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n)", A_pre=A_pre, A=A, b=b, up_sol=up_sol)
+    return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n)", A_pre=A_pre, A=A, b=b, up_sol=up_sol, bc_plan=bc_plan)
 
 
 def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_tstep, compiler_parameters,
                  dvp_, up_sol, dvp_res, rtol, atol, max_it, counter, first_step_num, verbose, assembler,
-                 residual_history=None, **namespace):
+                 residual_history=None, bc_plan=None, **namespace):
     """Newton scheme with the reference's Jacobian-reuse predicates (newtonsolver.py:44-113)."""
     # Initial values
     iter = 0
@@ -47,9 +49,15 @@ def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_t
     last_rel_res = residual
     last_residual = rel_res
     x, x1 = dvp_["n"], dvp_["n-1"]
-    bc_dofs, bc_vals = flatten_bcs(bcs)         # dof set is fixed; values may be time dependent
-    g = assembler.to_device(bc_vals)
-    up_sol_dirty = False
+    # The dof set uploaded by solver_setup is normally fixed and only the values are time dependent; a pre_solve
+    # hook may nevertheless hand back another list (the reference re-reads `bcs` at every call): then the device
+    # set is replaced, so that g always lines up with the dofs the kernels index.
+    if bc_plan is None or not bc_plan.matches(bcs):
+        bc_plan = BCPlan(bcs)
+    if getattr(assembler, "bc_dofs", None) is None or len(assembler.bc_dofs) != len(bc_plan.dofs) \
+            or not (assembler.bc_dofs == bc_plan.dofs).all():
+        assembler.set_bc_dofs(bc_plan.dofs)
+    g = assembler.to_device(bc_plan.values(bcs))
     while rel_res > rtol and residual > atol and iter < max_it:
         # Check if recompute Jacobian from 'recompute_tstep' (time step)
         recompute_for_timestep = iter == 0 and (counter % recompute_tstep == 0)
@@ -70,7 +78,6 @@ def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_t
             assembler.ident_zeros(A)
             assembler.apply_bc_matrix(A)
             up_sol.set_operator(A)                            # new values -> re-factorise
-            up_sol_dirty = True
 
         # Assemble right hand side vector
         if b is None:
@@ -104,4 +111,4 @@ def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_t
             residual_history.append((counter, iter, residual, rel_res))
         iter += 1
 
-    return dict(up_sol=up_sol, A=A, b=b)
+    return dict(up_sol=up_sol, A=A, b=b, bc_plan=bc_plan)

@@ -190,7 +190,8 @@ class HaloExchange:
                     for k, v in lists.items()}
         self.owned_mask = owned_dof_mask
 
-    def exchange(self, x):
+    def exchange(self, x, overlap=None):
+        """overlap: optional callable run after the transfers are queued and before they are waited for."""
         import ctypes as C
 
         import torch
@@ -206,9 +207,11 @@ class HaloExchange:
         for key, peer in (("recv_below", self.rank - 1), ("recv_above", self.rank + 1)):
             if self.idx[key] is not None:
                 ops.append(dist.P2POp(dist.irecv, self.buf[key], peer))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if overlap is not None:
+            overlap()
+        for req in reqs:
+            req.wait()
         for key in ("recv_below", "recv_above"):
             if self.idx[key] is not None:
                 asm._check(asm.lib.tfsi_halo_unpack(asm.h, p(x), p(self.idx[key]), self.idx[key].numel(), p(self.buf[key]), st))
@@ -234,4 +237,8 @@ def build_partitioned_workload(n, device, rank, world, regions, dt, theta, qdeg_
     bc = np.concatenate([space.node_dof(f, a)[on_bnd] for f in (0, 1) for a in range(3)]).astype(np.int32)
     asm.set_bc_dofs(bc)
     halo = HaloExchange(asm, halo_lists(slab, space, gk), rank, world, int(slab.cell_owned.sum()))
+    halo.owned_node_mask = gk.owned
+    ghost_nodes = np.nonzero(~gk.owned)[0]
+    base, nc = space.node_base[ghost_nodes], space.node_ncomp[ghost_nodes]
+    halo.ghost_dofs = (np.repeat(base, nc) + (np.arange(nc.sum()) - np.repeat(np.cumsum(nc) - nc, nc))).astype(np.int64)
     return mesh, space, asm, x, x1, bc, halo, time.time() - t0

@@ -6,8 +6,9 @@ The reference runs SPMD under MPI: DOLFIN partitions the cells (SCOTCH) and keep
 row blocks [dep]. Here, with no external partitioner:
 
 * cells -> parts by recursive coordinate bisection of the centroids (deterministic, balanced to one cell);
-* a mesh node (vertex or edge midpoint) is owned by the LOWEST part touching it [DOLFIN votes at
-  random: ownership need not match, only the global numbering does];
+* a mesh node (vertex or edge midpoint) is owned by ONE of the parts touching it, chosen by a deterministic
+  balanced rule (`node_owners`; the plain "lowest part" rule makes part 0 assemble all the ghost layers)
+  [DOLFIN votes at random: ownership need not match, only the global numbering does];
 * part r assembles its own cells plus the ghost cells that touch a node it owns, so that every OWNED
   CSR row is complete without any reduction of matrix entries; rows of ghost dofs are not used;
 * before an assembly the ghost dofs of the iterate are refreshed from their owners
@@ -25,10 +26,17 @@ from .mesh import Mesh
 from .space import MixedSpace
 
 
-def rcb_partition(mesh, nparts):
+def rcb_partition(mesh, nparts, metric="length"):
     """part id of every cell: recursive coordinate bisection of the cell centroids. The widest direction
-    is cut so that the two sides get cell counts proportional to the parts they will hold."""
-    cen = mesh.coords[mesh.cells].mean(axis=1)
+    is cut so that the two sides get cell counts proportional to the parts they will hold. metric="cells" measures
+    the width in CELLS (extent / median cell extent along the axis) instead of length: on anisotropic meshes the cut
+    then crosses the fewest cells, i.e. the interface (and the ghost layer) is smallest."""
+    X = mesh.coords[mesh.cells]
+    cen = X.mean(axis=1)
+    if metric == "cells":
+        cen = cen / np.median(X.max(axis=1) - X.min(axis=1), axis=0)
+    elif metric != "length":
+        raise ValueError(metric)
     part = np.zeros(mesh.num_cells, dtype=np.int32)
 
     def split(idx, p0, np_):
@@ -46,19 +54,75 @@ def rcb_partition(mesh, nparts):
     return part
 
 
+def node_owners(cell_nodes, cell_part, world, num_nodes, balanced=True):
+    """owner part of every mesh node (vertex or edge midpoint), a pure function of the SET of parts touching the node,
+    so that every rank computes the same answer from the global cell partition.
+
+    balanced=False: the lowest part touching the node (then part 0 owns all of its interfaces and assembles the most
+    ghost cells, the last part none). balanced=True: every pair of neighbouring parts (p, q) gets an orientation
+    "p owns the nodes shared with q", chosen greedily — largest interfaces first, towards the part that owns less so
+    far — and a node shared by several parts goes to the part that wins most of the pairwise contests inside its set
+    (ties: lowest part). The ghost layers (and with them the redundant cell work) are spread over the parts."""
+    if world > 62:
+        balanced = False
+    cn = cell_nodes
+    if not balanced:
+        owner = np.full(num_nodes, world, dtype=np.int32)
+        np.minimum.at(owner, cn.ravel(), np.repeat(cell_part, cn.shape[1]))
+        return owner
+    mask = np.zeros(num_nodes, dtype=np.int64)
+    for p in range(world):                                    # parts touching each node, as a bit set
+        nodes = np.unique(cn[cell_part == p])
+        mask[nodes] |= np.int64(1) << np.int64(p)
+    umask, inv, cnt = np.unique(mask, return_inverse=True, return_counts=True)
+    sets = [[p for p in range(world) if (int(m) >> p) & 1] for m in umask]
+    pair = {}
+    for st, c in zip(sets, cnt):
+        for i, p in enumerate(st):
+            for q in st[i + 1:]:
+                pair[(p, q)] = pair.get((p, q), 0) + int(c)
+    load = np.zeros(world, dtype=np.int64)
+    beats = np.zeros((world, world), dtype=bool)              # beats[p, q]: p owns what it shares with q
+    ordered = sorted(pair.items(), key=lambda kv: (-kv[1], kv[0]))
+    # the (up to 16) largest interfaces: exhaustive search for the orientation with the smallest maximum load
+    # (then the smallest sum of squares); the small rest greedily
+    top = ordered[:16]
+    if top:
+        k = len(top)
+        P = np.array([pq[0] for pq, _ in top]); Q = np.array([pq[1] for pq, _ in top])
+        Cw = np.array([c for _, c in top], dtype=np.int64)
+        bits = (np.arange(1 << k, dtype=np.int64)[:, None] >> np.arange(k)) & 1          # 1: q owns
+        loads = np.zeros((1 << k, world), dtype=np.int64)
+        for j in range(k):
+            np.add.at(loads, (np.arange(1 << k), np.where(bits[:, j] == 1, Q[j], P[j])), Cw[j])
+        score = loads.max(axis=1).astype(np.float64) * 1e6 + (loads.astype(np.float64) ** 2).sum(axis=1) / max(float(Cw.sum()) ** 2, 1.0)
+        best = int(np.argmin(score))                                                     # first minimum: deterministic
+        for j in range(k):
+            w, l = (Q[j], P[j]) if bits[best, j] else (P[j], Q[j])
+            beats[w, l] = True
+            load[w] += Cw[j]
+    for (p, q), c in ordered[16:]:
+        w, l = (p, q) if load[p] <= load[q] else (q, p)
+        beats[w, l] = True
+        load[w] += c
+    owner_of_set = np.empty(len(umask), dtype=np.int32)
+    for k, st in enumerate(sets):
+        wins = [sum(beats[p, q] for q in st) for p in st]
+        owner_of_set[k] = st[int(np.argmax(wins))] if st else world      # argmax: first maximum = lowest part
+    return owner_of_set[inv]
+
+
 class RankView:
     """what rank `rank` of `world` works on: local mesh (own + ghost cells), local space, maps to the
     global numbering and the halo lists per peer."""
 
-    def __init__(self, mesh, rank, world, biharmonic=False, cell_part=None, gspace=None):
+    def __init__(self, mesh, rank, world, biharmonic=False, cell_part=None, gspace=None, balanced=True, node_owner=None):
         self.rank, self.world = rank, world
         self.cell_part = rcb_partition(mesh, world) if cell_part is None else cell_part
         gs = MixedSpace(mesh, biharmonic=biharmonic) if gspace is None else gspace
         self.gspace = gs
         cn = gs.cell_nodes                                                    # [nc, n2] global node ids
-        # node owner = lowest part among the cells containing the node
-        owner = np.full(gs.num_nodes, world, dtype=np.int32)
-        np.minimum.at(owner, cn.ravel(), np.repeat(self.cell_part, cn.shape[1]))
+        owner = node_owners(cn, self.cell_part, world, gs.num_nodes, balanced) if node_owner is None else node_owner
         self.node_owner_global = owner
         own_cell = self.cell_part == rank
         ghost_cell = ~own_cell & (owner[cn] == rank).any(axis=1)
@@ -155,7 +219,9 @@ class HaloExchangeRCB:
         buf = lambda d: {p: torch.empty(len(v), dtype=torch.float64, device=dev) for p, v in d.items()}
         self.send_buf, self.recv_buf = buf(send), buf(recv)
 
-    def exchange(self, x):
+    def exchange(self, x, overlap=None):
+        """overlap: optional callable run after the transfers are queued and before they are waited for (work that
+        does not depend on the ghost values, e.g. the initialisation A := A_pre, then runs under the transfer)."""
         import ctypes as C
 
         import torch.distributed as dist
@@ -168,8 +234,10 @@ class HaloExchangeRCB:
             ops.append(dist.P2POp(dist.isend, self.send_buf[p], p))
         for p in sorted(self.recv_idx):
             ops.append(dist.P2POp(dist.irecv, self.recv_buf[p], p))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if overlap is not None:
+            overlap()
+        for req in reqs:
+            req.wait()
         for p, idx in sorted(self.recv_idx.items()):
             asm._check(asm.lib.tfsi_halo_unpack(asm.h, ptr(x), ptr(idx), idx.numel(), ptr(self.recv_buf[p]), st))
