@@ -552,7 +552,7 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong: skip the additional weak-scaling measurement")
     ap.add_argument("--sweep", default="", help="comma-separated ncube list: config 5 size sweep (per-GPU sizes, weak)")
     ap.add_argument("--deterministic", action="store_true", help="colour-ordered scatter (bitwise reproducible)")
-    ap.add_argument("--newton", type=int, default=int(os.environ.get("TFSI_BENCH_NEWTON_NCUBE", "10")),
+    ap.add_argument("--newton", type=int, default=int(os.environ.get("TFSI_BENCH_NEWTON_NCUBE", "6")),
                     help="ncube of the 3-D tube on which one full Newton step (with the device LU) is timed; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -84,6 +84,19 @@ class DeviceRfLU:
 
     def set_operator(self, A_vals):
         self._vals, self._dirty = A_vals, True
+        self._anorm = None
+
+    def _norm_inf(self):
+        """max row sum of |A| (for the normwise backward error of a solve)."""
+        if self._anorm is None:
+            import torch
+            if getattr(self, "_row_of", None) is None:
+                counts = (self.rowptr32[1:] - self.rowptr32[:-1]).long()
+                self._row_of = torch.repeat_interleave(torch.arange(self.n, device=counts.device), counts)
+            rs = torch.zeros(self.n, dtype=torch.float64, device=self._vals.device)
+            rs.index_add_(0, self._row_of, self._vals.abs())
+            self._anorm = float(rs.max())
+        return self._anorm
 
     def _host_analysis(self):
         import time
@@ -189,7 +202,10 @@ class DeviceRfLU:
                 rn = float(torch.linalg.vector_norm(r))
                 if not np.isfinite(rn):
                     break
-                if rn <= self.tol * bn or bn == 0.0:
+                # accepted: residual below tol |b|, or — when b itself is at round-off level of A x, as in the last
+                # Newton iterations — a normwise backward error |r| / (|A| |x| + |b|) of a few ulps
+                xn = float(torch.linalg.vector_norm(x, ord=float("inf")))
+                if rn <= self.tol * bn or bn == 0.0 or rn <= 64 * 2.2e-16 * (self._norm_inf() * xn * np.sqrt(self.n) + bn):
                     ok = True
                     break
                 if it < self.max_refine:
