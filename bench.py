@@ -345,21 +345,43 @@ def prepare_matrices(w):
     A = asm.new_matrix()
     asm.assemble_A_pre(w.xd, w.x1d, out=A)
     w.apre_nnz = asm.compress_A_pre(A)
-    w.bound_entries = asm.bind_matrix(A)
+    free, _ = torch.cuda.mem_get_info(asm.device)
+    w.pair = (not NO_PAIR) and 8 * asm.nnz * 2.5 < free        # two more matrices must fit comfortably (not at 6 M tets per GPU)
+    if w.pair:
+        # two matrices used alternately (the previous Jacobian is dead once the next one is assembled): the idle one
+        # is re-initialised in the background (masked copy from the dense A_pre) under the FP64-bound kernels
+        w.A_pre = A
+        w.As = [asm.new_matrix(), asm.new_matrix()]
+        w.bound_entries = asm.bind_matrix_pair(w.As[0], w.As[1], w.A_pre)
+        A = w.As[0]
+    else:
+        w.As = [A]
+        w.bound_entries = asm.bind_matrix(A)
+    w.k = 0
     w.A = A
     w.b = asm.new_vector()
     torch.cuda.synchronize()
 
 
+NO_PAIR = False
+
+
+def next_matrix(w):
+    w.k += 1
+    w.A = w.As[w.k % len(w.As)]
+    return w.A
+
+
 def make_step(w):
     asm, halo = w.asm, w.halo
     if halo is None:
-        return lambda: asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A)
+        return lambda: asm.assemble_jacobian(w.xd, w.x1d, "compressed", next_matrix(w))
 
     def step():
         # ghost dofs of the Newton iterate over NCCL; the x-independent A := A_pre runs under the transfer
-        halo.exchange(w.xd, overlap=lambda: asm.assemble_jacobian(None, None, "compressed", w.A, phase=1))
-        asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A, phase=2)
+        A = next_matrix(w)
+        halo.exchange(w.xd, overlap=lambda: asm.assemble_jacobian(None, None, "compressed", A, phase=1))
+        asm.assemble_jacobian(w.xd, w.x1d, "compressed", A, phase=2)
     return step
 
 
@@ -454,7 +476,13 @@ def measure(w, args, device, world, dist, local_rank, steps, warmup, full=True):
         return a.elapsed_time(z) / k
     gd = torch.zeros(len(w.bc), dtype=torch.float64, device=device)
     out["ms_res"] = timed(lambda: asm.assemble_residual(w.xd, w.x1d, w.b))
-    out["ms_init"] = timed(lambda: asm.assemble_jacobian(None, None, "compressed", w.A, phase=1))
+    # the same step with the masked re-initialisation in the FOREGROUND (what a single bound matrix costs)
+    os.environ["TFSI_NO_BACKGROUND_INIT"] = "1"
+    asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A)
+    t_both = timed(lambda: asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A))          # foreground init + kernels
+    del os.environ["TFSI_NO_BACKGROUND_INIT"]
+    out["ms_step_foreground_init"] = t_both
+    out["ms_init"] = t_both - out["kf_ms"] - out["ks_ms"]
     out["ms_ident"] = timed(lambda: asm.ident_zeros(w.A))
     out["ms_bc"] = timed(lambda: (asm.apply_bc_matrix(w.A), asm.apply_bc_rhs(w.b, w.xd, gd), asm.apply_bc_vec(w.xd, gd)))
     out["ms_norm"] = timed(lambda: asm.sumsq(w.b))
@@ -476,7 +504,7 @@ def measure(w, args, device, world, dist, local_rank, steps, warmup, full=True):
     e2e_steps = 8
     t0 = time.perf_counter()
     for it in range(e2e_steps):
-        asm.newton_assemble_host(xh, x1h if it % 4 == 0 else None, gh, "compressed", w.A, bh, recompute=True)
+        asm.newton_assemble_host(xh, x1h if it % 4 == 0 else None, gh, "compressed", next_matrix(w), bh, recompute=True)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     MX = None if world == 1 else dist.ReduceOp.MAX
@@ -552,10 +580,13 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong: skip the additional weak-scaling measurement")
     ap.add_argument("--sweep", default="", help="comma-separated ncube list: config 5 size sweep (per-GPU sizes, weak)")
     ap.add_argument("--deterministic", action="store_true", help="colour-ordered scatter (bitwise reproducible)")
+    ap.add_argument("--no-pair", action="store_true", help="one persistent matrix (foreground re-initialisation) instead of a pair")
     ap.add_argument("--newton", type=int, default=int(os.environ.get("TFSI_BENCH_NEWTON_NCUBE", "6")),
                     help="ncube of the 3-D tube on which one full Newton step (with the device LU) is timed; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    global NO_PAIR
+    NO_PAIR = args.no_pair
 
     if args.impl == "reference":
         run_reference(args)
@@ -590,6 +621,7 @@ def main():
     mesh_cells, n_fluid = w.mesh.num_cells, int((w.mesh.markers == 1).sum())
     ndofs, nnz, apre_nnz, bound_entries = w.space.num_dofs, w.asm.nnz, w.apre_nnz, w.bound_entries
     ncol = w.asm.num_colours
+    pair_mode = bool(w.pair)
 
     # ---- N > 1, strong: the weak-scaling configuration alongside (fewer steps) ------------------------------
     weak = None
@@ -653,10 +685,11 @@ def main():
         "problem_size": {"cells_total": m["total_cells"], "rank0_cells_incl_ghost": mesh_cells, "rank0_fluid_cells": n_fluid,
                          "rank0_dofs": ndofs, "rank0_nnz": nnz, "nnz_per_cell": nnz / mesh_cells,
                          "A_pre_nonzero_fraction": apre_nnz / nnz, "entries_rewritten_per_step": bound_entries,
-                         "max_ghost_cell_fraction": ghost_max, "colour_classes": ncol,
+                         "max_ghost_cell_fraction": ghost_max, "colour_classes": ncol, "matrix_pair": pair_mode,
                          "host_cpus_pinned_per_rank": ncpus_pinned},
         "breakdown_ms": {"jacobian_step": m["ms_step"], "jac_fluid_kernel": m["kf_ms"], "jac_solid_kernel": m["ks_ms"],
-                         "init_A_pre_rows": m["ms_init"], "halo_exchange_alone": m.get("ms_halo"),
+                         "init_A_pre_rows_if_foreground": m["ms_init"],
+                         "jacobian_step_foreground_init": m["ms_step_foreground_init"], "halo_exchange_alone": m.get("ms_halo"),
                          "residual": m["ms_res"], "ident_zeros": m["ms_ident"], "bc_apply": m["ms_bc"], "norm": m["ms_norm"],
                          "linear_solve": (newton or {}).get("linear_solve_ms")},
         "residual_cells_per_s": mesh_cells / (m["ms_res"] * 1e-3),

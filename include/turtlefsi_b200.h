@@ -167,7 +167,17 @@ int tfsi_invalidate_A_pre(tfsi_handle* h);
  * must not write to A_vals itself while it is bound. tfsi_set_bc_dofs, tfsi_compress_A_pre, tfsi_invalidate_A_pre
  * make the next assembly a full one. */
 int tfsi_bind_matrix(tfsi_handle* h, double* A_vals, void* stream);
+/* The same with TWO buffers that the caller alternates between re-assemblies (the previous Jacobian is dead once the
+ * next one is assembled): while tfsi_assemble_jacobian(..., A_k) runs its FP64-bound kernel over the fluid cells, the
+ * rows of the OTHER buffer are re-initialised in the background (lowest-priority stream, a 32-register masked copy
+ * from the DENSE A_pre — `Apre_vals`, the array registered by tfsi_compress_A_pre, which must stay valid and unchanged —
+ * that fits beside the Jacobian CTAs), so that the next assembly into it starts without any initialisation pass. The caller must
+ * be done with the other buffer (stream-ordered on `stream`) when it calls tfsi_assemble_jacobian. Costs a second
+ * matrix in HBM; any other order of use stays correct (the missing initialisation is then done in the foreground). */
+int tfsi_bind_matrix_pair(tfsi_handle* h, double* A0_vals, double* A1_vals, const double* Apre_vals, void* stream);
 int tfsi_unbind_matrix(tfsi_handle* h);
+/* statistics: blocks of the background kernel that ran on each SM since the last call (out256[smid]); synchronises */
+int tfsi_debug_bg_placement(tfsi_handle* h, int32_t* out256);
 /* entries rewritten by an assembly into the bound matrix (reporting) */
 int64_t tfsi_bound_init_entries(const tfsi_handle* h);
 

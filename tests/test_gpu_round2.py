@@ -77,6 +77,46 @@ def test_bound_matrix_partial_init_and_sentinel(tube_params):
     assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), asm.rowptr.cpu().numpy()) < 1e-14
 
 
+def test_matrix_pair_background_initialisation(tube_params):
+    """tfsi_bind_matrix_pair: two persistent matrices used alternately, the idle one re-initialised in the background
+    under the Jacobian kernels. Every assembly (also out-of-order use of the pair, and with ident_zeros / BC rows in
+    between) must give the matrix of the plain path."""
+    import torch
+    from turtlefsi_b200.assembler import FSIAssembler
+    common, regions = tube_params
+    mesh, space, x, x1 = _setup(6)
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"])
+    rng = np.random.default_rng(9)
+    asm.set_bc_dofs(rng.choice(space.num_dofs, size=500, replace=False).astype(np.int32))
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    A_pre = asm.assemble_A_pre(xd, x1d)
+    asm.compress_A_pre(A_pre)
+    A0, A1 = asm.new_matrix(), asm.new_matrix()
+    asm.bind_matrix_pair(A0, A1, A_pre)
+    rp = asm.rowptr.cpu().numpy()
+    order = [A0, A1, A0, A1, A1, A0, A0, A1, A0]              # regular alternation, then repeats (foreground fallback)
+    for it, A in enumerate(order):
+        xi = xd + 1e-3 * (it + 1) * torch.cos(torch.arange(space.num_dofs, device="cuda", dtype=torch.float64))
+        asm.assemble_jacobian(xi, x1d, "compressed", A)
+        asm.ident_zeros(A)
+        asm.apply_bc_matrix(A)
+        ref = asm.assemble_jacobian(xi, x1d, A_pre)               # unbound buffer, full path
+        asm.ident_zeros(ref)
+        asm.apply_bc_matrix(ref)
+        torch.cuda.synchronize()
+        assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), rp) < 1e-14, it
+    # split call (halo overlap): phase 1 then phase 2
+    A = A1 if order[-1] is A0 else A0
+    asm.assemble_jacobian(None, None, "compressed", A, phase=1)
+    asm.assemble_jacobian(xd, x1d, "compressed", A, phase=2)
+    asm.ident_zeros(A)
+    asm.apply_bc_matrix(A)                                    # bound matrices keep their unit rows: compare after both
+    ref = asm.assemble_jacobian(xd, x1d, A_pre)
+    asm.ident_zeros(ref)
+    asm.apply_bc_matrix(ref)
+    assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), rp) < 1e-14
+
+
 @pytest.mark.parametrize("degJ,npts", [(5, 15), (6, 24)])
 def test_jacobian_rule_in_chunks(degJ, npts, tube_params):
     """compiler_parameters["quadrature_degree"] is user-settable (problems/__init__.py:16-17, argpar.py:224-229):

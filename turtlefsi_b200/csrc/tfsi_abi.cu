@@ -66,8 +66,17 @@ struct tfsi_handle {
     // compressed copy of A_pre (tfsi_compress_A_pre)
     const double* cpre_src;
     uint32_t* cpre_bitmap; int64_t* cpre_base; double* cpre_val; int64_t cpre_nnz, cpre_words;
-    // persistent matrix (tfsi_bind_matrix): word mask of the rows J_nl scatters into
-    double* bound_A; int bound_dirty; uint32_t* tmask; int64_t bound_entries;
+    // persistent matrices (tfsi_bind_matrix / tfsi_bind_matrix_pair): word mask of the rows J_nl scatters into, and the
+    // state of each bound buffer: CLEAN = holds A_pre in every row an assembly will scatter into (no initialisation
+    // needed), USED = assembled into (masked re-initialisation needed), STALE = full initialisation needed
+    struct Bound { double* A; int state; int pending; cudaEvent_t ready; } bound[2];
+    int nbound;
+    uint32_t* tmask; int64_t bound_entries;
+    cudaStream_t bg_stream, hi_stream;        // pair mode: background initialisation (lowest priority) / cell kernels (highest)
+    cudaEvent_t ev_fork, ev_join;
+    int64_t bg_launches;
+    const double* pair_apre;                  // dense A_pre the background copy reads (pair mode)
+    int* bg_smid;                             // blocks of the background kernel per SM (debug statistics)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
@@ -197,32 +206,79 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
 // A := (A_pre | 0) + J_nl.
 // phase 0: everything; 1: only the x-independent initialisation A := A_pre; 2: only the cell kernels
 // (the host entry runs phase 1 under the H2D copy of x)
+enum { BOUND_CLEAN = 0, BOUND_USED = 1, BOUND_STALE = 2 };
+
+int find_bound(const tfsi_handle* h, const double* A) {
+    for (int i = 0; i < h->nbound; ++i) if (h->bound[i].A == A) return i;
+    return -1;
+}
+void mark_bound(tfsi_handle* h, int state) {          // A_pre / BC set changed: every bound matrix needs a full initialisation
+    for (int i = 0; i < h->nbound; ++i) h->bound[i].state = std::max(h->bound[i].state, state);
+}
+
 int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st, int phase = 0) {
     if (Apre == TFSI_APRE_COMPRESSED && !h->cpre_bitmap)
         return fail(h, TFSI_ERR_ARG, "TFSI_APRE_COMPRESSED given but no compressed A_pre is registered (tfsi_compress_A_pre)");
     const bool use_compressed = h->cpre_bitmap && Apre && (Apre == TFSI_APRE_COMPRESSED || Apre == h->cpre_src);
+    const int slot = find_bound(h, A);
+    const int64_t ngroups = (h->cpre_words + 31) / 32;
     if (phase != 2) {
-        // A := A_pre streamed ONCE from the bitmap-compressed copy (zero-fill + packed non-zeros); into the bound
-        // matrix only the rows that the cell kernels scatter into are rewritten
-        if (use_compressed) {
-            const bool partial = A == h->bound_A && h->tmask && !h->bound_dirty;
-            bitmap_stream_kernel<1><<<grid_for(((h->cpre_words + 31) / 32) * 32, 256, h->sm_count), 256, 0, st>>>(
+        if (slot >= 0 && h->bound[slot].pending) {     // initialised in the background during the previous assembly
+            CK(h, cudaStreamWaitEvent(st, h->bound[slot].ready, 0));
+            h->bound[slot].pending = 0;
+        }
+        // A := A_pre streamed ONCE from the bitmap-compressed copy (zero-fill + packed non-zeros); into a bound matrix
+        // only the rows that the cell kernels scatter into are rewritten, and nothing at all when it is still CLEAN
+        if (use_compressed && slot >= 0 && h->bound[slot].state == BOUND_CLEAN) {
+            ;
+        } else if (use_compressed) {
+            const bool partial = slot >= 0 && h->tmask && h->bound[slot].state == BOUND_USED;
+            bitmap_stream_kernel<1><<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(
                 h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A, partial ? h->tmask : nullptr);
             CK(h, cudaGetLastError());
-            if (A == h->bound_A) h->bound_dirty = 0;
+            h->launches++;
+            if (slot >= 0) h->bound[slot].state = BOUND_CLEAN;
         } else {
             if (Apre) CK(h, cudaMemcpyAsync(A, Apre, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
             else CK(h, cudaMemsetAsync(A, 0, (size_t)h->nnz * sizeof(double), st));
-            if (A == h->bound_A) h->bound_dirty = 1;      // not A_pre-initialised by the compressed copy
+            h->launches++;
+            if (slot >= 0) h->bound[slot].state = BOUND_STALE;      // not initialised from the compressed copy
         }
-        h->launches++;
     }
     if (phase == 1) return 0;
+    if (slot >= 0) h->bound[slot].state = (h->bound[slot].state == BOUND_CLEAN) ? BOUND_USED : BOUND_STALE;
+    // pair mode: the OTHER matrix of the pair is re-initialised in the background, under the FP64-bound kernel over
+    // the fluid cells (lowest-priority stream; the cell kernels move to a highest-priority stream so that the block
+    // scheduler always prefers them and the background blocks only fill the registers they leave free)
+    const int other = (slot >= 0 && h->nbound == 2) ? 1 - slot : -1;
+    const bool bg = other >= 0 && use_compressed && h->tmask && h->pair_apre && h->bound[other].state == BOUND_USED && !h->bound[other].pending &&
+                    !getenv("TFSI_NO_BACKGROUND_INIT");
+    cudaStream_t ks = st;
+    if (bg) {
+        CK(h, cudaEventRecord(h->ev_fork, st));
+        CK(h, cudaStreamWaitEvent(h->hi_stream, h->ev_fork, 0));
+        CK(h, cudaStreamWaitEvent(h->bg_stream, h->ev_fork, 0));
+        ks = h->hi_stream;
+    }
+    bool kicked = false;
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
-        int rc = h->gdim == 3 ? launch_jacobian_region<3>(h, r, x, x1, A, st) : launch_jacobian_region<2>(h, r, x, x1, A, st);
+        if (bg && !kicked) {
+            masked_copy_bg_kernel<<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, h->bg_smid);
+            CK(h, cudaGetLastError());
+            CK(h, cudaEventRecord(h->bound[other].ready, h->bg_stream));
+            h->bound[other].state = BOUND_CLEAN;
+            h->bound[other].pending = 1;
+            h->launches++; h->bg_launches++;
+            kicked = true;
+        }
+        int rc = h->gdim == 3 ? launch_jacobian_region<3>(h, r, x, x1, A, ks) : launch_jacobian_region<2>(h, r, x, x1, A, ks);
         if (rc) return rc;
+    }
+    if (bg) {
+        CK(h, cudaEventRecord(h->ev_join, h->hi_stream));
+        CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     return 0;
 }
@@ -348,6 +404,12 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals); cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val); cudaFree(h->tmask);
+    cudaFree(h->bg_smid);
+    if (h->bg_stream) cudaStreamDestroy(h->bg_stream);
+    if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (auto& b : h->bound) if (b.ready) cudaEventDestroy(b.ready);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
@@ -416,7 +478,9 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
     h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0; h->fl_scale = 1.0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
-    h->bound_A = nullptr; h->bound_dirty = 0; h->tmask = nullptr; h->bound_entries = 0;
+    h->nbound = 0; h->tmask = nullptr; h->bound_entries = 0; h->bg_launches = 0;
+    for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; b.ready = nullptr; }
+    h->bg_stream = h->hi_stream = nullptr; h->ev_fork = h->ev_join = nullptr; h->pair_apre = nullptr; h->bg_smid = nullptr;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     if (h->ext < 0 || h->ext > TFSI_EXT_ELASTIC) { delete h; return fail(nullptr, TFSI_ERR_ARG, "unknown extrapolation code %d", h->ext); }
@@ -590,7 +654,7 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
     if (!h || !x || !x1 || !Apre) return fail(h, TFSI_ERR_ARG, "null argument");
     if (!h->colidx) return fail(h, TFSI_ERR_UNSUPPORTED, "the column array was released (tfsi_release_pattern)");
     DeviceGuard dg(h);
-    if (Apre == h->cpre_src) { h->cpre_src = nullptr; h->bound_dirty = 1; }     // values change: compressed copy is stale
+    if (Apre == h->cpre_src) { h->cpre_src = nullptr; mark_bound(h, BOUND_STALE); }     // values change: compressed copy is stale
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(Apre, 0, (size_t)h->nnz * sizeof(double), st));
@@ -683,7 +747,9 @@ int tfsi_invalidate_A_pre(tfsi_handle* h) {
     h->cpre_src = nullptr;
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val);
     h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
-    h->bound_dirty = 1;
+    mark_bound(h, BOUND_STALE);
+    for (auto& b : h->bound) b.pending = 0;
+    h->pair_apre = nullptr;                   // the background copy must not read a dense A_pre that is being edited
     return 0;
 }
 
@@ -722,48 +788,103 @@ int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
 
 int64_t tfsi_compressed_nnz(const tfsi_handle* h) { return h ? h->cpre_nnz : -1; }
 
+namespace {
+int build_touched_mask(tfsi_handle* h, cudaStream_t st) {
+    if (h->tmask) return 0;
+    const int64_t ngroups = (h->cpre_words + 31) / 32;
+    // rows that J_nl scatters into: velocity + pressure rows of active fluid cells, velocity rows of active solid cells
+    uint8_t* flag = nullptr;
+    CK(h, cudaMalloc((void**)&flag, std::max<size_t>((size_t)h->N, 1)));
+    CK(h, cudaMemsetAsync(flag, 0, (size_t)h->N, st));
+    const int gn2 = h->gdim * h->n2;
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        const bool fl = r.rc.kind == TFSI_KIND_FLUID;
+        if (fl ? !r.rc.fluid_on : !r.rc.solid_on) continue;
+        const int lo = gn2, hi = fl ? 2 * gn2 + h->n1 : 2 * gn2;
+        mark_rows_kernel<<<grid_for(r.ncells * (hi - lo), 256, h->sm_count), 256, 0, st>>>(h->cell_dofs, r.cell_list, r.ncells, h->ndof, lo, hi, flag);
+    }
+    CK(h, cudaMalloc((void**)&h->tmask, std::max<size_t>((size_t)ngroups, 1) * sizeof(uint32_t)));
+    CK(h, cudaMemsetAsync(h->tmask, 0, (size_t)ngroups * sizeof(uint32_t), st));
+    touched_words_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, st>>>(h->rowptr, flag, h->N, h->tmask);
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(h->scratch + 2);
+    CK(h, cudaMemsetAsync(cnt, 0, sizeof *cnt, st));
+    count_pairs_kernel<<<grid_for(ngroups, 256, h->sm_count), 256, 0, st>>>(h->tmask, ngroups, cnt);
+    unsigned long long pairs = 0;
+    CK(h, cudaMemcpyAsync(&pairs, cnt, sizeof pairs, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    cudaFree(flag);
+    h->bound_entries = std::min<int64_t>((int64_t)pairs * 64, h->nnz);
+    return 0;
+}
+
+int bind_one(tfsi_handle* h, int slot, double* A, cudaStream_t st) {
+    const int64_t ngroups = (h->cpre_words + 31) / 32;
+    bitmap_stream_kernel<1><<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(
+        h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A, nullptr);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->bound[slot].A = A; h->bound[slot].state = BOUND_CLEAN; h->bound[slot].pending = 0;
+    if (!h->bound[slot].ready) CK(h, cudaEventCreateWithFlags(&h->bound[slot].ready, cudaEventDisableTiming));
+    return 0;
+}
+}  // namespace
+
 int tfsi_bind_matrix(tfsi_handle* h, double* A, void* stream) {
     if (!h || !A) return fail(h, TFSI_ERR_ARG, "null argument");
     if (!h->cpre_bitmap) return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix needs a compressed A_pre (tfsi_compress_A_pre)");
     DeviceGuard dg(h);
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ngroups = (h->cpre_words + 31) / 32;
-    if (!h->tmask) {
-        // rows that J_nl scatters into: velocity + pressure rows of active fluid cells, velocity rows of active solid cells
-        uint8_t* flag = nullptr;
-        CK(h, cudaMalloc((void**)&flag, std::max<size_t>((size_t)h->N, 1)));
-        CK(h, cudaMemsetAsync(flag, 0, (size_t)h->N, st));
-        const int gn2 = h->gdim * h->n2;
-        for (const Region& r : h->regions) {
-            if (r.ncells == 0) continue;
-            const bool fl = r.rc.kind == TFSI_KIND_FLUID;
-            if (fl ? !r.rc.fluid_on : !r.rc.solid_on) continue;
-            const int lo = gn2, hi = fl ? 2 * gn2 + h->n1 : 2 * gn2;
-            mark_rows_kernel<<<grid_for(r.ncells * (hi - lo), 256, h->sm_count), 256, 0, st>>>(h->cell_dofs, r.cell_list, r.ncells, h->ndof, lo, hi, flag);
-        }
-        CK(h, cudaMalloc((void**)&h->tmask, std::max<size_t>((size_t)ngroups, 1) * sizeof(uint32_t)));
-        CK(h, cudaMemsetAsync(h->tmask, 0, (size_t)ngroups * sizeof(uint32_t), st));
-        touched_words_kernel<<<grid_for(h->N, 256, h->sm_count), 256, 0, st>>>(h->rowptr, flag, h->N, h->tmask);
-        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(h->scratch + 2);
-        CK(h, cudaMemsetAsync(cnt, 0, sizeof *cnt, st));
-        count_pairs_kernel<<<grid_for(ngroups, 256, h->sm_count), 256, 0, st>>>(h->tmask, ngroups, cnt);
-        unsigned long long pairs = 0;
-        CK(h, cudaMemcpyAsync(&pairs, cnt, sizeof pairs, cudaMemcpyDeviceToHost, st));
-        CK(h, cudaStreamSynchronize(st));
-        cudaFree(flag);
-        h->bound_entries = std::min<int64_t>((int64_t)pairs * 64, h->nnz);
+    if (int rc = build_touched_mask(h, st)) return rc;
+    CK(h, cudaDeviceSynchronize());                       // a background initialisation of an earlier pair may be in flight
+    h->nbound = 1; h->bound[1].A = nullptr; h->pair_apre = nullptr;
+    return bind_one(h, 0, A, st);
+}
+
+int tfsi_bind_matrix_pair(tfsi_handle* h, double* A0, double* A1, const double* Apre_dense, void* stream) {
+    if (!h || !A0 || !A1 || A0 == A1) return fail(h, TFSI_ERR_ARG, "two distinct matrices are needed");
+    if (!Apre_dense || Apre_dense != h->cpre_src)
+        return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix_pair needs the dense A_pre that was given to tfsi_compress_A_pre");
+    if (!h->cpre_bitmap) return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix_pair needs a compressed A_pre (tfsi_compress_A_pre)");
+    DeviceGuard dg(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = build_touched_mask(h, st)) return rc;
+    CK(h, cudaDeviceSynchronize());
+    if (!h->bg_stream) {
+        int least = 0, greatest = 0;
+        CK(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const char* pe = getenv("TFSI_BG_PRIO");            // experiments: "same" = no priorities
+        if (pe && !strcmp(pe, "same")) greatest = least;
+        // the background copy is ONE persistent block per SM on the HIGHER-priority stream, launched first on the idle
+        // device: the work distributor hands a later grid's blocks out only after those of an earlier / higher one
+        CK(h, cudaStreamCreateWithPriority(&h->bg_stream, cudaStreamNonBlocking, greatest));
+        CK(h, cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, least));
+        CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        CK(h, cudaMalloc((void**)&h->bg_smid, 256 * sizeof(int)));
+        CK(h, cudaMemset(h->bg_smid, 0, 256 * sizeof(int)));
     }
-    bitmap_stream_kernel<1><<<grid_for(ngroups * 32, 256, h->sm_count), 256, 0, st>>>(
-        h->cpre_bitmap, h->cpre_words, h->cpre_base, h->nnz, nullptr, h->cpre_val, A, nullptr);
-    h->launches++;
-    CK(h, cudaGetLastError());
-    h->bound_A = A; h->bound_dirty = 0;
+    h->nbound = 2;
+    h->pair_apre = Apre_dense;
+    if (int rc = bind_one(h, 0, A0, st)) return rc;
+    return bind_one(h, 1, A1, st);
+}
+
+int tfsi_debug_bg_placement(tfsi_handle* h, int32_t* out256) {
+    if (!h || !out256 || !h->bg_smid) return fail(h, TFSI_ERR_ARG, "no matrix pair bound");
+    DeviceGuard dg(h);
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(out256, h->bg_smid, 256 * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemset(h->bg_smid, 0, 256 * sizeof(int)));
     return 0;
 }
 
 int tfsi_unbind_matrix(tfsi_handle* h) {
     if (!h) return TFSI_ERR_ARG;
-    h->bound_A = nullptr; h->bound_dirty = 0;
+    DeviceGuard dg(h);
+    CK(h, cudaDeviceSynchronize());
+    h->nbound = 0; h->pair_apre = nullptr;
+    for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; }
     return 0;
 }
 
@@ -810,7 +931,7 @@ int tfsi_set_bc_dofs(tfsi_handle* h, const int32_t* bc, int64_t n) {
     cudaFree(h->bc_dofs); h->bc_dofs = nullptr;
     cudaFree(h->hg); h->hg = nullptr;
     h->nbc = n;
-    h->bound_dirty = 1;            // unit rows of the previous set may sit in the bound matrix
+    mark_bound(h, BOUND_STALE);    // unit rows of the previous set may sit in the bound matrices
     if (int rc = upload(h, &h->bc_dofs, bc, (size_t)n)) return rc;
     CK(h, cudaMalloc((void**)&h->hg, std::max<size_t>((size_t)n, 1) * sizeof(double)));
     return 0;

@@ -273,7 +273,12 @@ __device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a,
 }
 
 template <int G, int NQ>
-__global__ void __launch_bounds__(FluidCfg<G>::WARPS * 32, FluidCfg<G>::CTAS) jac_fluid_kernel(CellArgs a)
+#ifndef TFSI_FLUID_MAXREG
+#define TFSI_FLUID_MAXREG 160
+#endif
+// 160 registers (no spills): 3 warps x 32 x 160 = 15360 of the 16384 registers of an SM sub-partition, so that one
+// 32-register warp of the background initialisation kernel (bitmap_expand_bg_kernel) fits beside them
+__global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     typedef typename FluidJac<G>::SM SM;
@@ -464,7 +469,8 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
 }
 
 template <int G, int NQ>
-__global__ void __launch_bounds__(SolidCfg<G>::WARPS * 32, SolidCfg<G>::CTAS) jac_solid_kernel(CellArgs a)
+// 160 registers as the fluid kernel: the background copy keeps running beside the three 4-warp CTAs per SM
+__global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
     typedef typename SolidJac<G>::SM SM;
@@ -1062,10 +1068,41 @@ __global__ void bitmap_build_kernel(const double* vals, int64_t nnz, uint32_t* b
         if (lane == 0) group_cnt[gidx] = c;
     }
 }
-// MODE 0: pack the non-zero values (cval[idx] = vals[k]); MODE 1: expand (A[k] = bit ? cval[idx] : 0).
-// MODE 1 with `tmask` (bit w & 31 of tmask[w >> 5] = bitmap word w holds an entry of a row the non-linear kernels
-// scatter into): only those words (in pairs: 64 entries, 512 B) are rewritten — the matrix bound by tfsi_bind_matrix
-// keeps A_pre in all other rows between assemblies.
+// expansion of ONE group (1024 consecutive entries, 32 bitmap words) by one warp: A[k] = bit ? cval[idx] : 0.
+// tm: bit w of the group's word mask = word w holds an entry of a row the non-linear kernels scatter into; only those
+// words (in pairs: 64 entries, 512 B) are rewritten. Every lane writes two consecutive entries (16-byte stores).
+__device__ __forceinline__ void expand_group(int64_t gidx, int lane, uint32_t tm, const uint32_t* bitmap, int64_t nwords,
+                                             const int64_t* group_base, int64_t nnz, const double* cval, double* A)
+{
+    const int64_t w = gidx * 32 + lane;
+    const uint32_t myword = (w < nwords) ? bitmap[w] : 0u;
+    int pre = __popc(myword);                         // inclusive scan over lanes -> exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+    pre -= __popc(myword);
+    const int64_t base = group_base[gidx];
+    const int pos = 2 * lane;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        if (((tm >> (2 * j)) & 3u) == 0u) continue;                 // warp-uniform: no lane reaches the shuffles
+        const uint32_t mlo = __shfl_sync(0xffffffffu, myword, 2 * j);
+        const uint32_t mhi = __shfl_sync(0xffffffffu, myword, 2 * j + 1);
+        const int start = __shfl_sync(0xffffffffu, pre, 2 * j);
+        const unsigned long long m = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
+        const int64_t k = (gidx * 32 + 2 * j) * 32 + pos;
+        if (k >= nnz) continue;
+        const int below = __popcll(m & ((1ull << pos) - 1ull));
+        const bool b0 = (m >> pos) & 1ull, b1 = (m >> (pos + 1)) & 1ull;
+        const int64_t idx = base + start + below;
+        const double v0 = b0 ? cval[idx] : 0.0;
+        const double v1 = b1 ? cval[idx + (b0 ? 1 : 0)] : 0.0;
+        if (k + 1 < nnz) *reinterpret_cast<double2*>(A + k) = make_double2(v0, v1);
+        else A[k] = v0;
+    }
+}
+
+// MODE 0: pack the non-zero values (cval[idx] = vals[k]); MODE 1: expand (A[k] = bit ? cval[idx] : 0), with `tmask`
+// (bit w & 31 of tmask[w >> 5], see expand_group) only into the rows of the bound matrix that have to be re-initialised.
 template <int MODE>
 __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, const int64_t* group_base, int64_t nnz,
                                      const double* vals_in, double* cval, double* A, const uint32_t* tmask = nullptr)
@@ -1076,8 +1113,11 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
     const int64_t ngroups = (nwords + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
     for (int64_t gidx = wid; gidx < ngroups; gidx += nw) {
-        const uint32_t tm = (MODE == 1 && tmask) ? tmask[gidx] : 0xffffffffu;   // warp-uniform
-        if (tm == 0u) continue;
+        if (MODE == 1) {
+            const uint32_t tm = tmask ? tmask[gidx] : 0xffffffffu;   // warp-uniform
+            if (tm != 0u) expand_group(gidx, lane, tm, bitmap, nwords, group_base, nnz, cval, A);
+            continue;
+        }
         const int64_t w = gidx * 32 + lane;
         const uint32_t myword = (w < nwords) ? bitmap[w] : 0u;
         int pre = __popc(myword);                         // inclusive scan over lanes -> exclusive
@@ -1085,36 +1125,68 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
         pre -= __popc(myword);
         const int64_t base = group_base[gidx];
-        if (MODE == 0) {
 #pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t m = __shfl_sync(0xffffffffu, myword, j);
-                const int start = __shfl_sync(0xffffffffu, pre, j);
-                const int64_t k = (gidx * 32 + j) * 32 + lane;
-                if (k < nnz && ((m >> lane) & 1u)) cval[base + start + __popc(m & lt)] = vals_in[k];   // all lanes run every shuffle
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t m = __shfl_sync(0xffffffffu, myword, j);
+            const int start = __shfl_sync(0xffffffffu, pre, j);
+            const int64_t k = (gidx * 32 + j) * 32 + lane;
+            if (k < nnz && ((m >> lane) & 1u)) cval[base + start + __popc(m & lt)] = vals_in[k];   // all lanes run every shuffle
+        }
+    }
+}
+
+// BACKGROUND re-initialisation of the idle matrix of a pair (tfsi_bind_matrix_pair) while the FP64-bound Jacobian
+// kernels run: dst[k] = src[k] (src = the dense A_pre) for the 64-entry word pairs of the rows the cell kernels scatter
+// into. A plain masked copy: loads are independent of each other (no bitmap / prefix / packed-value chain as in the
+// expansion above), so that ONE 32-register warp per SM sub-partition — what the 3 x 160-register warps of the Jacobian
+// CTAs leave free — keeps enough bytes in flight. A warp owns 32 consecutive groups (lane l fetches the mask of group l),
+// copies BG_BATCH pairs (512 B each) per round trip; many short blocks on a lowest-priority stream fill the gap on every SM.
+constexpr int BG_GROUPS_PER_WARP = 32;
+#ifndef BG_BATCH
+#define BG_BATCH 4
+#endif
+__global__ void __launch_bounds__(128, 16) masked_copy_bg_kernel(const uint32_t* tmask, int64_t ngroups, int64_t nnz,
+                                                                 const double* src, double* dst, int* smid_count)
+{
+    const int lane = threadIdx.x & 31;
+    if (smid_count && threadIdx.x == 0) {          // placement statistics: blocks per SM (tfsi_debug_bg_placement)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicAdd(smid_count + (smid & 255), 1);
+    }
+    // persistent: the grid is ONE block per SM (launched on an idle device, before the Jacobian kernel, on a stream of
+    // higher priority), every warp strides over chunks of 32 groups
+    for (int64_t g0 = ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * BG_GROUPS_PER_WARP; g0 < ngroups;
+         g0 += (int64_t)gridDim.x * 4 * BG_GROUPS_PER_WARP) {
+    const uint32_t mytm = (g0 + lane < ngroups) ? tmask[g0 + lane] : 0u;
+    // pair mask of my group: bit j = word pair j (entries 64 j .. 64 j + 63 of the group) is to be copied
+    uint32_t pm = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pm |= (((mytm >> (2 * j)) & 3u) ? 1u : 0u) << j;
+    for (int g = 0; g < BG_GROUPS_PER_WARP; ++g) {
+        const uint32_t p = __shfl_sync(0xffffffffu, pm, g);      // warp-uniform
+        if (p == 0u) continue;
+        const int64_t k0 = (g0 + g) * 1024 + 2 * lane;
+        constexpr int NB = BG_BATCH;
+#pragma unroll 1
+        for (int b0 = 0; b0 < 16; b0 += NB) {
+            if (((p >> b0) & ((1u << NB) - 1u)) == 0u) continue;
+            double2 v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int64_t k = k0 + (b0 + j) * 64;
+                if (((p >> (b0 + j)) & 1u) && k + 1 < nnz) v[j] = __ldcs(reinterpret_cast<const double2*>(src + k));
             }
-        } else {
-            // expand: every lane writes two consecutive entries (16-byte stores, 512 B per warp instruction)
-#pragma unroll 4
-            for (int j = 0; j < 16; ++j) {
-                if (((tm >> (2 * j)) & 3u) == 0u) continue;                 // warp-uniform: no lane reaches the shuffles
-                const uint32_t mlo = __shfl_sync(0xffffffffu, myword, 2 * j);
-                const uint32_t mhi = __shfl_sync(0xffffffffu, myword, 2 * j + 1);
-                const int start = __shfl_sync(0xffffffffu, pre, 2 * j);
-                const unsigned long long m = (unsigned long long)mlo | ((unsigned long long)mhi << 32);
-                const int pos = 2 * lane;
-                const int64_t k = (gidx * 32 + 2 * j) * 32 + pos;
-                if (k >= nnz) continue;
-                const int below = __popcll(m & ((1ull << pos) - 1ull));
-                const bool b0 = (m >> pos) & 1ull, b1 = (m >> (pos + 1)) & 1ull;
-                const int64_t idx = base + start + below;
-                const double v0 = b0 ? cval[idx] : 0.0;
-                const double v1 = b1 ? cval[idx + (b0 ? 1 : 0)] : 0.0;
-                if (k + 1 < nnz) *reinterpret_cast<double2*>(A + k) = make_double2(v0, v1);
-                else A[k] = v0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int64_t k = k0 + (b0 + j) * 64;
+                if (((p >> (b0 + j)) & 1u) && k + 1 < nnz) __stcs(reinterpret_cast<double2*>(dst + k), v[j]);
             }
         }
     }
+    }
+    // the last (odd) entry of the matrix, if any, is not covered by the 16-byte copies
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (nnz & 1)) dst[nnz - 1] = src[nnz - 1];
 }
 
 // rows that the non-linear Jacobian kernels scatter into: the local dofs [lo, hi) of every cell of a region
