@@ -1,5 +1,6 @@
 """GPU experiment: on which SMs do the blocks of the persistent background copy land (one per SM wanted)?"""
 import sys, os
+os.environ["TFSI_BG_STATS"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench

@@ -77,6 +77,7 @@ struct tfsi_handle {
     int64_t bg_launches;
     const double* pair_apre;                  // dense A_pre the background copy reads (pair mode)
     int* bg_smid;                             // blocks of the background kernel per SM (debug statistics)
+    int suppress_bg;                          // host entry: A := A_pre already runs under the H2D copy
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
@@ -252,7 +253,7 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const dou
     // scheduler always prefers them and the background blocks only fill the registers they leave free)
     const int other = (slot >= 0 && h->nbound == 2) ? 1 - slot : -1;
     const bool bg = other >= 0 && use_compressed && h->tmask && h->pair_apre && h->bound[other].state == BOUND_USED && !h->bound[other].pending &&
-                    !getenv("TFSI_NO_BACKGROUND_INIT");
+                    !h->suppress_bg && !getenv("TFSI_NO_BACKGROUND_INIT");
     cudaStream_t ks = st;
     if (bg) {
         CK(h, cudaEventRecord(h->ev_fork, st));
@@ -265,7 +266,10 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const dou
         if (r.ncells == 0) continue;
         if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
         if (bg && !kicked) {
-            masked_copy_bg_kernel<<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, h->bg_smid);
+            if (getenv("TFSI_BG_STATS"))
+                masked_copy_bg_kernel<true><<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, h->bg_smid);
+            else
+                masked_copy_bg_kernel<false><<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, nullptr);
             CK(h, cudaGetLastError());
             CK(h, cudaEventRecord(h->bound[other].ready, h->bg_stream));
             h->bound[other].state = BOUND_CLEAN;
@@ -480,7 +484,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     h->nbound = 0; h->tmask = nullptr; h->bound_entries = 0; h->bg_launches = 0;
     for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; b.ready = nullptr; }
-    h->bg_stream = h->hi_stream = nullptr; h->ev_fork = h->ev_join = nullptr; h->pair_apre = nullptr; h->bg_smid = nullptr;
+    h->bg_stream = h->hi_stream = nullptr; h->ev_fork = h->ev_join = nullptr; h->pair_apre = nullptr; h->bg_smid = nullptr; h->suppress_bg = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     if (h->ext < 0 || h->ext > TFSI_EXT_ELASTIC) { delete h; return fail(nullptr, TFSI_ERR_ARG, "unknown extrapolation code %d", h->ext); }
@@ -1034,7 +1038,10 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
     h->launches++;
     CK(h, cudaGetLastError());
     if (recompute) {
-        if (int rc = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 2)) return rc;
+        h->suppress_bg = 1;        // the initialisation of this call ran under the H2D copy: nothing to hide, and a
+        int rc2 = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 2);   // background copy would only slow the kernels down
+        h->suppress_bg = 0;
+        if (rc2) return rc2;
         if (int rc = tfsi_ident_zeros(h, A, st)) return rc;
         if (int rc = tfsi_apply_bc_matrix(h, A, st)) return rc;
     }
