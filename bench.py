@@ -346,7 +346,7 @@ def prepare_matrices(w):
     asm.assemble_A_pre(w.xd, w.x1d, out=A)
     w.apre_nnz = asm.compress_A_pre(A)
     free, _ = torch.cuda.mem_get_info(asm.device)
-    w.pair = (not NO_PAIR) and 8 * asm.nnz * 2.5 < free        # two more matrices must fit comfortably (not at 6 M tets per GPU)
+    w.pair = PAIR and 8 * asm.nnz * 2.5 < free                 # two more matrices must fit (not at 6 M tets per GPU)
     if w.pair:
         # two matrices used alternately (the previous Jacobian is dead once the next one is assembled): the idle one
         # is re-initialised in the background (masked copy from the dense A_pre) under the FP64-bound kernels
@@ -363,7 +363,7 @@ def prepare_matrices(w):
     torch.cuda.synchronize()
 
 
-NO_PAIR = False
+PAIR = False
 
 
 def next_matrix(w):
@@ -399,6 +399,10 @@ def parity_check(w, device, world, dist, nodes_per_rank=4):
         w.halo.exchange(xt)
         torch.cuda.synchronize()
         halo_exact = bool(torch.equal(xt, w.xd))
+    # a bound matrix keeps the unit rows that ident_zeros / bc.apply wrote into rows J_nl never touches (they are
+    # idempotent in the Newton loop); for the comparison with the unconstrained oracle, A is released first: the
+    # assembly below then is a full A := A_pre + J_nl
+    asm.unbind_matrix()
     asm.assemble_jacobian(xt, w.x1d, "compressed", w.A)
     asm.assemble_residual(xt, w.x1d, w.b)
     torch.cuda.synchronize()
@@ -484,7 +488,9 @@ def measure(w, args, device, world, dist, local_rank, steps, warmup, full=True):
     out["ms_step_foreground_init"] = t_both
     out["ms_init"] = t_both - out["kf_ms"] - out["ks_ms"]
     out["ms_ident"] = timed(lambda: asm.ident_zeros(w.A))
-    out["ms_bc"] = timed(lambda: (asm.apply_bc_matrix(w.A), asm.apply_bc_rhs(w.b, w.xd, gd), asm.apply_bc_vec(w.xd, gd)))
+    xs = w.xd.clone()                                   # bc.apply(x) writes the iterate: time it on a copy
+    out["ms_bc"] = timed(lambda: (asm.apply_bc_matrix(w.A), asm.apply_bc_rhs(w.b, xs, gd), asm.apply_bc_vec(xs, gd)))
+    del xs
     out["ms_norm"] = timed(lambda: asm.sumsq(w.b))
     if w.halo is not None:
         out["ms_halo"] = timed(lambda: w.halo.exchange(w.xd))
@@ -580,13 +586,15 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong: skip the additional weak-scaling measurement")
     ap.add_argument("--sweep", default="", help="comma-separated ncube list: config 5 size sweep (per-GPU sizes, weak)")
     ap.add_argument("--deterministic", action="store_true", help="colour-ordered scatter (bitwise reproducible)")
-    ap.add_argument("--no-pair", action="store_true", help="one persistent matrix (foreground re-initialisation) instead of a pair")
+    ap.add_argument("--pair", action="store_true",
+                    help="experimental: two persistent matrices, the idle one re-initialised in the background under the "
+                         "Jacobian kernels (tfsi_bind_matrix_pair; pays only for >= 2 M tets on an otherwise idle GPU)")
     ap.add_argument("--newton", type=int, default=int(os.environ.get("TFSI_BENCH_NEWTON_NCUBE", "6")),
                     help="ncube of the 3-D tube on which one full Newton step (with the device LU) is timed; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    global NO_PAIR
-    NO_PAIR = args.no_pair
+    global PAIR
+    PAIR = args.pair
 
     if args.impl == "reference":
         run_reference(args)

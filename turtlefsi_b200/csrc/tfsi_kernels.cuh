@@ -1082,6 +1082,8 @@ __device__ __forceinline__ void expand_group(int64_t gidx, int lane, uint32_t tm
     pre -= __popc(myword);
     const int64_t base = group_base[gidx];
     const int pos = 2 * lane;
+    // (tried: zero-fill stores first, then the non-zero entries as 8-byte overwrites, so that the bulk of the traffic does
+    // not wait for the bitmap / prefix / packed-value chain: 4.2 instead of 3.9 ms — twice the store instructions)
 #pragma unroll 4
     for (int j = 0; j < 16; ++j) {
         if (((tm >> (2 * j)) & 3u) == 0u) continue;                 // warp-uniform: no lane reaches the shuffles
