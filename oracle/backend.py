@@ -18,11 +18,11 @@ class OracleAssembler:
         self._c_ext = {"no_extrapolation": 0, "laplace": 1, "biharmonic": 2}.get(ext, -1)
         if use_c_port and (self._c_ext < 0 or (ext == "laplace" and sub != "constant")):
             raise ValueError("the C port covers lifting none | laplace/constant | biharmonic only")
+        self.mesh, self.space, self.regions, self.common = mesh, space, regions, dict(common)
         if use_c_port:
             # no_fluid / no_solid: the C port has no switch; drop the region instead (same zero forms)
             self.regions = [r for r in regions if not ((r["kind"] == "fluid" and common.get("fluid", "fluid") != "fluid" and self._c_ext == 0)
                                                         or (r["kind"] == "solid" and common.get("solid", "solid") != "solid"))]
-        self.mesh, self.space, self.regions, self.common = mesh, space, regions, dict(common)
         self.common.setdefault("hmin", mesh.hmin())
         self.degJ, self.degR = quad_degree_jacobian, quad_degree_residual
         self.pattern = pattern if pattern is not None else space.pattern()

@@ -1,11 +1,16 @@
-"""turtleFSI/modules/biharmonic.py counterpart: the mesh-lifting term added to F_fluid_linear
-(laplace.py:33-46 / biharmonic.py:31-36 cell terms / no_extrapolation.py)."""
+"""turtleFSI/modules/biharmonic.py counterpart: alpha_u (w . beta - grad(d) : grad(beta)) * dx_f +
+alpha_u grad(w) : grad(phi) * dx_f added to F_fluid_linear (biharmonic.py:31-36) as a named cell integral of the
+kernels; the `constrained_disp_vel` exterior-facet terms (:38-41) are a fixed sparse operator (`facet_terms`)."""
+from ..ufl_lite import KernelIntegral
+
+SUB_TYPES = ("constrained_disp", "constrained_disp_vel")
 
 
-def extrapolate_setup(F_fluid_linear, extrapolation_sub_type="constant", **namespace):
-    term = dict(F_fluid_linear)
-    term.update(extrapolation="biharmonic", extrapolation_sub_type=extrapolation_sub_type)
-    return dict(F_fluid_linear=term)
+def extrapolate_setup(F_fluid_linear, extrapolation_sub_type, dx_f_id_list, **namespace):
+    for fluid_region in range(len(dx_f_id_list)):
+        F_fluid_linear += KernelIntegral("biharmonic", "linear", dx_f_id_list[fluid_region],
+                                         extrapolation_sub_type=extrapolation_sub_type)
+    return dict(F_fluid_linear=F_fluid_linear)
 
 
 def facet_terms(assembler, mesh, DVP, boundaries, bc_ids, extrapolation_sub_type, **namespace):

@@ -17,14 +17,34 @@ sm_100a kernels (through an assembler object: turtlefsi_b200.assembler.FSIAssemb
 from math import isnan
 
 from ..boundary import BCPlan
+from ..ufl_lite import regions_of
 
 
-def solver_setup(assembler, dvp_, up_sol, bcs, **namespace):
-    """Pre-assemble the linear part of the Jacobian (frozen at the state present now, as in the
-    reference: SURVEY 8a "frozen-A_pre")."""
+def solver_setup(F_fluid_linear, F_fluid_nonlinear, F_solid_linear, F_solid_nonlinear, assembler, dvp_, up_sol, bcs,
+                 regions=None, **namespace):
+    """Pre-assemble the linear part of the Jacobian (frozen at the state present now, as in the reference: SURVEY 8a
+    "frozen-A_pre"). The forms are summed as the reference sums them (newtonsolver.py:18-24); their cell integrals
+    are the kernels' (the assembler was configured from them), facet terms a problem file has added since
+    (problem_aneu.py:214) are collected as loads."""
+    F_lin = F_fluid_linear + F_solid_linear
+    F_nonlin = F_solid_nonlinear + F_fluid_nonlinear
+    F = F_lin + F_nonlin
+    if regions is not None:
+        now, _ = regions_of(F)
+        if sorted(map(repr, map(sorted, (r.items() for r in now)))) != sorted(map(repr, map(sorted, (r.items() for r in regions)))):
+            raise RuntimeError("the cell integrals of the forms changed after the physics modules were set up; "
+                               "only facet terms can be added in initiate / create_bcs")
+    loads = F.expression_terms()
+    for it in loads:
+        if it.test_function() is None:
+            raise ValueError("a term added to the residual form has no test function")
+        if it.depends_on_state():
+            raise NotImplementedError("a facet / cell term that depends on the unknown was added to the residual form: "
+                                      "only loads (coefficients, expressions, normals) are evaluated on this path")
     bc_plan = BCPlan(bcs)                     # dof index maps built once; only values() runs per step
     assembler.set_bc_dofs(bc_plan.dofs)
-    A_pre = assembler.assemble_A_pre(dvp_["n"], dvp_["n-1"])
+    x = lambda f: getattr(f, "vec", f)        # dvp_ holds assembler vectors (or dolfin-style Functions around them)
+    A_pre = assembler.assemble_A_pre(x(dvp_["n"]), x(dvp_["n-1"]))
     if hasattr(assembler, "compress_A_pre"):
         assembler.compress_A_pre(A_pre)           # A_pre is final here (problem files edit the forms before)
     A = assembler.new_matrix()
@@ -32,13 +52,25 @@ def solver_setup(assembler, dvp_, up_sol, bcs, **namespace):
     if hasattr(assembler, "bind_matrix"):
         assembler.bind_matrix(A)              # persistent solver matrix: re-assemblies rewrite only the rows J_nl touches
     b = None
-    F = "F_lin + F_nonlin"                    # descriptor; the forms live in the kernels
-    return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n)", A_pre=A_pre, A=A, b=b, up_sol=up_sol, bc_plan=bc_plan)
+    return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n): hand-derived in the kernels", A_pre=A_pre, A=A, b=b,
+                up_sol=up_sol, bc_plan=bc_plan, facet_loads=loads)
+
+
+def _update_facet_loads(assembler, facet_loads, mesh, DVP, boundaries, compiler_parameters):
+    """loads added by the problem file, p(t) * inner(n('+'), psi('+')) * dS(id) and the like: re-evaluated with the
+    CURRENT values of their coefficients (pre_solve has just updated them) and handed to the device as a sparse
+    vector (tfsi_set_facet_load: b -= l)."""
+    import numpy as np
+    from ..ufl_lite import assemble_load
+    # assemble(-F) carries no form_compiler_parameters in the reference (newtonsolver.py:88): estimated degree
+    l = assemble_load(facet_loads, mesh, DVP, boundaries)
+    dofs = np.nonzero(l)[0].astype(np.int32)
+    assembler.set_facet_load(dofs, l[dofs], 1.0)
 
 
 def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_tstep, compiler_parameters,
                  dvp_, up_sol, dvp_res, rtol, atol, max_it, counter, first_step_num, verbose, assembler,
-                 residual_history=None, bc_plan=None, **namespace):
+                 residual_history=None, bc_plan=None, facet_loads=None, **namespace):
     """Newton scheme with the reference's Jacobian-reuse predicates (newtonsolver.py:44-113)."""
     # Initial values
     iter = 0
@@ -49,6 +81,9 @@ def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_t
     last_rel_res = residual
     last_residual = rel_res
     x, x1 = dvp_["n"], dvp_["n-1"]
+    if facet_loads:
+        _update_facet_loads(assembler, facet_loads, namespace["mesh"], namespace["DVP"], namespace["boundaries"],
+                            compiler_parameters)
     # The dof set uploaded by solver_setup is normally fixed and only the values are time dependent; a pre_solve
     # hook may nevertheless hand back another list (the reference re-reads `bcs` at every call): then the device
     # set is replaced, so that g always lines up with the dofs the kernels index.

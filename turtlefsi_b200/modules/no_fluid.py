@@ -1,7 +1,7 @@
-"""turtleFSI/modules/no_fluid.py counterpart: selects the fluid terms assembled by the CUDA kernels
-(N1..N6, L1, L2, L4 of fluid.py:32-56; zero forms of no_fluid.py:14-15)."""
+"""turtleFSI/modules/no_fluid.py counterpart: zero forms over the fluid regions (no_fluid.py:14-15) — no kernel term,
+so nothing is assembled there and `ident_zeros` puts unit rows, as in the reference."""
+from ..ufl_lite import Form
 
 
 def fluid_setup(**namespace):
-    term = dict(fluid="no_fluid")
-    return dict(F_fluid_linear=term, F_fluid_nonlinear=term)
+    return dict(F_fluid_linear=Form(), F_fluid_nonlinear=Form())

@@ -1,7 +1,6 @@
-"""turtleFSI/modules/no_solid.py counterpart: selects the solid terms assembled by the CUDA kernels
-(solid.py:41-43, 62-68 St.Venant-Kirchhoff; zero forms of no_solid.py:14-15)."""
+"""turtleFSI/modules/no_solid.py counterpart: zero forms over the solid regions (no_solid.py:14-15)."""
+from ..ufl_lite import Form
 
 
 def solid_setup(**namespace):
-    term = dict(solid="no_solid")
-    return dict(F_solid_linear=term, F_solid_nonlinear=term)
+    return dict(F_solid_linear=Form(), F_solid_nonlinear=Form())

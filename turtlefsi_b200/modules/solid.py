@@ -1,10 +1,21 @@
-"""turtleFSI/modules/solid.py counterpart: selects the solid terms assembled by the CUDA kernels
-(solid.py:41-43, 62-68 St.Venant-Kirchhoff; zero forms of no_solid.py:14-15)."""
+"""turtleFSI/modules/solid.py counterpart: inertia + kinematic constraint (linear, solid.py:41-43), St.Venant-Kirchhoff
+stress (non-linear, :62-63) and gravity (:65-68) of every solid region as named cell integrals of the sm_100a kernels
+(`jac_solid_kernel`, `residual_kernel`, `lin_jacobian_kernel`); the Robin condition (:76-86) is a pair of fixed sparse
+facet operators (`facet_terms`)."""
+from ..ufl_lite import Form, KernelIntegral
 
 
-def solid_setup(**namespace):
-    term = dict(solid="solid")
-    return dict(F_solid_linear=term, F_solid_nonlinear=term)
+def solid_setup(dx_s_id_list, solid_properties, **namespace):
+    F_solid_linear = Form()
+    F_solid_nonlinear = Form()
+    for solid_region in range(len(dx_s_id_list)):
+        sp = solid_properties[solid_region]
+        if sp["material_model"] != "StVenantKirchoff":
+            raise RuntimeError("material model '%s' is not available on the B200 path" % sp["material_model"])
+        const = dict(rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"])
+        F_solid_linear += KernelIntegral("solid", "linear", dx_s_id_list[solid_region], **const)
+        F_solid_nonlinear += KernelIntegral("solid", "nonlinear", dx_s_id_list[solid_region], **const)
+    return dict(F_solid_linear=F_solid_linear, F_solid_nonlinear=F_solid_nonlinear)
 
 
 def facet_terms(mesh, DVP, boundaries, theta, robin_bc=False, ds_s_ext_id_list=None, k_s=0.0, c_s=0.0, **namespace):

@@ -45,7 +45,7 @@ def _set_facet_terms(assembler, ns):
     import numpy as np
     terms = {"now": [], "prev": []}
     for key in ("extrapolation", "solid"):
-        m = importlib.import_module("turtlefsi_b200.modules." + ns[key])
+        m = _physics_module(ns[key])
         t = m.facet_terms(**ns) if hasattr(m, "facet_terms") else None
         for lvl in terms:
             if t and t.get(lvl) is not None and len(t[lvl][2]):
@@ -55,14 +55,41 @@ def _set_facet_terms(assembler, ns):
             getattr(assembler, setter)(*[np.concatenate([t[i] for t in terms[lvl]]) for i in range(3)])
 
 
-def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
-    """problem: module name under turtlefsi_b200.problems (or a module object).
-    make_assembler(mesh, space, regions, ns) -> assembler; make_solver(assembler) -> up_sol.
-    Returns the final namespace (what the reference keeps in its module globals)."""
-    mod = importlib.import_module("turtlefsi_b200.problems." + problem) if isinstance(problem, str) else problem
+def _physics_module(name):
+    """`exec("from turtleFSI.modules.{} import fluid_setup".format(fluid))` of monolithic.py:139-144: the module is
+    looked up BY NAME under turtlefsi_b200.modules; a name that is not there is imported as the user's own module
+    (it must return turtlefsi_b200.ufl_lite Forms, see modules/fluid.py)."""
+    try:
+        return importlib.import_module("turtlefsi_b200.modules." + name)
+    except ModuleNotFoundError as e:
+        if e.name != "turtlefsi_b200.modules." + name:
+            raise
+        return importlib.import_module(name)
+
+
+def load_problem(problem):
+    """problem: a module object (or any object with the seven hooks), the name of a module under
+    turtlefsi_b200.problems, or the path of a problem file. A file that is written against DOLFIN (`from dolfin import
+    *`, e.g. the reference's own turtleFSI/problems/TF_fsi.py, unmodified) is run through turtlefsi_b200.compat."""
+    import os
+    if not isinstance(problem, str):
+        return problem
+    path = problem if problem.endswith(".py") else problem + ".py"
+    if os.path.isfile(path):                                                # monolithic.py:24-25: a local file first
+        from .compat import load_problem_file
+        return load_problem_file(path)
+    return importlib.import_module("turtlefsi_b200.problems." + problem)
+
+
+def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, create_results_folder=False):
+    """problem: see load_problem. make_assembler(mesh, space, regions, ns) -> assembler;
+    make_solver(assembler) -> up_sol. Returns the final namespace (what the reference keeps in its module globals)."""
+    mod = load_problem(problem)
     ns = {}
     default_variables = copy.deepcopy(_defaults)
-    default_variables.update(mod.set_problem_parameters(default_variables=default_variables) or {})   # monolithic.py:35
+    import argparse
+    ns["args"] = argparse.Namespace(**(overrides or {}))                                             # monolithic.py:21
+    default_variables.update(mod.set_problem_parameters(default_variables=default_variables, args=ns["args"]) or {})   # :35
     default_variables.update(overrides or {})                                                        # CLI: :38-43
     if default_variables.get("restart_folder") is not None:                                          # :44-50
         import json
@@ -76,15 +103,24 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
     ns.update(default_variables)
     ns["default_variables"] = default_variables
     ns.setdefault("results_folder", None)
+    if create_results_folder:                                                                         # :59
+        from .problems import create_folders
+        ns.update(create_folders(**ns))
     mesh, domains, boundaries = mod.get_mesh_domain_and_boundaries(**ns)                              # :63
     ns.update(mesh=mesh, domains=domains, boundaries=boundaries)
     DVP = MixedSpace(mesh, biharmonic=(ns["extrapolation"] == "biharmonic"))                          # :77-92
     ns["DVP"] = DVP
     ns.update(assign_domain_properties(**ns))                                                         # :124-125
     for key, fn in (("fluid", "fluid_setup"), ("solid", "solid_setup"), ("extrapolation", "extrapolate_setup")):
-        m = importlib.import_module("turtlefsi_b200.modules." + ns[key])                              # :139-144
-        ns.update(getattr(m, fn)(**ns))
-    assembler = make_assembler(mesh, DVP, ns["regions"], ns)
+        ns.update(getattr(_physics_module(ns[key]), fn)(**ns))                                        # :139-144
+    # what the modules RETURNED decides what is assembled: region table and switches from the kernel terms of the forms
+    from .ufl_lite import regions_of
+    regions, switches = regions_of(ns["F_fluid_linear"] + ns["F_fluid_nonlinear"] + ns["F_solid_linear"] + ns["F_solid_nonlinear"])
+    if (switches["extrapolation"] == "biharmonic") != DVP.biharmonic:
+        raise RuntimeError("the mixed space has %s w field but the forms %s the biharmonic lifting"
+                           % ("a" if DVP.biharmonic else "no", "lack" if DVP.biharmonic else "carry"))
+    ns["regions"] = regions
+    assembler = make_assembler(mesh, DVP, regions, dict(ns, **switches))
     ns["assembler"] = assembler
     _set_facet_terms(assembler, ns)
     dvp_ = {k: assembler.new_vector() for k in ("n-2", "n-1", "n")}                                   # :95-111
@@ -92,7 +128,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None):
     ns["up_sol"] = make_solver(assembler)                                                             # :136
     ns.update(mod.initiate(**ns) or {})                                                               # :147
     ns.update(mod.create_bcs(**ns) or {})                                                             # :150
-    solver = importlib.import_module("turtlefsi_b200.modules." + ns["solver"])                        # :153
+    solver = _physics_module(ns["solver"])                                                            # :153
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
     # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them

@@ -56,6 +56,33 @@ def finished(**namespace):
     pass
 
 
+def create_folders(folder, sub_folder, restart_folder, **namespace):
+    """reference :118-180: <cwd>/<folder>/<sub_folder or next free number>/{Checkpoint, Visualization}; a restart
+    continues in the folder it restarts from."""
+    from pathlib import Path
+    if restart_folder is None:
+        path = Path.cwd() / folder
+        if sub_folder is not None:
+            path = path.joinpath(str(sub_folder))
+        else:
+            numbers = [int(i.name) for i in path.glob("*") if i.name.isdigit()]
+            path = path.joinpath(str(max(numbers) + 1 if numbers else 1))
+    else:
+        path = Path(restart_folder)
+    if "Checkpoint" in str(path):
+        path = path.parent
+    if not path.joinpath("Checkpoint").exists() and restart_folder is not None:
+        raise NotADirectoryError(("The restart folder: {} does not have a sub folder 'Checkpoint' where we can"
+                                  " restart the simulation from.").format(restart_folder))
+    checkpoint_folder = path.joinpath("Checkpoint")
+    visualization_folder = path.joinpath("Visualization")
+    if int(os.environ.get("RANK", "0")) == 0:
+        checkpoint_folder.mkdir(parents=True, exist_ok=True)
+        visualization_folder.mkdir(parents=True, exist_ok=True)
+    return dict(checkpoint_folder=str(checkpoint_folder), visualization_folder=str(visualization_folder),
+                results_folder=str(path), run_number=0)
+
+
 def checkpoint(dvp_, default_variables, checkpoint_folder, assembler, **namespace):
     """reference :183-219: store the current parameters (only keys of default_variables, e.g. t and counter) and
     the fields of the LAST time level (d1, v1, p1, (w1) = dvp_["n-1"] after the state rotation). Written to a
