@@ -87,6 +87,22 @@ def test_tf_fsi_laplace_volume_change():
     assert np.isclose(ns["drag_list"][-1], g["drag"]) and np.isclose(ns["lift_list"][-1], g["lift"], rtol=1e-4)
 
 
+def test_tf_fsi_elastic_lifting():
+    """test_elastic of the reference (tests/test_turtleFSI.py:106-123: `--extrapolation elastic -et constant`, its own
+    goldens :115-118): CUDA path (elastic.py:18-27 in the residual kernel, its Jacobian frozen into A_pre) vs the stored
+    numpy-oracle run at 1e-8 and vs the reference's goldens."""
+    hist, gold = _fixtures()
+    ns = _run_gpu("TF_fsi", theta=0.51, extrapolation="elastic", extrapolation_sub_type="constant")
+    h = hist["tf_fsi_elastic_numpy_oracle"]
+    assert np.allclose(ns["drag_list"], h["drag"], rtol=1e-8, atol=0)
+    assert np.allclose(ns["displacement_x_list"], h["dis_x"], rtol=1e-8, atol=0)
+    assert np.allclose(ns["lift_list"], h["lift"], rtol=1e-6, atol=0)
+    g = gold["TF_fsi_elastic"]
+    assert np.isclose(ns["displacement_x_list"][-1], g["dis_x"]) and np.isclose(ns["displacement_y_list"][-1], g["dis_y"])
+    assert np.isclose(ns["drag_list"][-1], g["drag"]) and np.isclose(ns["lift_list"][-1], g["lift"])
+    assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-10
+
+
 def test_tf_cfd():
     hist, gold = _fixtures()
     ns = _run_gpu("TF_cfd", theta=0.5)
