@@ -559,6 +559,11 @@ def roofline_of(w, m, steps):
         "flops_per_cell": flops_fluid, "cells_per_launch": n_fluid, "launches_per_step": m["kf_n"],
         "ms_per_launch": m["kf_ms"] / max(m["kf_n"], 1),
         "traffic": traffic, "traffic_note": tnote,
+        # the same launch against SURVEY.md 8(d)'s counting model (dense sum factorisation, 23.8 kFLOP per point = 0.333
+        # MFLOP per fluid tet at 14 points): the kernels integrate the same forms with 34 % fewer operations (sparse P2
+        # reference gradients), so `frac` above is quoted on the SMALLER count they actually need
+        "survey_model": {"flops_per_cell": 23800 * NQ_J, "achieved": 23800 * NQ_J * n_fluid / (m["kf_ms"] * 1e-3) / 1e12,
+                         "frac": 23800 * NQ_J * n_fluid / (m["kf_ms"] * 1e-3) / 1e12 / peak_tf},
         "step": {"achieved": step_flops / (m["ms_step"] * 1e-3) / 1e12, "frac": step_flops / (m["ms_step"] * 1e-3) / 1e12 / peak_tf,
                  "what": "(fluid + solid algorithmic FLOPs of this rank) / whole step time incl. A := A_pre"},
         "hbm": {"achieved": alg_bytes_step / (m["ms_step"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
