@@ -1110,6 +1110,19 @@ int tfsi_expand_node_pattern(int64_t num_nodes, int64_t nnz_node, const int64_t*
     return 0;
 }
 
+#ifdef TFSI_PHASE_CLOCKS
+// debugging aid (scripts/phase_clocks.py): reads and clears the per-phase cycle sums of the fluid Jacobian kernel
+extern "C" int tfsi_debug_phase_clocks(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    static unsigned long long z[256 * 16];
+    if (cudaMemcpyFromSymbol(z, tfsi::g_phase_clk, sizeof(z)) != cudaSuccess) return -1;
+    for (int k = 0; k < 16; ++k) { out16[k] = 0; for (int s = 0; s < 256; ++s) out16[k] += z[s * 16 + k]; }
+    for (auto& v : z) v = 0;
+    cudaMemcpyToSymbol(tfsi::g_phase_clk, z, sizeof(z));
+    return 0;
+}
+#endif
+
 int tfsi_probe_fp64_peak(double* out_tflops, double* out_ms) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, TFSI_ERR_CUDA, "no CUDA device");

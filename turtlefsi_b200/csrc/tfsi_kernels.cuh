@@ -219,6 +219,17 @@ __global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_
 }
 
 // scatter one P2xP2 half block of cell slot c: rows (row_loc + i), cols (col_off + HalfCols)
+// optional phase timing of the fluid kernel (scripts/phase_clocks.py; -DTFSI_PHASE_CLOCKS): cycles summed over warps
+#ifdef TFSI_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[256 * 16];          // [smid][slot]: summed by the reader (no hot address)
+__shared__ unsigned long long s_phase_clk[16];
+#define PCLK(var) const long long var = clock64()
+#define PCLK_ADD(slot, val) do { if ((threadIdx.x & 31) == 0) atomicAdd(&s_phase_clk[slot], (unsigned long long)(val)); } while (0)
+#else
+#define PCLK(var)
+#define PCLK_ADD(slot, val)
+#endif
+
 template <int G, class L, int NCOLS, int HALF>
 __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* rowst, const uint16_t* srank,
                                              int c, int row_loc, int col_off,
@@ -231,7 +242,13 @@ __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* r
         double* dst = a.out + rowst[(row_loc + i) * NC + c];
         const uint16_t* rk = srank + ((i * NCOLS) + col_off) * RKS + c;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * RKS], Z[i][jj]);
+        for (int jj = 0; jj < NJ; ++jj) {
+#ifdef TFSI_EXP_NOSCATTER        // experiment: what the REDs cost (results are wrong); one guarded store keeps Z alive
+            if (Z[i][jj] == 1.2345e300) dst[rk[HalfCols<G, HALF>::col(jj) * RKS]] = Z[i][jj];
+#else
+            atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * RKS], Z[i][jj]);
+#endif
+        }
     }
 }
 
@@ -259,6 +276,7 @@ __device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a,
 #pragma unroll
         for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
     const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
+    PCLK(t_loop0);
 #pragma unroll 1
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return basec[q * QSTR + item]; };
@@ -267,9 +285,13 @@ __device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a,
         else fluid_C_psi_dv<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 7>(c_tabJ, q0 + q, C, Z);
     }
+    PCLK(t_loop1);
     mbar_wait(mbar, 0);                       // ranks have landed (immediately true after the first task)
+    PCLK(t_loop2);
     if (valid)
         scatter_p2p2<G, typename FluidJac<G>::L, FluidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, FLD * G * N2 + cb * N2, Z);
+    PCLK(t_loop3);
+    PCLK_ADD(4, t_loop1 - t_loop0); PCLK_ADD(5, t_loop2 - t_loop1); PCLK_ADD(6, t_loop3 - t_loop2);
 }
 
 template <int G, int NQ>
@@ -299,6 +321,10 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::off_mbar(nq));
 
     const int lane = threadIdx.x & 31;
+    PCLK(t_start);
+#ifdef TFSI_PHASE_CLOCKS
+    if (threadIdx.x < 16) s_phase_clk[threadIdx.x] = 0;
+#endif
     if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
     stage_cells<G, L>(a, scell, sgeo);
     {   // gather of the batch: dofs are pre-blocked [k][cell] (coalesced), the state gathers hit L2
@@ -330,6 +356,7 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
         }
     }
     __syncthreads();
+    PCLK(t_gathered);
     for (int t = threadIdx.x; t < nq * NC; t += JAC_THREADS) {   // phase 0: one (cell, q) per thread
         const int c = t % NC, q = t / NC;
         double K[G][G];
@@ -344,7 +371,9 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
         auto out = [&](int item, double v) { dstb[item] = v; };
         fluid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, cf1, out);
     }
+    PCLK(t_p0done);
     __syncthreads();
+    PCLK(t_p0sync);
     if (threadIdx.x == 0) {   // scatter ranks of the batch: one TMA bulk copy into the (now dead) coefficient region;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // it lands while the first tasks compute
         mbar_expect_tx(mbar, (uint32_t)SM::RANK_BYTES);
@@ -357,10 +386,16 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
     const bool lane_on = lane < CPW * G;
     constexpr int NBIG = NGRP * 4 * G;                  // group x (field d|v) x a x half ; b = lane
     constexpr int NTASK = NBIG + NGRP * 3;              // + psi x dp, gamma x dd, gamma x dv per group
+#ifdef TFSI_PHASE_CLOCKS
+    long long t_big_end = 0;
+#endif
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
+#ifdef TFSI_PHASE_CLOCKS
+        if (t >= NBIG && t_big_end == 0) t_big_end = clock64();
+#endif
         if (t >= NTASK) break;
         if (t < NBIG) {
             const int grp = t % NGRP, r = t / NGRP;
@@ -431,6 +466,24 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
             }
         }
     }
+#ifdef TFSI_PHASE_CLOCKS
+    {
+        const long long t_end = clock64();
+        PCLK_ADD(0, t_gathered - t_start);      // stage + gather (incl. barrier)
+        PCLK_ADD(1, t_p0done - t_gathered);     // phase 0 work of this warp
+        PCLK_ADD(2, t_p0sync - t_p0done);       // waiting at the phase-0 barrier
+        PCLK_ADD(3, t_big_end - t_p0sync);      // big tasks
+        PCLK_ADD(7, t_end - t_big_end);         // small tasks
+        PCLK_ADD(8, t_end - t_start);           // warp lifetime
+        PCLK_ADD(9, threadIdx.x == 0 ? 1 : 0);
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            atomicAdd(&g_phase_clk[(smid & 255) * 16 + threadIdx.x], s_phase_clk[threadIdx.x]);
+        }
+    }
+#endif
 }
 
 // -------------------------------------------------------------------------------------------
