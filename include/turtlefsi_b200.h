@@ -45,6 +45,14 @@ extern "C" {
                                           FROZEN A_pre (newtonsolver.py:26-27), evaluated at the state handed to
                                           tfsi_assemble_A_pre (d = 0 in every shipped problem, any state supported) */
 
+/* material_model strings of common.py:104-121. StVenantKirchoff is the closed form P = F (2 mu E + lambda tr(E) I);
+ * the others are P = dW/dF of the strain-energy densities common.py:214-273 (their tangent is part of J_nonlinear). */
+#define TFSI_MAT_SVK 0             /* "StVenantKirchoff"        */
+#define TFSI_MAT_SVK_ENERGY 1      /* "StVenantKirchoffEnergy"  */
+#define TFSI_MAT_NEO_HOOKEAN 2     /* "NeoHookean"              */
+#define TFSI_MAT_MOONEY_RIVLIN 3   /* "MooneyRivlin"            */
+#define TFSI_MAT_GENT 4            /* "Gent"                    */
+
 typedef struct tfsi_handle tfsi_handle;
 
 /* one entry per cell-marker id that carries integrals: dx_f[i] / dx_s[i]
@@ -55,6 +63,13 @@ typedef struct {
     double rho;       /* rho_f | rho_s                                                  */
     double mu;        /* mu_f  | mu_s                                                   */
     double lambda;    /* lambda_s (solid, St.Venant-Kirchhoff: common.py:104-109)       */
+    /* solid regions only (zero = the reference's defaults: StVenantKirchoff, no viscoelasticity) */
+    int32_t material;         /* TFSI_MAT_*: solid_properties["material_model"] (common.py:104-121)            */
+    int32_t viscoelasticity;  /* 0 none, 1 "Form1", 2 "Form2": solid_properties["viscoelasticity"] (solid.py:46-59) */
+    double C01, C10, C11;     /* MooneyRivlin constants (common.py:258-273)                                   */
+    double Jm;                /* Gent constant (common.py:242-256)                                            */
+    double mu_visc;           /* solid_properties["mu_visc_s"]     (Svisc_D, common.py:129-139)               */
+    double lambda_visc;       /* solid_properties["lambda_visc_s"]                                            */
 } tfsi_region;
 
 typedef struct {

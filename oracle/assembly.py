@@ -22,6 +22,9 @@ def region_params(common, region):
         prm.update(rho_f=region["rho"], mu_f=region["mu"])
     else:
         prm.update(rho_s=region["rho"], mu_s=region["mu"], lambda_s=region.get("lambda_", 0.0))
+        for key in ("material_model", "C01", "C10", "C11", "Jm", "viscoelasticity", "mu_visc_s", "lambda_visc_s"):
+            if key in region:
+                prm[key] = region[key]
     return prm
 
 

@@ -4,7 +4,8 @@ numpy float64/complex128 restatement of turtleFSI's per-cell weak forms, written
 from the UFL expressions of the reference:
 
   fluid      turtleFSI/modules/fluid.py:32-56      (N1..N6 non-linear, L1, L2, L4 "linear")
-  solid      turtleFSI/modules/solid.py:29-68      (S1-S3, S5 linear; S4 non-linear; gravity)
+  solid      turtleFSI/modules/solid.py:29-68      (S1-S3, S5 linear; S4 non-linear; gravity; viscoelasticity :46-59;
+             material models common.py:100-127, 214-273)
   laplace    turtleFSI/modules/laplace.py:33-46    (4 alfa sub-types)
   biharmonic turtleFSI/modules/biharmonic.py:31-36 (cell terms)
   elastic    turtleFSI/modules/elastic.py:18-27
@@ -49,6 +50,67 @@ def geometry(X):
 
 def _inv_det(F):
     return np.linalg.inv(F), np.linalg.det(F)
+
+
+def strain_energy(Fm, model, prm):
+    """W(F) of turtleFSI/modules/common.py:214-273, transcribed literally (incl. the hard-coded 3s of Gent and
+    MooneyRivlin and get_dimension(F) of NeoHookean). Fm[..., g, g]."""
+    g = Fm.shape[-1]
+    lam, mu = prm['lambda_s'], prm['mu_s']
+    FT = np.swapaxes(Fm, -1, -2)
+    tr = lambda A: np.trace(A, axis1=-2, axis2=-1)
+    J = np.linalg.det(Fm)
+    if model == 'StVenantKirchoffEnergy':                                  # :214-225
+        E_ = 0.5 * (FT @ Fm - np.eye(g))
+        return lam / 2 * tr(E_) ** 2 + mu * tr(E_ @ E_)
+    if model == 'NeoHookean':                                              # :228-240
+        C1, D1 = mu / 2, lam / 2
+        return C1 * (tr(FT @ Fm) - g - 2 * np.log(J)) + D1 * (J - 1) ** 2
+    if model == 'Gent':                                                    # :242-256
+        Jm = prm['Jm']
+        return -(mu / 2) * (Jm * np.log(1 - (tr(Fm @ FT) - 3) / Jm) + 2 * np.log(J))
+    if model == 'MooneyRivlin':                                            # :258-273
+        Kb = lam + 2 * mu / 3
+        D1 = 2 / Kb
+        B = Fm @ FT
+        I1 = tr(B)
+        I2 = 0.5 * (tr(B) ** 2 - tr(B @ B))
+        Ibar1, Ibar2 = J ** (-2 / 3) * I1, J ** (-4 / 3) * I2
+        return (prm['C01'] * (Ibar2 - 3) + prm['C10'] * (Ibar1 - 3) + prm['C11'] * (Ibar2 - 3) * (Ibar1 - 3)
+                + (1 / D1) * (J - 1) ** 2)
+    raise RuntimeError('Invalid entry for material_model')
+
+
+def piola1(Fm, model, prm):
+    """First Piola-Kirchhoff stress, common.py:100-127. StVenantKirchoff: the explicit form :104-109. The other models
+    are P = diff(W, F) (:110-125); here the derivative is written out by hand in terms of F
+    (tests/test_oracle_forms.py checks it against a complex-step derivative of `strain_energy`). Works on complex F."""
+    g = Fm.shape[-1]
+    I = np.eye(g)
+    lam, mu = prm['lambda_s'], prm['mu_s']
+    FT = np.swapaxes(Fm, -1, -2)
+    tr = lambda A: np.trace(A, axis1=-2, axis2=-1)[..., None, None]
+    if model in ('StVenantKirchoff', 'StVenantKirchoffEnergy'):            # common.py:84-88,104-109
+        E = 0.5 * (FT @ Fm - I)
+        return Fm @ (2.0 * mu * E + lam * tr(E) * I)
+    FiT = np.swapaxes(np.linalg.inv(Fm), -1, -2)
+    J = np.linalg.det(Fm)[..., None, None]
+    C = FT @ Fm
+    I1 = tr(C)
+    if model == 'NeoHookean':
+        return mu * (Fm - FiT) + lam * (J - 1) * J * FiT
+    if model == 'Gent':
+        return mu / (1 - (I1 - 3) / prm['Jm']) * Fm - mu * FiT
+    if model == 'MooneyRivlin':
+        Kb = lam + 2 * mu / 3
+        I2 = 0.5 * (I1 ** 2 - tr(C @ C))
+        Ib1, Ib2 = J ** (-2 / 3) * I1, J ** (-4 / 3) * I2
+        dIb1 = J ** (-2 / 3) * (2 * Fm - (2 / 3) * I1 * FiT)
+        dIb2 = J ** (-4 / 3) * (2 * I1 * Fm - 2 * Fm @ C - (4 / 3) * I2 * FiT)
+        return ((prm['C01'] + prm['C11'] * (Ib1 - 3)) * dIb2 + (prm['C10'] + prm['C11'] * (Ib2 - 3)) * dIb1
+                + Kb * (J - 1) * J * FiT)
+    raise RuntimeError('Invalid entry for material_model, choose from ["StVenantKirchoff",'
+                       '"StVenantKirchoffEnergy","NeoHookean","MooneyRivlin","Gent"]')
 
 
 class CellForms:
@@ -198,12 +260,25 @@ class CellForms:
             self._test_vec(Rl, sp.off_d, K, wdet,
                            fval=delta * rho / k * (d - d1) - delta * rho * (th0 * v + th1 * v1))
 
-            def piola(Fm):                                                 # common.py:84-88,104-109
-                E = 0.5 * (np.swapaxes(Fm, -1, -2) @ Fm - I)
-                S = 2.0 * mu * E + lam * np.trace(E, axis1=-2, axis2=-1)[..., None, None] * I
-                return Fm @ S
+            model = prm.get('material_model', 'StVenantKirchoff')
+
+            def piola(Fm):                                                 # common.py:100-127
+                return piola1(Fm, model, prm)
             self._test_vec(Rn, sp.off_v, K, wdet, fgrad=th0 * piola(F))    # solid.py:62
             self._test_vec(Rl, sp.off_v, K, wdet, fgrad=th1 * piola(F1))   # solid.py:63
+            visco = prm.get('viscoelasticity')
+            if visco in ('Form1', 'Form2'):                                # solid.py:46-55
+
+                def svisc(Gw):                                             # common.py:129-139, D_ :43-47
+                    D = 0.5 * (Gw + np.swapaxes(Gw, -1, -2))
+                    return (prm['mu_visc_s'] * np.trace(D, axis1=-2, axis2=-1)[..., None, None] * I
+                            + 2.0 * prm['lambda_visc_s'] * D)
+                if visco == 'Form1':                                       # :48-50
+                    self._test_vec(Rn, sp.off_v, K, wdet, fgrad=th0 * (F @ svisc(Gv)))
+                    self._test_vec(Rl, sp.off_v, K, wdet, fgrad=th1 * (F1 @ svisc(Gv1)))
+                else:                                                      # :51-55
+                    self._test_vec(Rn, sp.off_v, K, wdet, fgrad=(1.0 / k) * (F @ (th0 * svisc(Gd - Gd1))))
+                    self._test_vec(Rl, sp.off_v, K, wdet, fgrad=(1.0 / k) * (F1 @ (th1 * svisc(Gd - Gd1))))
             if prm.get('gravity') is not None:                            # solid.py:65-68
                 gv = np.zeros(g)
                 gv[1] = -prm['gravity'] * rho

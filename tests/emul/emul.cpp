@@ -76,11 +76,13 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
                 addblock(2 * G * N2, fld * G * N2 + b * N2, N1, N2, &Z[0][0], N2);
             }
     } else {
-        typedef SolidBase<G> SB;
-        std::vector<double> base((size_t)SB::COUNT * nq);
+        const bool energy = rc.mat != MAT_SVK;
+        const int count = energy ? SolidBaseGen<G>::COUNT : SolidBase<G>::COUNT;
+        std::vector<double> base((size_t)count * nq);
         for (int q = 0; q < nq; ++q) {
             auto out = [&](int item, double v) { base[(size_t)item * nq + q] = v; };
-            solid_base<G>(tab, q, K, adet, rc, cf, out);
+            if (energy) solid_base_energy<G>(tab, q, K, adet, rc, cf, out);
+            else solid_base<G>(tab, q, K, adet, rc, cf, out);
         }
         constexpr int NJ = HalfCols<G, 0>::NJ;
         for (int a = 0; a < G; ++a)
@@ -91,7 +93,8 @@ void jac_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, const double* X
                     for (int q = 0; q < nq; ++q) {
                         auto bv = [&](int item) { return base[(size_t)item * nq + q]; };
                         double C[G + 1][G + 1];
-                        solid_C_psi_dd<G>(bv, rc, a, b, C);
+                        if (energy) solid_C_psi_dd_energy<G>(bv, a, b, C);
+                        else solid_C_psi_dd<G>(bv, rc, a, b, C);
                         if (half == 0) block_p2p2<G, 0, 4>(tab, q, C, Z); else block_p2p2<G, 1, 4>(tab, q, C, Z);
                     }
                     for (int i = 0; i < N2; ++i) for (int jj = 0; jj < NJ; ++jj) {
@@ -120,6 +123,7 @@ void res_cell(const QuadTab<MAXQ_R>& tab, const RegionConst& rc, const double* X
         PointFlux<G> f;
         if (rc.ext == 1 && rc.ext_sub == 3) residual_point<G, LIFT_VOLUME_CHANGE>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         else if (rc.ext == 3) residual_point<G, LIFT_ELASTIC>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
+        else if (rc.kind == 1 && (rc.mat != MAT_SVK || rc.visco)) residual_point<G, LIFT_SOLID_GENERAL>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         else residual_point<G>(tab, q, K, adet, rc, alfa_cell, cf, cf1, f);
         for (int c = 0; c < G; ++c)
             for (int i = 0; i < N2; ++i) {
@@ -183,9 +187,101 @@ void lift_cell(const QuadTab<MAXQ_J>& tab, int gen_kind, const double* Xp, const
             }
 }
 
+// one viscoelastic block (gen_kind 3..6 of lin_jacobian_kernel) of one cell: rows psi, columns delta d | delta v
+template <int G>
+void visco_cell(const QuadTab<MAXQ_J>& tab, const RegionConst& rc, int gen_kind, const double* Xp, const double* u,
+                const double* u1, int ndof, double* Ae)
+{
+    constexpr int N2 = Dim<G>::N2;
+    constexpr int NJ = HalfCols<G, 0>::NJ;
+    double X[G + 1][G];
+    for (int v = 0; v <= G; ++v) for (int c = 0; c < G; ++c) X[v][c] = Xp[v * G + c];
+    double K[G][G];
+    const double adet = cell_geometry<G>(X, K);
+    const int trial_off = (gen_kind == GEN_VISCO_F1_DV) ? G * N2 : 0;
+    for (int ca = 0; ca < G; ++ca)
+        for (int cb = 0; cb < G; ++cb)
+            for (int half = 0; half < 2; ++half) {
+                double Z[N2][NJ];
+                memset(Z, 0, sizeof Z);
+                for (int q = 0; q < tab.nq; ++q) {
+                    const double jw = tab.w[q] * adet;
+                    auto phys_grad = [&](const double* vec, int off, double (&out)[G][G]) {
+                        for (int aa = 0; aa < G; ++aa) {
+                            double Gr[G] = {};
+                            for (int j = 0; j < N2; ++j) for (int t = 0; t < G; ++t) Gr[t] += vec[off + aa * N2 + j] * tab.dphi2[q][j][t];
+                            for (int b = 0; b < G; ++b) { double sacc = 0; for (int t = 0; t < G; ++t) sacc += Gr[t] * K[t][b]; out[aa][b] = sacc; }
+                        }
+                    };
+                    double Fm[G][G], Gw[G][G], D[G][G][G][G];
+                    phys_grad(gen_kind == GEN_VISCO_F2_LIN ? u1 : u, 0, Fm);
+                    if (gen_kind == GEN_VISCO_F2_DD) {
+                        double G1[G][G];
+                        phys_grad(u1, 0, G1);
+                        for (int aa = 0; aa < G; ++aa) for (int b = 0; b < G; ++b) Gw[aa][b] = Fm[aa][b] - G1[aa][b];
+                    } else if (gen_kind == GEN_VISCO_F2_LIN) {
+                        for (int aa = 0; aa < G; ++aa) for (int b = 0; b < G; ++b) Gw[aa][b] = 0.0;
+                    } else phys_grad(u, G * N2, Gw);
+                    for (int aa = 0; aa < G; ++aa) Fm[aa][aa] += 1.0;
+                    visco_flux_derivative<G>(gen_kind, rc, Fm, Gw, D);
+                    double C[G + 1][G + 1];
+                    C[0][0] = 0.0;
+                    for (int s = 0; s < G; ++s) {
+                        C[0][1 + s] = 0; C[1 + s][0] = 0;
+                        for (int t = 0; t < G; ++t) {
+                            double z = 0;
+                            for (int s2 = 0; s2 < G; ++s2) for (int t2 = 0; t2 < G; ++t2) z += K[s][s2] * D[ca][s2][cb][t2] * K[t][t2];
+                            C[1 + s][1 + t] = jw * z;
+                        }
+                    }
+                    if (half == 0) block_p2p2<G, 0, 5>(tab, q, C, Z); else block_p2p2<G, 1, 5>(tab, q, C, Z);
+                }
+                for (int i = 0; i < N2; ++i) for (int jj = 0; jj < NJ; ++jj) {
+                    int j = half == 0 ? HalfCols<G, 0>::col(jj) : HalfCols<G, 1>::col(jj);
+                    Ae[(G * N2 + ca * N2 + i) * ndof + trial_off + cb * N2 + j] += Z[i][jj];
+                }
+            }
+}
+
 }  // namespace
 
 extern "C" {
+
+// solid region with any material model / viscoelasticity. part 0: element matrices of J_nonlinear (jac_solid_kernel +
+// the viscoelastic blocks), 1: the state-dependent block of J_linear ("Form2", frozen in A_pre), 2: element vectors of F
+int emul_solid_general(int g, int nqJ, const double* ptsJ, const double* wtsJ, int nqR, const double* ptsR, const double* wtsR,
+                       double rho, double mu, double lambda, double dt, double theta, int material, double C01, double C10,
+                       double C11, double Jm, int visco, double mu_visc, double lam_visc, int part, int64_t nc,
+                       const double* X, const double* u, const double* u1, int ndof, double* out)
+{
+    RegionConst rc = make_region_const(1, rho, mu, lambda, dt, theta, 1, 1, 1, 0, 0.0, 0.0);
+    set_solid_model(rc, material, C01, C10, C11, Jm, visco, mu_visc, lam_visc);
+    if (part == 2) {
+        QuadTab<MAXQ_R> tab;
+        if (tabulate<MAXQ_R>(g, nqR, ptsR, wtsR, tab)) return -1;
+        for (int64_t c = 0; c < nc; ++c) {
+            if (g == 3) res_cell<3>(tab, rc, X + c * 12, u + c * ndof, u1 + c * ndof, ndof, out + c * ndof);
+            else res_cell<2>(tab, rc, X + c * 6, u + c * ndof, u1 + c * ndof, ndof, out + c * ndof);
+        }
+        return 0;
+    }
+    QuadTab<MAXQ_J> tab;
+    if (tabulate<MAXQ_J>(g, nqJ, ptsJ, wtsJ, tab)) return -1;
+    for (int64_t c = 0; c < nc; ++c) {
+        const double* Xc = X + c * (g + 1) * g;
+        const double *uc = u + c * ndof, *u1c = u1 + c * ndof;
+        double* Ae = out + c * ndof * ndof;
+        auto visco_blk = [&](int kind) {
+            if (g == 3) visco_cell<3>(tab, rc, kind, Xc, uc, u1c, ndof, Ae); else visco_cell<2>(tab, rc, kind, Xc, uc, u1c, ndof, Ae);
+        };
+        if (part == 0) {
+            if (g == 3) jac_cell<3>(tab, rc, Xc, uc, u1c, ndof, Ae); else jac_cell<2>(tab, rc, Xc, uc, u1c, ndof, Ae);
+            if (visco == 1) { visco_blk(GEN_VISCO_F1_DD); visco_blk(GEN_VISCO_F1_DV); }
+            else if (visco == 2) visco_blk(GEN_VISCO_F2_DD);
+        } else if (visco == 2) visco_blk(GEN_VISCO_F2_LIN);
+    }
+    return 0;
+}
 
 // Ae[nc][ndof][ndof] += phi x delta d block of the non-linear lifting (gen_kind 1 volume_change, 2 elastic) at state u
 int emul_lifting_jacobian(int g, int nq, const double* pts, const double* wts, int gen_kind, int64_t nc, const double* X,

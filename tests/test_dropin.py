@@ -130,8 +130,20 @@ def test_setup_modules_decide_what_is_assembled(tmp_path):
     F = ns["F_fluid_linear"] + ns["F_fluid_nonlinear"] + ns["F_solid_linear"] + ns["F_solid_nonlinear"]
     regions, sw = regions_of(F)
     assert regions == [dict(marker=1, kind="fluid", rho=1.0, mu=2.0), dict(marker=7, kind="fluid", rho=3.0, mu=4.0),
-                       dict(marker=2, kind="solid", rho=5.0, mu=6.0, lambda_=7.0)]
+                       dict(marker=2, kind="solid", rho=5.0, mu=6.0, lambda_=7.0, material_model="StVenantKirchoff")]
     assert sw == dict(fluid="fluid", solid="solid", extrapolation="laplace", extrapolation_sub_type="volume")
+    # the reference's other material models and viscoelasticity travel under their own keys (common.py:104-139,
+    # solid.py:46-59); a missing constant is a KeyError as in the reference, an unknown model is refused
+    sp = dict(material_model="MooneyRivlin", rho_s=5.0, mu_s=6.0, lambda_s=7.0, C01=1.0, C10=2.0, C11=3.0,
+              viscoelasticity="Form1", mu_visc_s=8.0, lambda_visc_s=9.0)
+    r = regions_of(solid.solid_setup([2], [sp])["F_solid_nonlinear"])[0][0]
+    assert r == dict(marker=2, kind="solid", rho=5.0, mu=6.0, lambda_=7.0, material_model="MooneyRivlin", C01=1.0, C10=2.0,
+                     C11=3.0, viscoelasticity="Form1", mu_visc_s=8.0, lambda_visc_s=9.0)
+    with pytest.raises(KeyError):
+        solid.solid_setup([2], [dict(material_model="Gent", rho_s=5.0, mu_s=6.0, lambda_s=7.0)])
+    with pytest.raises(RuntimeError, match="Invalid entry for material_model"):
+        solid.solid_setup([2], [dict(material_model="Ogden", rho_s=5.0, mu_s=6.0, lambda_s=7.0)])
+    assert "viscoelasticity" not in regions_of(solid.solid_setup([2], [dict(sp, viscoelasticity="None")])["F_solid_linear"])[0][0]
     # structure + mesh motion only: lifting terms keep the fluid markers as (inactive) fluid regions
     regions, sw = regions_of(Form() + laplace.extrapolate_setup(Form(), "constant", [1, 7])["F_fluid_linear"] + ns["F_solid_linear"])
     assert sw["fluid"] == "no_fluid" and sorted(r["marker"] for r in regions) == [1, 2, 7]

@@ -249,6 +249,54 @@ def test_nonlinear_lifting_frozen_at_nonzero_state(gdim, ext, sub, tube_params):
     assert np.abs(b.cpu().numpy() - ref_b).max() / np.abs(ref_b).max() < TOL
 
 
+SOLID_MODELS = [dict(material_model="StVenantKirchoffEnergy"), dict(material_model="NeoHookean"),
+                dict(material_model="Gent", Jm=2.5), dict(material_model="MooneyRivlin", C01=3.0e4, C10=1.2e5, C11=7.0e3),
+                dict(viscoelasticity="Form1", mu_visc_s=1.0e4, lambda_visc_s=2.0e4),
+                dict(viscoelasticity="Form2", mu_visc_s=1.0e2, lambda_visc_s=3.0e2),
+                dict(material_model="NeoHookean", viscoelasticity="Form1", mu_visc_s=1.0e4, lambda_visc_s=2.0e4)]
+
+
+@pytest.mark.parametrize("gdim", [3, 2])
+@pytest.mark.parametrize("extra", SOLID_MODELS, ids=lambda m: m.get("material_model", "SVK") + "-" + str(m.get("viscoelasticity")))
+def test_material_models_and_viscoelasticity(gdim, extra, tube_params):
+    """solid_properties["material_model"] in {StVenantKirchoffEnergy, NeoHookean, MooneyRivlin, Gent} (common.py:110-125,
+    214-273) and ["viscoelasticity"] in {Form1, Form2} (solid.py:46-59): A_pre, A = A_pre + J_nl and b of a fluid region
+    + a DEFAULT solid region + a solid region with the model, at a large-deformation state, against the oracle."""
+    import torch
+    from oracle import assembly as oa
+    from tests.helpers import square_mesh
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.mesh import synthetic_state, tube_mesh
+    from turtlefsi_b200.space import MixedSpace
+    common, regions = tube_params
+    mesh = tube_mesh(3) if gdim == 3 else square_mesh(6)
+    space = MixedSpace(mesh)
+    ax = mesh.coords[mesh.cells].mean(axis=1)[:, gdim - 1]
+    mesh.markers = np.where((mesh.markers == 2) & (ax > np.median(ax)), 3, mesh.markers).astype(np.int32)
+    regions = list(regions) + [dict(regions[1], marker=3, **extra)]
+    assert (mesh.markers == 3).sum() > 5 and (mesh.markers == 2).sum() > 5
+    h = 3.0 if gdim == 3 else 2.0
+    x, x1 = synthetic_state(mesh, space, 2024, h=h), synthetic_state(mesh, space, 2025, h=h)
+    degJ, degR = (4, 6) if gdim == 3 else (5, 10)
+    pattern = space.pattern()
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], quad_degree_jacobian=degJ,
+                       quad_degree_residual=degR, pattern=pattern)
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    A_pre = asm.assemble_A_pre(xd, x1d)
+    A = asm.assemble_jacobian(xd, x1d, A_pre)
+    b = asm.assemble_residual(xd, x1d)
+    ref_pre = oa.assemble_matrix(mesh, space, regions, common, x, x1, "lin", degJ, pattern)
+    ref = oa.assemble_matrix(mesh, space, regions, common, x, x1, "all", degJ, pattern)
+    ref_b = oa.assemble_vector(mesh, space, regions, common, x, x1, degR)
+    assert _row_rel_err(A_pre.cpu().numpy(), ref_pre, pattern[0]) < 1e-11
+    assert _row_rel_err(A.cpu().numpy(), ref, pattern[0]) < 1e-11
+    assert np.abs(b.cpu().numpy() - ref_b).max() / np.abs(ref_b).max() < TOL
+    # the model matters: the default St.Venant-Kirchhoff table for region 3 gives another matrix
+    if extra.get("material_model", "") != "StVenantKirchoffEnergy":
+        plain = list(regions[:-1]) + [dict(regions[1], marker=3)]
+        assert _row_rel_err(oa.assemble_matrix(mesh, space, plain, common, x, x1, "all", degJ, pattern), ref, pattern[0]) > 1e-4
+
+
 def test_release_pattern(tube_params):
     """the column array (4 B per entry) is only needed during set-up: after tfsi_release_pattern the hot path still
     runs, the calls that need columns fail loudly."""

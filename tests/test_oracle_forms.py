@@ -207,6 +207,81 @@ def test_nonlinear_lifting_math_matches_oracle(emul, g, deg, amp):
         assert np.abs(Ae0 - Ae).max() > 1e-4 * np.abs(Ae).max()
 
 
+MATERIALS = [dict(material_model="StVenantKirchoffEnergy"), dict(material_model="NeoHookean"),
+             dict(material_model="Gent", Jm=2.5), dict(material_model="MooneyRivlin", C01=3.0e4, C10=1.2e5, C11=7.0e3)]
+MAT_CODE = {"StVenantKirchoff": 0, "StVenantKirchoffEnergy": 1, "NeoHookean": 2, "MooneyRivlin": 3, "Gent": 4}
+
+
+@pytest.mark.parametrize("g", [2, 3])
+@pytest.mark.parametrize("mat", MATERIALS, ids=lambda m: m["material_model"])
+def test_piola_is_the_derivative_of_the_energy(g, mat):
+    """common.py:110-125: P = diff(W, F). The oracle's hand-written P against a complex-step derivative of the
+    literally transcribed energy densities (common.py:214-273), at random deformation gradients."""
+    from oracle.forms import piola1, strain_energy
+    rng = np.random.default_rng(5)
+    prm = dict(mat, lambda_s=3.1e6, mu_s=3.4e5)
+    F = np.eye(g) + 0.15 * rng.uniform(-1, 1, (40, g, g))
+    P = piola1(F, mat["material_model"], prm)
+    h = 1e-30
+    for a in range(g):
+        for b in range(g):
+            Fc = F.astype(np.complex128)
+            Fc[:, a, b] += 1j * h
+            dW = strain_energy(Fc, mat["material_model"], prm).imag / h
+            assert np.abs(dW - P[:, a, b]).max() < 1e-12 * np.abs(P).max()
+    if mat["material_model"] == "StVenantKirchoffEnergy":      # the two St.Venant-Kirchhoff routes of the reference agree
+        assert np.abs(P - piola1(F, "StVenantKirchoff", prm)).max() < 1e-12 * np.abs(P).max()
+
+
+def _general_solid(emul, g, deg, reg, common, Xs, us, u1s, ndof, part):
+    ptsJ, wtsJ = map(np.ascontiguousarray, ft.quadrature(g, deg))
+    ptsR, wtsR = map(np.ascontiguousarray, ft.quadrature(g, deg))
+    out = np.zeros((len(Xs), ndof) if part == 2 else (len(Xs), ndof, ndof))
+    d = C.c_double
+    rc = emul.emul_solid_general(g, len(wtsJ), _dp(ptsJ), _dp(wtsJ), len(wtsR), _dp(ptsR), _dp(wtsR), d(reg["rho"]), d(reg["mu"]),
+                                 d(reg["lambda_"]), d(common["dt"]), d(common["theta"]), MAT_CODE[reg.get("material_model", "StVenantKirchoff")],
+                                 d(reg.get("C01", 0.0)), d(reg.get("C10", 0.0)), d(reg.get("C11", 0.0)), d(reg.get("Jm", 0.0)),
+                                 {None: 0, "Form1": 1, "Form2": 2}[reg.get("viscoelasticity")], d(reg.get("mu_visc_s", 0.0)),
+                                 d(reg.get("lambda_visc_s", 0.0)), part, C.c_int64(len(Xs)), _dp(Xs), _dp(us), _dp(u1s), ndof, _dp(out))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("g,deg,amp", [(3, 4, 3.0), (2, 5, 2.0)])
+@pytest.mark.parametrize("extra", MATERIALS + [dict(viscoelasticity="Form1", mu_visc_s=1.0e4, lambda_visc_s=2.0e4),
+                                               dict(viscoelasticity="Form2", mu_visc_s=1.0e2, lambda_visc_s=3.0e2),
+                                               dict(material_model="NeoHookean", viscoelasticity="Form1", mu_visc_s=1.0e4, lambda_visc_s=2.0e4)],
+                         ids=lambda m: m.get("material_model", "SVK") + "-" + str(m.get("viscoelasticity")))
+def test_material_and_viscoelastic_math_matches_oracle(emul, g, deg, amp, extra):
+    """energy-based material models (common.py:110-125: tangent from hyper-dual derivatives of W(I1, I2, J)) and
+    viscoelasticity (solid.py:46-59): host-compiled kernel mathematics — residual fluxes, J_nonlinear (psi x delta d,
+    psi x delta v) and the "Form2" block of J_linear — against the complex-step oracle at a large-deformation state."""
+    mesh, sp, x, x1 = _case(g, False, amp)
+    common = dict(TUBE_PARAMS)
+    reg = dict(TUBE_REGIONS[1], **extra)
+    cf = CellForms(g, False, deg)
+    X = np.ascontiguousarray(mesh.coords[mesh.cells])
+    u, u1 = np.ascontiguousarray(x[sp.cell_dofs]), np.ascontiguousarray(x1[sp.cell_dofs])
+    sel = mesh.markers == reg["marker"]
+    Xs, us, u1s = map(np.ascontiguousarray, (X[sel], u[sel], u1[sel]))
+    prm = oa.region_params(common, reg)
+    Rl, Rn = cf.residual("solid", Xs, us, u1s, prm)
+    Fe = _general_solid(emul, g, deg, reg, common, Xs, us, u1s, sp.ndof_cell, 2)
+    assert np.abs(Fe - (Rl + Rn)).max() < 1e-12 * np.abs(Rl + Rn).max()
+    for part, name in ((0, "nl"), (1, "lin")):
+        Jo = cf.jacobian("solid", Xs, us, u1s, prm, name)
+        Ae = _general_solid(emul, g, deg, reg, common, Xs, us, u1s, sp.ndof_cell, part)
+        if part == 1:                      # the emulation returns only the state-dependent viscoelastic block of J_linear
+            base = cf.jacobian("solid", Xs, us, u1s, oa.region_params(common, TUBE_REGIONS[1]), "lin")
+            Jo = Jo - base
+        scale = np.abs(Jo).max(axis=(1, 2), keepdims=True)
+        scale[scale == 0] = 1
+        assert (np.abs(Ae - Jo) / scale).max() < 1e-11, name
+    if "viscoelasticity" in extra:         # the rate term matters
+        Rl0, Rn0 = cf.residual("solid", Xs, us, u1s, oa.region_params(common, dict(reg, viscoelasticity=None)))
+        assert np.abs(Rn - Rn0).max() > 1e-6 * np.abs(Rn).max()
+
+
 @pytest.mark.parametrize("g,n", [(3, 3), (2, 6)])
 def test_c_port_matches_numpy_oracle(g, n):
     mesh = tube_mesh(n) if g == 3 else square_mesh(n)

@@ -32,7 +32,8 @@ class FSIAssembler:
     """One handle = one mesh partition on one GPU.
 
     regions: list of dicts {marker, kind ("fluid"|"solid"), rho, mu, lambda_} — what
-    turtleFSI/modules/domain.py:54-103 derives from dx_f_id / dx_s_id and the property lists.
+    turtleFSI/modules/domain.py:54-103 derives from dx_f_id / dx_s_id and the property lists; solid regions may add
+    the reference's material_model / C01 / C10 / C11 / Jm / viscoelasticity / mu_visc_s / lambda_visc_s entries.
     """
 
     def __init__(self, mesh, space, regions, dt, theta, fluid="fluid", solid="solid",
@@ -81,6 +82,17 @@ class FSIAssembler:
             regs[i].rho = float(r["rho"])
             regs[i].mu = float(r["mu"])
             regs[i].lam = float(r.get("lambda_", 0.0))
+            if r["kind"] == "solid":         # common.py:104-139, solid.py:46-59 (keys of the reference's solid_properties)
+                model, visco = r.get("material_model", "StVenantKirchoff"), r.get("viscoelasticity")
+                if model not in _lib.MATERIAL_MODELS:
+                    raise RuntimeError('Invalid entry for material_model, choose from ["StVenantKirchoff",'
+                                       '"StVenantKirchoffEnergy","NeoHookean","MooneyRivlin","Gent"]')
+                regs[i].material = _lib.MATERIAL_MODELS[model]
+                regs[i].viscoelasticity = _lib.VISCOELASTICITY.get(visco, 0)     # invalid entry: none, as solid.py:56-58
+                for key in ("C01", "C10", "C11", "Jm"):
+                    setattr(regs[i], key, float(r.get(key, 0.0)))
+                regs[i].mu_visc = float(r.get("mu_visc_s", 0.0))
+                regs[i].lambda_visc = float(r.get("lambda_visc_s", 0.0))
         p = _lib.TfsiProblem()
         p.gdim, p.biharmonic = g, int(space.biharmonic)
         p.num_vertices, p.num_cells, p.num_dofs = mesh.num_vertices, mesh.num_cells, self.num_dofs

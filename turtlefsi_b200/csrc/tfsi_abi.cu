@@ -171,7 +171,9 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
     const bool is_fluid = r.rc.kind == TFSI_KIND_FLUID;
     const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
     const int grid = (int)((r.ncells + ncta - 1) / ncta);
-    const int chunk = is_fluid ? max_points<typename FluidJac<G>::SM>(nq) : max_points<typename SolidJac<G>::SM>(nq);
+    const bool energy = !is_fluid && r.rc.mat != MAT_SVK;        // energy-based solid model: tangent-table variant
+    const int chunk = is_fluid ? max_points<typename FluidJac<G>::SM>(nq)
+                               : (energy ? max_points<typename SolidJac<G, 1>::SM>(nq) : max_points<typename SolidJac<G>::SM>(nq));
     const int nchunk = (nq + chunk - 1) / chunk;
     for (int c = 0; c < nchunk; ++c) {
         a.q0 = (int)((int64_t)nq * c / nchunk);
@@ -188,6 +190,10 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
                 CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
             }
+        } else if (energy) {
+            const size_t smem = SolidJac<G, 1>::SM::bytes(a.nq);
+            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            jac_solid_kernel<G, 0, 1><<<grid, SolidJac<G, 1>::THREADS, smem, st>>>(a);
         } else {
             const size_t smem = SolidJac<G>::SM::bytes(a.nq);
             if (G == 3 && nq == 14) {
@@ -198,6 +204,27 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
                 jac_solid_kernel<G, 0><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
             }
         }
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (!is_fluid && r.rc.visco) {
+        // viscoelastic part of J_nl (solid.py:49,54): blocks psi x delta d (and psi x delta v for "Form1") through the
+        // generic derivative-tensor kernel (binary-search scatter: needs the column array)
+        if (!h->colidx) return fail(h, TFSI_ERR_ARG, "the viscoelastic solid needs the column array (tfsi_release_pattern was called)");
+        const int off_v = G * Dim<G>::N2;
+        LinArgs la;
+        la.c = cell_args(h, r, nq, x, x1, A);
+        la.nblk = 0;
+        auto add = [&](int to, int tr, int gen) {
+            LinBlock b; b.test_off = to; b.trial_off = tr; b.mass_kind = 0; b.cm = 0.0; b.ck = 0.0;
+            b.ck_per_volume = 0; b.pad_ = 0; b.gen_kind = gen;
+            la.blk[la.nblk++] = b;
+        };
+        if (r.rc.visco == 1) { add(off_v, 0, GEN_VISCO_F1_DD); add(off_v, off_v, GEN_VISCO_F1_DV); }
+        else add(off_v, 0, GEN_VISCO_F2_DD);
+        const int64_t ntask = r.ncells * la.nblk * 2;
+        KernelTimer kt(h, 1, st);
+        lin_jacobian_kernel<G><<<(unsigned)((ntask + 127) / 128), 128, 0, st>>>(la);
         h->launches++;
         CK(h, cudaGetLastError());
     }
@@ -323,6 +350,10 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
             add(off_v, off_v, 1, rc.rho_s_k, 0.0, 0);
             add(off_d, off_d, 1, rc.delta_rho_k, 0.0, 0);
             add(off_d, off_v, 1, -rc.delta_rho * rc.th0, 0.0, 0);
+            if (rc.visco == 2) {                                                        // solid.py:55, frozen at x1
+                add(off_v, off_d, 0, 0.0, 0.0, 0);
+                la.blk[la.nblk - 1].gen_kind = GEN_VISCO_F2_LIN;
+            }
         }
         if (la.nblk == 0) continue;
         const int64_t ntask = r.ncells * la.nblk * 2;
@@ -333,6 +364,9 @@ int launch_linear(tfsi_handle* h, const double* x, const double* x1, double* A, 
     return 0;
 }
 
+// solid regions with an energy-based material model or viscoelasticity run the LIFT_SOLID_GENERAL instantiation
+inline bool general_solid(const RegionConst& rc) { return rc.kind == TFSI_KIND_SOLID && (rc.mat != MAT_SVK || rc.visco != 0); }
+
 template <int G, bool BIH, int NC, int LIFT>
 int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
     typedef ResCfg<G, BIH> R;
@@ -341,6 +375,7 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         const RegionConst& rc = r.rc;
+        if (general_solid(rc) != (LIFT == LIFT_SOLID_GENERAL)) continue;
         if (rc.kind == TFSI_KIND_FLUID && !rc.fluid_on && rc.ext == 0) continue;
         if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
@@ -371,6 +406,14 @@ int residual_nc(const tfsi_handle* h) {
 
 template <int G, bool BIH>
 int launch_residual_t(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    bool any_general = false;
+    for (const Region& r : h->regions) any_general = any_general || (r.ncells && general_solid(r.rc));
+    if (any_general) {
+        int rc = h->res_nc == 32 ? launch_residual_nc<G, BIH, 32, LIFT_SOLID_GENERAL>(h, x, x1, b, st)
+               : h->res_nc == 16 ? launch_residual_nc<G, BIH, 16, LIFT_SOLID_GENERAL>(h, x, x1, b, st)
+               : fail(h, TFSI_ERR_UNSUPPORTED, "residual rule with %d points does not fit in shared memory", h->tabR.nq);
+        if (rc) return rc;
+    }
     if (!BIH && h->ext == TFSI_EXT_LAPLACE && h->ext_sub == TFSI_LAPLACE_VOLUME_CHANGE) {      // alfa = 1/J(d)
         if (h->res_nc == 32) return launch_residual_nc<G, false, 32, LIFT_VOLUME_CHANGE>(h, x, x1, b, st);
         if (h->res_nc == 16) return launch_residual_nc<G, false, 16, LIFT_VOLUME_CHANGE>(h, x, x1, b, st);
@@ -545,6 +588,17 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             r.marker = rg.marker; r.colour = 0;
             r.rc = make_region_const(rg.kind, rg.rho, rg.mu, rg.lambda, p->dt, p->theta, p->fluid_on, p->solid_on,
                                      p->extrapolation, p->extrapolation_sub_type, p->hmin, p->has_gravity ? p->gravity : 0.0);
+            if (rg.kind == TFSI_KIND_SOLID) {
+                if (rg.material < TFSI_MAT_SVK || rg.material > TFSI_MAT_GENT || rg.viscoelasticity < 0 || rg.viscoelasticity > 2) {
+                    tfsi_destroy(h);
+                    return fail(nullptr, TFSI_ERR_ARG, "region %d: unknown material model %d / viscoelasticity %d", i, rg.material, rg.viscoelasticity);
+                }
+                if (rg.material == TFSI_MAT_GENT && !(rg.Jm > 0.0)) {
+                    tfsi_destroy(h);
+                    return fail(nullptr, TFSI_ERR_ARG, "region %d: the Gent model needs Jm > 0", i);
+                }
+                set_solid_model(r.rc, rg.material, rg.C01, rg.C10, rg.C11, rg.Jm, rg.viscoelasticity, rg.mu_visc, rg.lambda_visc);
+            }
             r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);

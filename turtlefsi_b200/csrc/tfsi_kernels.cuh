@@ -488,22 +488,25 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
 
 // -------------------------------------------------------------------------------------------
 // SOLID non-linear Jacobian (solid.py:62, St.Venant-Kirchhoff)
-template <int G> struct SolidJac {
+// MAT = 0: St.Venant-Kirchhoff in closed form (28 per-point items, C' from <= 4 FMAs per entry); MAT = 1: any
+// energy-based model (common.py:110-125) through the per-point tangent table of solid_base_energy
+template <int G, int MAT = 0> struct SolidJac {
     static constexpr int N2 = Dim<G>::N2;
     static constexpr int NCOEF = G * N2;               // d dofs = trial columns
     static constexpr int NROWS = G * N2;               // psi rows
     typedef typename SolidCfg<G>::L L;
     static constexpr int THREADS = SolidCfg<G>::WARPS * 32;
-    typedef JacSmem<G, L, SolidBase<G>::COUNT, NCOEF, NCOEF, NROWS> SM;
+    static constexpr int NBASE = MAT ? SolidBaseGen<G>::COUNT : SolidBase<G>::COUNT;
+    typedef JacSmem<G, L, NBASE, NCOEF, NCOEF, NROWS> SM;
 };
 
-template <int G, int NQ, int HALF>
+template <int G, int NQ, int HALF, int MAT>
 __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* basec, const int64_t* rowst,
                                                const uint16_t* srank, uint64_t* mbar, int c, bool valid, int ca, int cb)
 {
     constexpr int N2 = Dim<G>::N2;
     constexpr int NJ = HalfCols<G, HALF>::NJ;
-    constexpr int QSTR = SolidJac<G>::L::NC * SolidJac<G>::SM::STRIDE;
+    constexpr int QSTR = SolidJac<G, MAT>::L::NC * SolidJac<G, MAT>::SM::STRIDE;
     double Z[N2][NJ];
 #pragma unroll
     for (int i = 0; i < N2; ++i)
@@ -514,22 +517,23 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
     for (int q = 0; q < nq; ++q) {
         auto bv = [&](int item) { return basec[q * QSTR + item]; };
         double C[G + 1][G + 1];
-        solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
+        if (MAT) solid_C_psi_dd_energy<G>(bv, ca, cb, C);
+        else solid_C_psi_dd<G>(bv, a.rc, ca, cb, C);
         block_p2p2<G, HALF, 4>(c_tabJ, q0 + q, C, Z);
     }
     mbar_wait(mbar, 0);
-    if (valid) scatter_p2p2<G, typename SolidJac<G>::L, SolidJac<G>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
+    if (valid) scatter_p2p2<G, typename SolidJac<G, MAT>::L, SolidJac<G, MAT>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
 }
 
-template <int G, int NQ>
+template <int G, int NQ, int MAT = 0>
 // 160 registers as the fluid kernel: the background copy keeps running beside the three 4-warp CTAs per SM
 __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
-    typedef typename SolidJac<G>::SM SM;
-    constexpr int NCOEF = SolidJac<G>::NCOEF;
-    typedef typename SolidJac<G>::L L;
-    constexpr int JAC_THREADS = SolidJac<G>::THREADS;
+    typedef typename SolidJac<G, MAT>::SM SM;
+    constexpr int NCOEF = SolidJac<G, MAT>::NCOEF;
+    typedef typename SolidJac<G, MAT>::L L;
+    constexpr int JAC_THREADS = SolidJac<G, MAT>::THREADS;
     constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, STRIDE = SM::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nq = NQ ? NQ : a.nq, q0 = NQ ? 0 : a.q0;
@@ -580,7 +584,8 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
         auto cf = [&](int k) { return coef[k * NC + c]; };
         double* dstb = base + ((size_t)q * NC + c) * STRIDE;
         auto out = [&](int item, double v) { dstb[item] = v; };
-        solid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, out);
+        if (MAT) solid_base_energy<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, out);
+        else solid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, out);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -602,8 +607,8 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
         const int c = grp * CPW + cw;
         const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
         const double* basec = base + (size_t)c * STRIDE;
-        if (half == 0) solid_big_task<G, NQ, 0>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
-        else solid_big_task<G, NQ, 1>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+        if (half == 0) solid_big_task<G, NQ, 0, MAT>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
+        else solid_big_task<G, NQ, 1, MAT>(a, basec, rowst, srank, mbar, c, valid, ca, lcomp);
     }
 }
 
@@ -677,22 +682,42 @@ __global__ void __launch_bounds__(128) lin_jacobian_kernel(LinArgs la)
                 for (int i = 0; i < N2; ++i) for (int j = 0; j < NJ; ++j) Z[i][j] = 0.0;
                 for (int q = 0; q < a.nq; ++q) {
                     const double jw = c_tabJ.w[q] * adet;
-                    double Gp[G][G];
-                    for (int aa = 0; aa < G; ++aa) {
-                        double Gd[G];
-                        for (int t = 0; t < G; ++t) Gd[t] = 0;
-                        for (int j = 0; j < N2; ++j) {
-                            const double dj = a.x[dofs[aa * N2 + j]];
-                            for (int t = 0; t < G; ++t) Gd[t] += dj * c_tabJ.dphi2[q][j][t];
+                    // physical gradient of the P2 vector field at local offset `off` of the state vector `vec`
+                    auto phys_grad = [&](const double* vec, int off, double (&out)[G][G]) {
+                        for (int aa = 0; aa < G; ++aa) {
+                            double Gr[G];
+                            for (int t = 0; t < G; ++t) Gr[t] = 0;
+                            for (int j = 0; j < N2; ++j) {
+                                const double uj = vec[dofs[off + aa * N2 + j]];
+                                for (int t = 0; t < G; ++t) Gr[t] += uj * c_tabJ.dphi2[q][j][t];
+                            }
+                            for (int b = 0; b < G; ++b) {
+                                double sacc = 0;
+                                for (int t = 0; t < G; ++t) sacc += Gr[t] * K[t][b];
+                                out[aa][b] = sacc;
+                            }
                         }
-                        for (int b = 0; b < G; ++b) {
-                            double sacc = 0;
-                            for (int t = 0; t < G; ++t) sacc += Gd[t] * K[t][b];
-                            Gp[aa][b] = sacc;
-                        }
-                    }
+                    };
                     double D[G][G][G][G];
-                    lift_flux_derivative<G>(blk.gen_kind, Gp, a_mu, a_lam, D);
+                    if (blk.gen_kind <= 2) {
+                        double Gp[G][G];
+                        phys_grad(a.x, 0, Gp);
+                        lift_flux_derivative<G>(blk.gen_kind, Gp, a_mu, a_lam, D);
+                    } else {                                   // viscoelastic solid (solid.py:46-59)
+                        double Fm[G][G], Gw[G][G];
+                        phys_grad(blk.gen_kind == GEN_VISCO_F2_LIN ? a.x1 : a.x, 0, Fm);
+                        if (blk.gen_kind == GEN_VISCO_F2_DD) {
+                            double G1[G][G];
+                            phys_grad(a.x1, 0, G1);
+                            for (int aa = 0; aa < G; ++aa) for (int b = 0; b < G; ++b) Gw[aa][b] = Fm[aa][b] - G1[aa][b];
+                        } else if (blk.gen_kind == GEN_VISCO_F2_LIN) {
+                            for (int aa = 0; aa < G; ++aa) for (int b = 0; b < G; ++b) Gw[aa][b] = 0.0;
+                        } else {
+                            phys_grad(a.x, G * N2, Gw);
+                        }
+                        for (int aa = 0; aa < G; ++aa) Fm[aa][aa] += 1.0;
+                        visco_flux_derivative<G>(blk.gen_kind, a.rc, Fm, Gw, D);
+                    }
                     double C[G + 1][G + 1];
                     C[0][0] = 0.0;
                     for (int s = 0; s < G; ++s) {

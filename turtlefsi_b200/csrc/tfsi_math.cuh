@@ -21,8 +21,10 @@
 
 #if defined(__CUDACC__)
 #define TFSI_HD __host__ __device__ __forceinline__
+#define TFSI_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define TFSI_HD inline
+#define TFSI_HD_NOINLINE inline
 #endif
 
 namespace tfsi {
@@ -118,8 +120,16 @@ struct RegionConst {
     int fluid_on, solid_on;
     int ext;               // 0 none, 1 laplace, 2 biharmonic, 3 elastic
     int ext_sub;           // laplace: 0 constant, 1 small_constant, 2 volume, 3 volume_change
-    int pad_;
+    int mat;               // solid material model: 0 StVenantKirchoff (closed form), else MAT_* (energy based, common.py:110-125)
+    double mC01, mC10, mC11, mJm;   // MooneyRivlin C01, C10, C11; Gent Jm
+    int visco;             // viscoelasticity (solid.py:46-59): 0 none, 1 "Form1" (rate from v), 2 "Form2" (rate from (d - d1)/k)
+    int pad2_;
+    double mu_visc, lam_visc;   // Svisc_D = mu_visc tr(D) I + 2 lambda_visc D (common.py:129-139)
+    double inv_k;               // 1 / k
 };
+
+// material models of turtleFSI/modules/common.py:100-127 (the `material_model` strings, :104-121)
+enum { MAT_SVK = 0, MAT_SVK_ENERGY = 1, MAT_NEO_HOOKEAN = 2, MAT_MOONEY_RIVLIN = 3, MAT_GENT = 4 };
 
 // ---------------------------------------------------------------------------------------------
 // FLUID, non-linear Jacobian: per-point base items (stored lane-contiguous in shared memory).
@@ -411,6 +421,207 @@ TFSI_HD void solid_base(const Tab& tab, int q, const double (&K)[G][G], double a
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ENERGY-BASED solid materials (common.py:110-125: P = diff(W, F) with F a ufl variable; W_St_Venant_Kirchoff :214-225,
+// W_Neo_Hookean :228-240, W_Gent :242-256, W_Mooney_Rivlin :258-273). Every W of the reference is a function of the
+// invariants I1 = tr(F^T F), I2 = (I1^2 - tr((F^T F)^2)) / 2 and J = det F, so
+//     P = W_1 dI1/dF + W_2 dI2/dF + W_J dJ/dF ,   dI1/dF = 2 F,  dI2/dF = 2 (I1 F - F C),  dJ/dF = cof F = J F^-T
+//     dP/dF = sum_ab W_ab (d a/dF) (x) (d b/dF) + W_1 d2I1 + W_2 d2I2 + W_J d2J
+// and only the SCALAR function W(I1, I2, J) differs between the models. Its gradient and Hessian come from evaluating
+// it on hyper-dual numbers (f + a e1 + b e2 + ab e1 e2, e1^2 = e2^2 = 0): exact derivatives, one definition per model.
+struct HDual { double v, a, b, ab; };
+TFSI_HD HDual hd(double v) { return HDual{v, 0.0, 0.0, 0.0}; }
+TFSI_HD HDual operator+(HDual x, HDual y) { return HDual{x.v + y.v, x.a + y.a, x.b + y.b, x.ab + y.ab}; }
+TFSI_HD HDual operator-(HDual x, HDual y) { return HDual{x.v - y.v, x.a - y.a, x.b - y.b, x.ab - y.ab}; }
+TFSI_HD HDual operator*(HDual x, HDual y) {
+    return HDual{x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b, x.ab * y.v + x.a * y.b + x.b * y.a + x.v * y.ab};
+}
+TFSI_HD HDual operator*(double c, HDual x) { return HDual{c * x.v, c * x.a, c * x.b, c * x.ab}; }
+TFSI_HD HDual operator+(HDual x, double c) { return HDual{x.v + c, x.a, x.b, x.ab}; }
+TFSI_HD HDual operator-(HDual x, double c) { return HDual{x.v - c, x.a, x.b, x.ab}; }
+// g(x) for a scalar function with derivatives g1, g2 at x.v
+TFSI_HD HDual hd_chain(HDual x, double g0, double g1, double g2) {
+    return HDual{g0, g1 * x.a, g1 * x.b, g1 * x.ab + g2 * x.a * x.b};
+}
+TFSI_HD HDual hd_log(HDual x) { return hd_chain(x, log(x.v), 1.0 / x.v, -1.0 / (x.v * x.v)); }
+TFSI_HD HDual hd_pow(HDual x, double p) {
+    const double f = pow(x.v, p);
+    return hd_chain(x, f, p * f / x.v, p * (p - 1.0) * f / (x.v * x.v));
+}
+
+// W(I1, I2, J) of the model rc.mat in G dimensions (the reference's expressions, incl. their hard-coded 3s)
+TFSI_HD HDual solid_energy(const RegionConst& rc, int G, HDual I1, HDual I2, HDual J) {
+    switch (rc.mat) {
+    case MAT_SVK_ENERGY: {        // lambda/2 tr(E)^2 + mu tr(E E),  tr E = (I1 - G)/2, tr(E E) = (I1^2 - 2 I2 - 2 I1 + G)/4
+        const HDual trE = 0.5 * (I1 - (double)G);
+        return (0.5 * rc.lam) * (trE * trE) + (0.25 * rc.mu) * (I1 * I1 - 2.0 * I2 - 2.0 * I1 + (double)G);
+    }
+    case MAT_NEO_HOOKEAN: {       // C1 (I1 - G - 2 ln J) + D1 (J - 1)^2,  C1 = mu/2, D1 = lambda/2
+        const HDual Jm1 = J - 1.0;
+        return (0.5 * rc.mu) * (I1 - (double)G - 2.0 * hd_log(J)) + (0.5 * rc.lam) * (Jm1 * Jm1);
+    }
+    case MAT_GENT: {              // -(mu/2) (Jm ln(1 - (I1 - 3)/Jm) + 2 ln J)
+        const HDual arg = hd(1.0) - (1.0 / rc.mJm) * (I1 - 3.0);
+        return (-0.5 * rc.mu) * (rc.mJm * hd_log(arg) + 2.0 * hd_log(J));
+    }
+    case MAT_MOONEY_RIVLIN: {     // C01 (Ib2 - 3) + C10 (Ib1 - 3) + C11 (Ib2 - 3)(Ib1 - 3) + (1/D1)(J - 1)^2, D1 = 2/(lambda + 2 mu/3)
+        const HDual Ib1 = hd_pow(J, -2.0 / 3.0) * I1, Ib2 = hd_pow(J, -4.0 / 3.0) * I2;
+        const HDual Jm1 = J - 1.0;
+        return rc.mC01 * (Ib2 - 3.0) + rc.mC10 * (Ib1 - 3.0) + rc.mC11 * ((Ib2 - 3.0) * (Ib1 - 3.0)) +
+               (0.5 * (rc.lam + 2.0 * rc.mu / 3.0)) * (Jm1 * Jm1);
+    }
+    default: return hd(0.0);
+    }
+}
+
+// gradient w[3] = (W_1, W_2, W_J) and Hessian h[6] = (W_11, W_12, W_1J, W_22, W_2J, W_JJ) at (I1, I2, J)
+TFSI_HD void solid_energy_derivatives(const RegionConst& rc, int G, double I1, double I2, double J, double (&w)[3], double (&h)[6]) {
+    const double x[3] = {I1, I2, J};
+    int k = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            HDual v[3] = {hd(x[0]), hd(x[1]), hd(x[2])};
+            v[i].a = 1.0;
+            v[j].b = 1.0;
+            const HDual W = solid_energy(rc, G, v[0], v[1], v[2]);
+            if (j == i) w[i] = W.a;
+            h[k++] = W.ab;
+        }
+}
+
+// kinematic pieces shared by stress and tangent
+template <int G> struct MatKin {
+    double C[G][G], B[G][G], cof[G][G], G2[G][G];     // F^T F, F F^T, cof F = J F^-T, dI2/dF = 2 (I1 F - F C)
+    double I1, I2, J;
+};
+template <int G>
+TFSI_HD void material_kinematics(const double (&F)[G][G], MatKin<G>& k) {
+    double Fi[G][G];
+    k.J = inv<G>(F, Fi);
+    double trC2 = 0;
+    k.I1 = 0;
+    for (int i = 0; i < G; ++i)
+        for (int j = 0; j < G; ++j) {
+            double c = 0, b = 0;
+            for (int m = 0; m < G; ++m) { c += F[m][i] * F[m][j]; b += F[i][m] * F[j][m]; }
+            k.C[i][j] = c; k.B[i][j] = b;
+            k.cof[i][j] = k.J * Fi[j][i];
+            trC2 += c * c;
+            if (i == j) k.I1 += c;
+        }
+    k.I2 = 0.5 * (k.I1 * k.I1 - trC2);
+    for (int a = 0; a < G; ++a)
+        for (int j = 0; j < G; ++j) {
+            double fc = 0;
+            for (int m = 0; m < G; ++m) fc += F[a][m] * k.C[m][j];
+            k.G2[a][j] = 2.0 * (k.I1 * F[a][j] - fc);
+        }
+}
+
+// first Piola-Kirchhoff stress of an energy-based model (kept out of line: the St.Venant-Kirchhoff hot path of the
+// residual kernel must not pay registers for it)
+template <int G>
+TFSI_HD_NOINLINE void solid_piola_energy(const RegionConst& rc, const double (&F)[G][G], double (&P)[G][G]) {
+    MatKin<G> k;
+    material_kinematics<G>(F, k);
+    double w[3], h[6];
+    solid_energy_derivatives(rc, G, k.I1, k.I2, k.J, w, h);
+    for (int a = 0; a < G; ++a)
+        for (int j = 0; j < G; ++j) P[a][j] = 2.0 * w[0] * F[a][j] + w[1] * k.G2[a][j] + w[2] * k.cof[a][j];
+}
+
+// per-point base of the non-linear solid Jacobian for energy-based models: the tangent dP/dF contracted with the
+// geometry on both gradient slots and pre-scaled,  T[(a,s)][(b,t)] = theta0 w |detJ| sum_JL K_sJ (dP_aJ/dF_bL) K_tL,
+// symmetric in (a,s) <-> (b,t) (hyperelasticity): n (n + 1) / 2 entries, n = G*G.
+template <int G> struct SolidBaseGen {
+    static constexpr int JW = 0;
+    static constexpr int TAN = 1;
+    static constexpr int NT = (G * G) * (G * G + 1) / 2;   // 45 (3-D), 10 (2-D)
+    static constexpr int COUNT = TAN + NT;
+};
+
+template <int G, class Tab, class CF, class OUT>
+TFSI_HD void solid_base_energy(const Tab& tab, int q, const double (&K)[G][G], double adet,
+                               const RegionConst& rc, CF cf, OUT out)
+{
+    constexpr int N2 = Dim<G>::N2;
+    typedef SolidBaseGen<G> I;
+    double F[G][G];
+    for (int a = 0; a < G; ++a) {
+        double Gd[G];
+        for (int t = 0; t < G; ++t) Gd[t] = 0;
+        for (int j = 0; j < N2; ++j) {
+            const double dj = cf(a * N2 + j);
+            for (int t = 0; t < G; ++t) Gd[t] += dj * tab.dphi2[q][j][t];
+        }
+        for (int b = 0; b < G; ++b) {
+            double s = (a == b) ? 1.0 : 0.0;
+            for (int t = 0; t < G; ++t) s += Gd[t] * K[t][b];
+            F[a][b] = s;
+        }
+    }
+    MatKin<G> k;
+    material_kinematics<G>(F, k);
+    double w[3], h[6];
+    solid_energy_derivatives(rc, G, k.I1, k.I2, k.J, w, h);
+    const double jw = rc.th0 * tab.w[q] * adet;
+    out(I::JW, jw);
+    // geometry-contracted pieces  X~[a][s] = sum_J K[s][J] X[a][J]
+    double Ft[G][G], G2t[G][G], Ct[G][G], KK[G][G], KCK[G][G];
+    for (int a = 0; a < G; ++a)
+        for (int s = 0; s < G; ++s) {
+            double x = 0, y = 0, z = 0;
+            for (int j = 0; j < G; ++j) { x += K[s][j] * F[a][j]; y += K[s][j] * k.G2[a][j]; z += K[s][j] * k.cof[a][j]; }
+            Ft[a][s] = x; G2t[a][s] = y; Ct[a][s] = z;
+        }
+    for (int s = 0; s < G; ++s)
+        for (int t = 0; t < G; ++t) {
+            double x = 0, y = 0;
+            for (int j = 0; j < G; ++j) {
+                x += K[s][j] * K[t][j];
+                double kc = 0;
+                for (int l = 0; l < G; ++l) kc += k.C[l][j] * K[t][l];
+                y += K[s][j] * kc;
+            }
+            KK[s][t] = x; KCK[s][t] = y;
+        }
+    // T_alpha[b][t] = sum_beta W_alpha,beta (d beta/dF)~[b][t]   with (d I1/dF)~ = 2 F~
+    const double H[3][3] = {{h[0], h[1], h[2]}, {h[1], h[3], h[4]}, {h[2], h[4], h[5]}};
+    double T[3][G][G];
+    for (int al = 0; al < 3; ++al)
+        for (int b = 0; b < G; ++b)
+            for (int t = 0; t < G; ++t)
+                T[al][b][t] = 2.0 * H[al][0] * Ft[b][t] + H[al][1] * G2t[b][t] + H[al][2] * Ct[b][t];
+    const double wJ_J = w[2] / k.J;
+    for (int a = 0; a < G; ++a)
+        for (int s = 0; s < G; ++s)
+            for (int b = 0; b < G; ++b)
+                for (int t = 0; t < G; ++t) {
+                    const int p = a * G + s, r = b * G + t;
+                    if (r < p) continue;
+                    const double dab = (a == b) ? 1.0 : 0.0;
+                    double v = 2.0 * Ft[a][s] * T[0][b][t] + G2t[a][s] * T[1][b][t] + Ct[a][s] * T[2][b][t];
+                    v += dab * ((2.0 * w[0] + 2.0 * w[1] * k.I1) * KK[s][t] - 2.0 * w[1] * KCK[s][t]);
+                    v += 2.0 * w[1] * (2.0 * Ft[b][t] * Ft[a][s] - Ft[a][t] * Ft[b][s] - k.B[a][b] * KK[s][t]);
+                    v += wJ_J * (Ct[b][t] * Ct[a][s] - Ct[a][t] * Ct[b][s]);
+                    out(I::TAN + symi(p, r, G * G), jw * v);
+                }
+}
+
+// C' (gradient slots only) of psi_a x delta d_b for energy-based models: read from the tangent table
+template <int G, class BV>
+TFSI_HD void solid_C_psi_dd_energy(BV bv, int a, int b, double (&C)[G + 1][G + 1])
+{
+    typedef SolidBaseGen<G> I;
+    C[0][0] = 0.0;
+#pragma unroll
+    for (int t = 0; t < G; ++t) { C[0][1 + t] = 0.0; C[1 + t][0] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < G; ++s)
+#pragma unroll
+        for (int t = 0; t < G; ++t) C[1 + s][1 + t] = bv(I::TAN + symi(a * G + s, b * G + t, G * G));
+}
+
 // C' (gradient slots only) of  psi_a x delta d_b :
 //   d_ab G_j.S G_i + mu (f_a.G_j)(f_b.G_i) + mu (F F^T)_ab G_i.G_j + lam (f_a.G_i)(f_b.G_j)
 template <int G, class BV>
@@ -629,7 +840,8 @@ template <int G> struct PointFlux {
 
 // LIFT: 1 = laplace "volume_change" (alfa = 1/J(d^n), laplace.py:33-34), 2 = elastic lifting (elastic.py:18-27)
 // compiled in; a template flag so that the default instantiation keeps its register allocation
-constexpr int LIFT_DEFAULT = 0, LIFT_VOLUME_CHANGE = 1, LIFT_ELASTIC = 2;
+// 3 = general solid (energy-based material models common.py:110-125 and / or viscoelasticity solid.py:46-59) compiled in
+constexpr int LIFT_DEFAULT = 0, LIFT_VOLUME_CHANGE = 1, LIFT_ELASTIC = 2, LIFT_SOLID_GENERAL = 3;
 template <int G, int LIFT = 0, class Tab, class CF, class CF1>
 TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], double adet,
                             const RegionConst& rc, double alfa_cell, CF cf, CF1 cf1,
@@ -863,8 +1075,73 @@ TFSI_HD void residual_point(const Tab& tab, int q, const double (&K)[G][G], doub
                 }
             }
         };
-        piolaK(F, jw * rc.th0, f.psi_grad);
-        piolaK(F1, jw * rc.th1, f.psi_grad);
+        auto piolaE = [&](const double (&Fm)[G][G], double scale, double (&out)[G][G]) {   // energy-based models
+            double P[G][G];
+            solid_piola_energy<G>(rc, Fm, P);
+#pragma unroll
+            for (int a = 0; a < G; ++a)
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    double x = 0;
+#pragma unroll
+                    for (int b = 0; b < G; ++b) x += K[s][b] * P[a][b];
+                    out[a][s] += scale * x;
+                }
+        };
+        if (LIFT != LIFT_SOLID_GENERAL || rc.mat == MAT_SVK) {
+            piolaK(F, jw * rc.th0, f.psi_grad);
+            piolaK(F1, jw * rc.th1, f.psi_grad);
+        } else {
+            piolaE(F, jw * rc.th0, f.psi_grad);
+            piolaE(F1, jw * rc.th1, f.psi_grad);
+        }
+        if (LIFT == LIFT_SOLID_GENERAL && rc.visco) {
+            // solid.py:46-59: + theta0 F(d) Svisc_D(w) : grad psi + theta1 F(d1) Svisc_D(w1) : grad psi with the rate
+            // w = v, w1 = v1 ("Form1") or w = w1 = (d - d1) / k ("Form2"); Svisc_D of common.py:129-139
+            auto viscK = [&](const double (&Fm)[G][G], const double (&Gw)[G][G], double scale, double (&out)[G][G]) {
+                double S[G][G], tr = 0;
+#pragma unroll
+                for (int a = 0; a < G; ++a) tr += Gw[a][a];
+#pragma unroll
+                for (int a = 0; a < G; ++a)
+#pragma unroll
+                    for (int b = 0; b < G; ++b) S[a][b] = rc.lam_visc * (Gw[a][b] + Gw[b][a]) + ((a == b) ? rc.mu_visc * tr : 0.0);
+#pragma unroll
+                for (int a = 0; a < G; ++a) {
+                    double P[G];
+#pragma unroll
+                    for (int b = 0; b < G; ++b) {
+                        double x = 0;
+#pragma unroll
+                        for (int c = 0; c < G; ++c) x += Fm[a][c] * S[c][b];
+                        P[b] = x;
+                    }
+#pragma unroll
+                    for (int s = 0; s < G; ++s) {
+                        double x = 0;
+#pragma unroll
+                        for (int b = 0; b < G; ++b) x += K[s][b] * P[b];
+                        out[a][s] += scale * x;
+                    }
+                }
+            };
+            double W0[G][G], W1[G][G];
+#pragma unroll
+            for (int a = 0; a < G; ++a)
+#pragma unroll
+                for (int b = 0; b < G; ++b) {
+                    if (rc.visco == 1) {
+                        double x = 0, y = 0;
+#pragma unroll
+                        for (int t = 0; t < G; ++t) { x += Gv[a][t] * K[t][b]; y += Gv1[a][t] * K[t][b]; }
+                        W0[a][b] = x; W1[a][b] = y;
+                    } else {
+                        W0[a][b] = W1[a][b] = rc.inv_k * (F[a][b] - F1[a][b]);
+                    }
+                }
+            viscK(F, W0, jw * rc.th0, f.psi_grad);
+            viscK(F1, W1, jw * rc.th1, f.psi_grad);
+        }
 #pragma unroll
         for (int a = 0; a < G; ++a) {
             f.psi_val[a] = jw * rc.rho_s_k * (v[a] - v1[a]);
@@ -916,6 +1193,38 @@ TFSI_HD void lift_flux_derivative(int kind, const double (&Gp)[G][G], double a_m
             }
             D[a][s][b][t] = dJ * SFt[a][s] + J * x - J * SFt[a][t] * Fi[s][b];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Derivative of the viscoelastic fluxes of the solid (solid.py:46-59, Svisc_D of common.py:129-139) with respect to the
+// gradient of the trial field, D[a][s][b][t] = d Phi_as / d (grad u)_bt, Phi the tensor contracted with grad psi:
+//   kind 3  "Form1", non-linear, u = d :  Phi = theta0 F(d) Sv(grad v)          -> theta0 d_ab Sv_ts
+//   kind 4  "Form1", non-linear, u = v :  Phi = theta0 F(d) Sv(grad v)          -> theta0 F dSv
+//   kind 5  "Form2", non-linear, u = d :  Phi = theta0/k F(d) Sv(grad(d - d1))  -> theta0/k (d_ab Sv_ts + F dSv)
+//   kind 6  "Form2", "linear",   u = d :  Phi = theta1/k F(d1) Sv(grad(d - d1)) -> theta1/k F(d1) dSv   (frozen in A_pre)
+// with (F dSv)[a][s][b][t] = mu_visc d_bt F_as + lambda_visc (F_ab d_st + F_at d_sb).
+// Fm = F(d) (kinds 3-5) or F(d1) (kind 6); Gw = grad v (3) or grad(d - d1) (5), unused otherwise.
+constexpr int GEN_VISCO_F1_DD = 3, GEN_VISCO_F1_DV = 4, GEN_VISCO_F2_DD = 5, GEN_VISCO_F2_LIN = 6;
+template <int G>
+TFSI_HD void visco_flux_derivative(int kind, const RegionConst& rc, const double (&Fm)[G][G], const double (&Gw)[G][G],
+                                   double (&D)[G][G][G][G])
+{
+    const double scale = (kind == GEN_VISCO_F1_DD || kind == GEN_VISCO_F1_DV) ? rc.th0
+                       : (kind == GEN_VISCO_F2_DD ? rc.th0 * rc.inv_k : rc.th1 * rc.inv_k);
+    const double rate = (kind == GEN_VISCO_F2_DD) ? rc.inv_k : 1.0;     // Sv of (d - d1)/k
+    double Sv[G][G], tr = 0;
+    for (int a = 0; a < G; ++a) tr += Gw[a][a];
+    for (int a = 0; a < G; ++a) for (int b = 0; b < G; ++b)
+        Sv[a][b] = rate * (rc.lam_visc * (Gw[a][b] + Gw[b][a]) + ((a == b) ? rc.mu_visc * tr : 0.0));
+    const double th = (kind == GEN_VISCO_F2_DD) ? rc.th0 : scale;
+    for (int a = 0; a < G; ++a) for (int s = 0; s < G; ++s) for (int b = 0; b < G; ++b) for (int t = 0; t < G; ++t) {
+        double x = 0.0;
+        if (kind == GEN_VISCO_F1_DD || kind == GEN_VISCO_F2_DD) x += (a == b) ? th * Sv[t][s] : 0.0;
+        if (kind != GEN_VISCO_F1_DD)
+            x += scale * (((b == t) ? rc.mu_visc * Fm[a][s] : 0.0)
+                          + rc.lam_visc * (((s == t) ? Fm[a][b] : 0.0) + ((s == b) ? Fm[a][t] : 0.0)));
+        D[a][s][b][t] = x;
     }
 }
 
@@ -978,7 +1287,16 @@ inline RegionConst make_region_const(int kind, double rho, double mu, double lam
         rc.rho_s_k = rho / k; rc.delta_rho_k = delta * rho / k; rc.delta_rho = delta * rho;
         rc.grav_rho = gravity * rho;
     }
+    rc.inv_k = 1.0 / k;
     return rc;
+}
+
+// material model (MAT_*) and viscoelasticity of a solid region (common.py:104-139, solid.py:46-59)
+inline void set_solid_model(RegionConst& rc, int material, double C01, double C10, double C11, double Jm,
+                            int visco, double mu_visc, double lam_visc)
+{
+    rc.mat = material; rc.mC01 = C01; rc.mC10 = C10; rc.mC11 = C11; rc.mJm = Jm;
+    rc.visco = visco; rc.mu_visc = mu_visc; rc.lam_visc = lam_visc;
 }
 
 }  // namespace tfsi

@@ -23,7 +23,15 @@ APRE_COMPRESSED = 1     # TFSI_APRE_COMPRESSED sentinel (include/turtlefsi_b200.
 
 class TfsiRegion(C.Structure):
     _fields_ = [("marker", C.c_int32), ("kind", C.c_int32), ("rho", C.c_double),
-                ("mu", C.c_double), ("lam", C.c_double)]
+                ("mu", C.c_double), ("lam", C.c_double),
+                ("material", C.c_int32), ("viscoelasticity", C.c_int32),
+                ("C01", C.c_double), ("C10", C.c_double), ("C11", C.c_double), ("Jm", C.c_double),
+                ("mu_visc", C.c_double), ("lambda_visc", C.c_double)]
+
+
+# solid_properties["material_model"] (common.py:104-121) -> TFSI_MAT_*; ["viscoelasticity"] (solid.py:46-59)
+MATERIAL_MODELS = {"StVenantKirchoff": 0, "StVenantKirchoffEnergy": 1, "NeoHookean": 2, "MooneyRivlin": 3, "Gent": 4}
+VISCOELASTICITY = {None: 0, "None": 0, "Form1": 1, "Form2": 2}
 
 
 class TfsiProblem(C.Structure):

@@ -1,8 +1,29 @@
-"""turtleFSI/modules/solid.py counterpart: inertia + kinematic constraint (linear, solid.py:41-43), St.Venant-Kirchhoff
-stress (non-linear, :62-63) and gravity (:65-68) of every solid region as named cell integrals of the sm_100a kernels
+"""turtleFSI/modules/solid.py counterpart: inertia + kinematic constraint (linear, solid.py:41-43), the stress of the
+region's material model (non-linear, :62-63; common.py:104-125), viscoelasticity (:46-59) and gravity (:65-68) of every solid region as named cell integrals of the sm_100a kernels
 (`jac_solid_kernel`, `residual_kernel`, `lin_jacobian_kernel`); the Robin condition (:76-86) is a pair of fixed sparse
 facet operators (`facet_terms`)."""
 from ..ufl_lite import Form, KernelIntegral
+
+
+MATERIAL_KEYS = {"StVenantKirchoff": (), "StVenantKirchoffEnergy": (), "NeoHookean": (),
+                 "MooneyRivlin": ("C01", "C10", "C11"), "Gent": ("Jm",)}
+
+
+def material_constants(sp):
+    """the constants of one solid region beyond rho_s / mu_s / lambda_s, under the reference's own keys: material model
+    (common.py:104-125; the extra constants are read there with sp["C01"] ... so a missing one is a KeyError, as in the
+    reference) and viscoelasticity (solid.py:46-59, Svisc_D of common.py:129-139; an entry other than Form1 / Form2 means
+    none, solid.py:56-61)."""
+    model = sp["material_model"]
+    if model not in MATERIAL_KEYS:
+        raise RuntimeError('Invalid entry for material_model, choose from ["StVenantKirchoff",'
+                           '"StVenantKirchoffEnergy","NeoHookean","MooneyRivlin","Gent"]')
+    const = dict(material_model=model)
+    for key in MATERIAL_KEYS[model]:
+        const[key] = sp[key]
+    if sp.get("viscoelasticity") in ("Form1", "Form2"):
+        const.update(viscoelasticity=sp["viscoelasticity"], mu_visc_s=sp["mu_visc_s"], lambda_visc_s=sp["lambda_visc_s"])
+    return const
 
 
 def solid_setup(dx_s_id_list, solid_properties, **namespace):
@@ -10,9 +31,8 @@ def solid_setup(dx_s_id_list, solid_properties, **namespace):
     F_solid_nonlinear = Form()
     for solid_region in range(len(dx_s_id_list)):
         sp = solid_properties[solid_region]
-        if sp["material_model"] != "StVenantKirchoff":
-            raise RuntimeError("material model '%s' is not available on the B200 path" % sp["material_model"])
         const = dict(rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"])
+        const.update(material_constants(sp))
         F_solid_linear += KernelIntegral("solid", "linear", dx_s_id_list[solid_region], **const)
         F_solid_nonlinear += KernelIntegral("solid", "nonlinear", dx_s_id_list[solid_region], **const)
     return dict(F_solid_linear=F_solid_linear, F_solid_nonlinear=F_solid_nonlinear)

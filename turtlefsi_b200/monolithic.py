@@ -28,12 +28,10 @@ def assign_domain_properties(dx_f_id, rho_f, mu_f, fluid_properties, dx_s_id, ma
                              "mu_s": pick(mu_s, k), "lambda_s": pick(lambda_s, k)} for k, i in enumerate(dx_s_id_list)]
     elif isinstance(solid_properties, dict):
         solid_properties = [solid_properties]
-    for sp in solid_properties:
-        if sp["material_model"] != "StVenantKirchoff":
-            raise RuntimeError("material model '%s' is not available on the B200 path" % sp["material_model"])
+    from .modules.solid import material_constants
     regions = [dict(marker=fp["dx_f_id"], kind="fluid", rho=fp["rho_f"], mu=fp["mu_f"]) for fp in fluid_properties]
-    regions += [dict(marker=sp["dx_s_id"], kind="solid", rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"])
-                for sp in solid_properties]
+    regions += [dict(marker=sp["dx_s_id"], kind="solid", rho=sp["rho_s"], mu=sp["mu_s"], lambda_=sp["lambda_s"],
+                     **material_constants(sp)) for sp in solid_properties]
     ds_s_ext_id_list = (ds_s_id if isinstance(ds_s_id, list) else [ds_s_id]) if robin_bc else None   # domain.py:106-119
     return dict(dx_f_id_list=dx_f_id_list, dx_s_id_list=dx_s_id_list, fluid_properties=fluid_properties,
                 solid_properties=solid_properties, regions=regions, ds_s_ext_id_list=ds_s_ext_id_list)
