@@ -346,14 +346,13 @@ def prepare_matrices(w):
     asm.assemble_A_pre(w.xd, w.x1d, out=A)
     w.apre_nnz = asm.compress_A_pre(A)
     free, _ = torch.cuda.mem_get_info(asm.device)
-    w.pair = PAIR and 8 * asm.nnz * 2.5 < free                 # two more matrices must fit (not at 6 M tets per GPU)
+    w.pair = PAIR and 8 * asm.nnz * 1.35 < free                # one more matrix + the fix-up list must fit (not at 6 M tets per GPU)
     if w.pair:
-        # two matrices used alternately (the previous Jacobian is dead once the next one is assembled): the idle one
-        # is re-initialised in the background (masked copy from the dense A_pre) under the FP64-bound kernels
-        w.A_pre = A
-        w.As = [asm.new_matrix(), asm.new_matrix()]
-        w.bound_entries = asm.bind_matrix_pair(w.As[0], w.As[1], w.A_pre)
-        A = w.As[0]
+        # two matrices used alternately (the previous Jacobian is dead once the next one is assembled): the rows of the
+        # idle one are re-initialised by the fluid kernel of the running assembly (TMA zero-fill between its tasks,
+        # A_pre non-zeros added by REDs at the next assembly): no separate A := A_pre pass
+        w.As = [A, asm.new_matrix()]
+        w.bound_entries = asm.bind_matrix_pair(w.As[0], w.As[1], "compressed")
     else:
         w.As = [A]
         w.bound_entries = asm.bind_matrix(A)
@@ -363,7 +362,7 @@ def prepare_matrices(w):
     torch.cuda.synchronize()
 
 
-PAIR = False
+PAIR = True
 
 
 def next_matrix(w):
@@ -403,7 +402,21 @@ def parity_check(w, device, world, dist, nodes_per_rank=4):
     # idempotent in the Newton loop); for the comparison with the unconstrained oracle, A is released first: the
     # assembly below then is a full A := A_pre + J_nl
     asm.unbind_matrix()
-    asm.assemble_jacobian(xt, w.x1d, "compressed", w.A)
+    fused = 0
+    if w.pair:
+        # the pair is bound afresh (both matrices = A_pre in every row) and used A0, A1, A0: the second assembly zero-fills
+        # A0 from inside its fluid kernel, the third adds the A_pre non-zeros back while it assembles — the matrix that
+        # is checked went through the fused re-initialisation, with no unit rows written in between
+        asm.bind_matrix_pair(w.As[0], w.As[1], "compressed")
+        f0 = asm.fused_launches()
+        for A in (w.As[0], w.As[1], w.As[0]):
+            asm.assemble_jacobian(xt, w.x1d, "compressed", A)
+        w.A = w.As[0]
+        fused = asm.fused_launches() - f0
+        if fused != 2:
+            raise RuntimeError("parity check: the matrix pair did not take the fused path (%d fused launches)" % fused)
+    else:
+        asm.assemble_jacobian(xt, w.x1d, "compressed", w.A)
     asm.assemble_residual(xt, w.x1d, w.b)
     torch.cuda.synchronize()
     rng = np.random.default_rng(100 + (0 if world == 1 else dist.get_rank()))
@@ -432,6 +445,7 @@ def parity_check(w, device, world, dist, nodes_per_rank=4):
         "max_rel_A": allreduce(errA, mx, device, world, dist),
         "max_rel_b": allreduce(rel_b, mx, device, world, dist),
         "ranks": world,
+        "fused_reinitialisation_checked": bool(fused),
         "rows_checked_per_rank": int(sum(int(space.node_ncomp[n]) for n in picks)),
         "halo_exact": bool(allreduce(0.0 if halo_exact else 1.0, mx, device, world, dist) == 0.0),
         "tolerance": 1e-12,
@@ -481,10 +495,10 @@ def measure(w, args, device, world, dist, local_rank, steps, warmup, full=True):
     gd = torch.zeros(len(w.bc), dtype=torch.float64, device=device)
     out["ms_res"] = timed(lambda: asm.assemble_residual(w.xd, w.x1d, w.b))
     # the same step with the masked re-initialisation in the FOREGROUND (what a single bound matrix costs)
-    os.environ["TFSI_NO_BACKGROUND_INIT"] = "1"
+    os.environ["TFSI_NO_FUSED_INIT"] = "1"
     asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A)
     t_both = timed(lambda: asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A))          # foreground init + kernels
-    del os.environ["TFSI_NO_BACKGROUND_INIT"]
+    del os.environ["TFSI_NO_FUSED_INIT"]
     out["ms_step_foreground_init"] = t_both
     out["ms_init"] = t_both - out["kf_ms"] - out["ks_ms"]
     out["ms_ident"] = timed(lambda: asm.ident_zeros(w.A))
@@ -591,15 +605,17 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong: skip the additional weak-scaling measurement")
     ap.add_argument("--sweep", default="", help="comma-separated ncube list: config 5 size sweep (per-GPU sizes, weak)")
     ap.add_argument("--deterministic", action="store_true", help="colour-ordered scatter (bitwise reproducible)")
-    ap.add_argument("--pair", action="store_true",
-                    help="experimental: two persistent matrices, the idle one re-initialised in the background under the "
-                         "Jacobian kernels (tfsi_bind_matrix_pair; pays only for >= 2 M tets on an otherwise idle GPU)")
+    ap.add_argument("--no-pair", action="store_true",
+                    help="ONE persistent matrix re-initialised by a separate masked A := A_pre pass before every assembly, "
+                         "instead of the default matrix pair (tfsi_bind_matrix_pair: the idle matrix is re-initialised by "
+                         "the fluid kernel of the running assembly); the pair needs a second matrix in HBM and is "
+                         "dropped automatically when it does not fit")
     ap.add_argument("--newton", type=int, default=int(os.environ.get("TFSI_BENCH_NEWTON_NCUBE", "6")),
                     help="ncube of the 3-D tube on which one full Newton step (with the device LU) is timed; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     global PAIR
-    PAIR = args.pair
+    PAIR = not args.no_pair and not args.deterministic
 
     if args.impl == "reference":
         run_reference(args)

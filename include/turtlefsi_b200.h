@@ -183,16 +183,18 @@ int tfsi_invalidate_A_pre(tfsi_handle* h);
  * make the next assembly a full one. */
 int tfsi_bind_matrix(tfsi_handle* h, double* A_vals, void* stream);
 /* The same with TWO buffers that the caller alternates between re-assemblies (the previous Jacobian is dead once the
- * next one is assembled): while tfsi_assemble_jacobian(..., A_k) runs its FP64-bound kernel over the fluid cells, the
- * rows of the OTHER buffer are re-initialised in the background (lowest-priority stream, a 32-register masked copy
- * from the DENSE A_pre — `Apre_vals`, the array registered by tfsi_compress_A_pre, which must stay valid and unchanged —
- * that fits beside the Jacobian CTAs), so that the next assembly into it starts without any initialisation pass. The caller must
- * be done with the other buffer (stream-ordered on `stream`) when it calls tfsi_assemble_jacobian. Costs a second
- * matrix in HBM; any other order of use stays correct (the missing initialisation is then done in the foreground). */
+ * next one is assembled). While tfsi_assemble_jacobian(..., A_k) runs, the rows of the OTHER buffer that the cell
+ * kernels scatter into are re-initialised BY THE FLUID KERNEL ITSELF, between its tasks: zero-fill with TMA bulk stores
+ * (shared -> global from a zero block), and the A_pre non-zeros of those runs are added with REDs by the fluid kernel
+ * of the next assembly into that buffer. The separate HBM-bound pass A := A_pre of the single-buffer mode (18 % of the
+ * step at 2 M tets) disappears into the FP64-bound kernel. `Apre_vals`: the array registered by tfsi_compress_A_pre or
+ * TFSI_APRE_COMPRESSED. The caller must be done with the other buffer (stream-ordered on `stream`) when it calls
+ * tfsi_assemble_jacobian. Costs a second matrix in HBM plus 16 B per A_pre non-zero in the rewritten rows; any other
+ * order of use, a problem without fluid cells or the deterministic mode stay correct (foreground initialisation). */
 int tfsi_bind_matrix_pair(tfsi_handle* h, double* A0_vals, double* A1_vals, const double* Apre_vals, void* stream);
 int tfsi_unbind_matrix(tfsi_handle* h);
-/* statistics: blocks of the background kernel that ran on each SM since the last call (out256[smid]); synchronises */
-int tfsi_debug_bg_placement(tfsi_handle* h, int32_t* out256);
+/* number of fluid launches that carried re-initialisation work for a matrix pair so far (reporting, tests) */
+int64_t tfsi_fused_launches(const tfsi_handle* h);
 /* entries rewritten by an assembly into the bound matrix (reporting) */
 int64_t tfsi_bound_init_entries(const tfsi_handle* h);
 

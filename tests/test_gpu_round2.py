@@ -77,10 +77,11 @@ def test_bound_matrix_partial_init_and_sentinel(tube_params):
     assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), asm.rowptr.cpu().numpy()) < 1e-14
 
 
-def test_matrix_pair_background_initialisation(tube_params):
-    """tfsi_bind_matrix_pair: two persistent matrices used alternately, the idle one re-initialised in the background
-    under the Jacobian kernels. Every assembly (also out-of-order use of the pair, and with ident_zeros / BC rows in
-    between) must give the matrix of the plain path."""
+def test_matrix_pair_fused_reinitialisation(tube_params):
+    """tfsi_bind_matrix_pair: two persistent matrices used alternately, the idle one re-initialised by the fluid kernel
+    of the running assembly (TMA zero-fill between its tasks; the A_pre non-zeros added back by REDs at the next assembly).
+    Every assembly (also out-of-order use of the pair, and with ident_zeros / BC rows in between) must give the matrix
+    of the plain path."""
     import torch
     from turtlefsi_b200.assembler import FSIAssembler
     common, regions = tube_params
@@ -92,9 +93,10 @@ def test_matrix_pair_background_initialisation(tube_params):
     A_pre = asm.assemble_A_pre(xd, x1d)
     asm.compress_A_pre(A_pre)
     A0, A1 = asm.new_matrix(), asm.new_matrix()
-    asm.bind_matrix_pair(A0, A1, A_pre)
+    asm.bind_matrix_pair(A0, A1, "compressed")
     rp = asm.rowptr.cpu().numpy()
     order = [A0, A1, A0, A1, A1, A0, A0, A1, A0]              # regular alternation, then repeats (foreground fallback)
+    fused_before = asm.fused_launches()
     for it, A in enumerate(order):
         xi = xd + 1e-3 * (it + 1) * torch.cos(torch.arange(space.num_dofs, device="cuda", dtype=torch.float64))
         asm.assemble_jacobian(xi, x1d, "compressed", A)
@@ -105,6 +107,7 @@ def test_matrix_pair_background_initialisation(tube_params):
         asm.apply_bc_matrix(ref)
         torch.cuda.synchronize()
         assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), rp) < 1e-14, it
+    assert asm.fused_launches() - fused_before >= 5          # the alternating part did take the fused path
     # split call (halo overlap): phase 1 then phase 2
     A = A1 if order[-1] is A0 else A0
     asm.assemble_jacobian(None, None, "compressed", A, phase=1)

@@ -231,18 +231,18 @@ class FSIAssembler:
         self._bound = A            # keep the tensor alive: the handle holds its address
         return int(self.lib.tfsi_bound_init_entries(self.h))
 
-    def bind_matrix_pair(self, A0, A1, A_pre):
-        """two persistent matrices used alternately: the one not being assembled is re-initialised in the background
-        under the Jacobian kernels (tfsi_bind_matrix_pair). A_pre: the dense array given to compress_A_pre."""
-        self._check(self.lib.tfsi_bind_matrix_pair(self.h, _ptr(A0), _ptr(A1), _ptr(A_pre), self._stream()))
-        self._bound = (A0, A1, A_pre)
+    def bind_matrix_pair(self, A0, A1, A_pre="compressed"):
+        """two persistent matrices used alternately: the rows of the one not being assembled are re-initialised by the
+        fluid kernel of the running assembly itself (tfsi_bind_matrix_pair). A_pre: the array given to compress_A_pre,
+        or "compressed" once that array has been freed."""
+        ap = C.c_void_p(_lib.APRE_COMPRESSED) if isinstance(A_pre, str) else _ptr(A_pre)
+        self._check(self.lib.tfsi_bind_matrix_pair(self.h, _ptr(A0), _ptr(A1), ap, self._stream()))
+        self._bound = (A0, A1)
         return int(self.lib.tfsi_bound_init_entries(self.h))
 
-    def bg_placement(self):
-        """blocks of the background kernel per SM since the last call (debug statistics)."""
-        out = np.zeros(256, dtype=np.int32)
-        self._check(self.lib.tfsi_debug_bg_placement(self.h, C.c_void_p(out.ctypes.data)))
-        return out
+    def fused_launches(self):
+        """fluid launches that carried re-initialisation work for the matrix pair so far."""
+        return int(self.lib.tfsi_fused_launches(self.h))
 
     def unbind_matrix(self):
         self._check(self.lib.tfsi_unbind_matrix(self.h))

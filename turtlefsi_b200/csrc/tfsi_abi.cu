@@ -30,6 +30,9 @@ struct Region {
     int32_t* dofs_blk;    // device, per CTA batch
     int32_t* res_dofs_blk; // device, per residual CTA batch: [ndof][res_nc]
     size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
+    double* massJ;        // pair mode, fluid: frozen mass factors [batch][q][NC] (tfsi_assemble_A_pre)
+    uint16_t* rank_blk_v; // pair mode, solid: ranks of the velocity columns per CTA batch (tfsi_bind_matrix_pair)
+    size_t rank_v_elems;
 };
 
 }  // namespace
@@ -72,11 +75,16 @@ struct tfsi_handle {
     struct Bound { double* A; int state; int pending; cudaEvent_t ready; } bound[2];
     int nbound;
     uint32_t* tmask; int64_t bound_entries;
-    cudaStream_t bg_stream, hi_stream;        // pair mode: background initialisation (lowest priority) / cell kernels (highest)
-    cudaEvent_t ev_fork, ev_join;
-    int64_t bg_launches;
-    const double* pair_apre;                  // dense A_pre the background copy reads (pair mode)
-    int* bg_smid;                             // blocks of the background kernel per SM (debug statistics)
+    // pair mode (tfsi_bind_matrix_pair): the re-initialisation of the idle matrix is FUSED into the cell kernels — the
+    // rows J_nl scatters into are zero-filled by the fluid kernel of the current assembly (TMA bulk stores from a zero
+    // block), and the A_pre part of those rows (mass blocks of fluid.py:33 / solid.py:41, facet operators) is added by
+    // the kernels of the next assembly into that matrix
+    FillPiece* fill_pieces; int64_t n_fill;
+    int64_t* fill_scalar; int64_t n_fill_scalar;
+    uint8_t* row_flag;                        // rows J_nl scatters into
+    const double* apre_last; double apre_sumsq;   // array written by the last tfsi_assemble_A_pre and its sum of squares
+    int apre_own;                             // the compressed A_pre is that array (pair mode relies on its structure)
+    int64_t fused_launches;                   // fluid launches that carried fill / fix-up work (tests, bench)
     int suppress_bg;                          // host entry: A := A_pre already runs under the H2D copy
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
@@ -130,6 +138,16 @@ int bind_tables(tfsi_handle* h, cudaStream_t st) {
     if (owner != 0) CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpyToSymbolAsync(c_tabJ, &h->tabJ, sizeof h->tabJ, 0, cudaMemcpyHostToDevice, st));
     CK(h, cudaMemcpyToSymbolAsync(c_tabR, &h->tabR, sizeof h->tabR, 0, cudaMemcpyHostToDevice, st));
+    {   // P2 reference mass matrix of the Jacobian rule (mass block of the solid kernel in pair mode)
+        static thread_local double m2[10][10];
+        for (int i = 0; i < 10; ++i)
+            for (int j = 0; j < 10; ++j) {
+                double z = 0.0;
+                for (int q = 0; q < h->tabJ.nq; ++q) z = fma(h->tabJ.phi2[q][i], h->tabJ.w[q] * h->tabJ.phi2[q][j], z);
+                m2[i][j] = z;
+            }
+        CK(h, cudaMemcpyToSymbolAsync(c_mass2, m2, sizeof m2, 0, cudaMemcpyHostToDevice, st));
+    }
     owner = h->id;
     return 0;
 }
@@ -139,6 +157,8 @@ CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* 
     a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
     a.colidx = h->colidx; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.rank_blk = r.rank_blk; a.dofs_blk = r.dofs_blk;
     a.ncell_region = r.ncells; a.ndof = h->ndof; a.q0 = 0; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
+    a.fill_pieces = nullptr; a.n_fill = 0; a.fill_scalar = nullptr; a.n_fill_scalar = 0; a.fill_dst = nullptr;
+    a.massJ = nullptr; a.rank_v = nullptr;
     return a;
 }
 
@@ -164,11 +184,19 @@ template <class SM> int max_points(int nq) {
 
 // J_nl of one region: one launch per chunk of the quadrature rule (the REDs of the chunks add up). The rule of the
 // headline config (Keast 14-point, 3-D) runs in one launch of the compile-time-sized instantiation.
+// what ONE fluid launch of an assembly carries for the matrix pair (see CellArgs)
+struct FusedWork { double* fill_dst; bool zeroed; bool used; };
+
 template <int G>
-int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, const double* x1, double* A, cudaStream_t st) {
+int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, const double* x1, double* A, cudaStream_t st,
+                           FusedWork* fw = nullptr) {
     const int nq = h->tabJ.nq;
     CellArgs a = cell_args(h, r, nq, x, x1, A);
     const bool is_fluid = r.rc.kind == TFSI_KIND_FLUID;
+    if (fw && fw->zeroed && !getenv("TFSI_EXP_NOMASS")) {   // the matrix holds zeros in the rows J_nl scatters into: + the A_pre part
+        if (is_fluid) a.massJ = r.massJ;
+        else a.rank_v = r.rank_blk_v;
+    }
     const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
     const int grid = (int)((r.ncells + ncta - 1) / ncta);
     const bool energy = !is_fluid && r.rc.mat != MAT_SVK;        // energy-based solid model: tangent-table variant
@@ -180,9 +208,21 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
         a.nq = (int)((int64_t)nq * (c + 1) / nchunk) - a.q0;           // balanced chunks, each <= chunk
         KernelTimer kt(h, is_fluid ? 0 : 1, st);
         if (is_fluid) {
-            const size_t smem = FluidJac<G>::SM::bytes(a.nq);
+            size_t smem = FluidJac<G>::SM::bytes(a.nq);
             if (smem > 227 * 1024)
                 return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
+            a.fill_dst = nullptr;
+            if (fw && !fw->used && fw->fill_dst) {
+                if (FluidJac<G>::SM::bytes_with_zero(a.nq) > 227 * 1024)
+                    return fail(h, TFSI_ERR_UNSUPPORTED, "internal: fused re-initialisation does not fit beside %d points", a.nq);
+                smem = FluidJac<G>::SM::bytes_with_zero(a.nq);
+                a.fill_dst = fw->fill_dst; a.fill_pieces = h->fill_pieces; a.n_fill = h->n_fill;
+                a.fill_scalar = h->fill_scalar; a.n_fill_scalar = h->n_fill_scalar;
+                if (getenv("TFSI_EXP_NOSCALAR")) a.n_fill_scalar = 0;          // timing experiments (wrong results)
+                if (getenv("TFSI_EXP_NOPIECES")) a.n_fill = 0;
+                fw->used = true;
+                h->fused_launches++;
+            }
             if (G == 3 && nq == 14) {
                 CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 jac_fluid_kernel<G, 14><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
@@ -195,7 +235,8 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
             CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             jac_solid_kernel<G, 0, 1><<<grid, SolidJac<G, 1>::THREADS, smem, st>>>(a);
         } else {
-            const size_t smem = SolidJac<G>::SM::bytes(a.nq);
+            if (c > 0) a.rank_v = nullptr;                       // the mass block goes with the first chunk only
+            const size_t smem = a.rank_v ? SolidJac<G>::SM::bytes_with_rank_v(a.nq) : SolidJac<G>::SM::bytes(a.nq);
             if (G == 3 && nq == 14) {
                 CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
@@ -231,10 +272,11 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
     return 0;
 }
 
-// A := (A_pre | 0) + J_nl.
-// phase 0: everything; 1: only the x-independent initialisation A := A_pre; 2: only the cell kernels
-// (the host entry runs phase 1 under the H2D copy of x)
-enum { BOUND_CLEAN = 0, BOUND_USED = 1, BOUND_STALE = 2 };
+// state of a bound matrix. CLEAN: holds A_pre in every row an assembly scatters into (nothing to do); ZEROED (pair
+// mode): the runs the cell kernels scatter into were zero-filled during the previous assembly, the A_pre part of
+// them is added by this assembly's cell kernels themselves; USED: assembled into (masked re-initialisation needed); STALE: full
+// initialisation needed
+enum { BOUND_CLEAN = 0, BOUND_ZEROED = 1, BOUND_USED = 2, BOUND_STALE = 3 };
 
 int find_bound(const tfsi_handle* h, const double* A) {
     for (int i = 0; i < h->nbound; ++i) if (h->bound[i].A == A) return i;
@@ -244,20 +286,45 @@ void mark_bound(tfsi_handle* h, int state) {          // A_pre / BC set changed:
     for (int i = 0; i < h->nbound; ++i) h->bound[i].state = std::max(h->bound[i].state, state);
 }
 
+// the first fluid launch of an assembly can carry the fused work: an active fluid region whose first quadrature chunk
+// leaves room for the zero block, and no colour-ordered (deterministic) scatter
+bool fused_possible(const tfsi_handle* h) {
+    if (!h->fill_pieces || !h->apre_own || h->ncolours > 0 || getenv("TFSI_NO_FUSED_INIT")) return false;
+    bool fluid = false;
+    for (const Region& r : h->regions) {
+        if (r.ncells == 0) continue;
+        if (r.rc.kind == TFSI_KIND_FLUID) {
+            if (!r.rc.fluid_on) continue;
+            if (!r.massJ) return false;
+            fluid = true;
+        } else if (r.rc.solid_on && (!r.rank_blk_v || r.rc.visco == 2)) return false;     // "Form2" has a block in A_pre
+    }
+    if (!fluid) return false;
+    const int nq = h->tabJ.nq;
+    if (h->gdim == 3) {
+        const int chunk = max_points<FluidJac<3>::SM>(nq), nchunk = (nq + chunk - 1) / chunk;
+        return FluidJac<3>::SM::bytes_with_zero(nq / nchunk) <= 227 * 1024;
+    }
+    const int chunk = max_points<FluidJac<2>::SM>(nq), nchunk = (nq + chunk - 1) / chunk;
+    return FluidJac<2>::SM::bytes_with_zero(nq / nchunk) <= 227 * 1024;
+}
+
+// A := (A_pre | 0) + J_nl.
+// phase 0: everything; 1: only the x-independent initialisation A := A_pre; 2: only the cell kernels
+// (the host entry runs phase 1 under the H2D copy of x)
 int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const double* Apre, double* A, cudaStream_t st, int phase = 0) {
     if (Apre == TFSI_APRE_COMPRESSED && !h->cpre_bitmap)
         return fail(h, TFSI_ERR_ARG, "TFSI_APRE_COMPRESSED given but no compressed A_pre is registered (tfsi_compress_A_pre)");
     const bool use_compressed = h->cpre_bitmap && Apre && (Apre == TFSI_APRE_COMPRESSED || Apre == h->cpre_src);
     const int slot = find_bound(h, A);
     const int64_t ngroups = (h->cpre_words + 31) / 32;
+    const bool can_fuse = use_compressed && slot >= 0 && h->nbound == 2 && fused_possible(h);
+    if (slot >= 0 && h->bound[slot].state == BOUND_ZEROED && !can_fuse) h->bound[slot].state = BOUND_STALE;
+    bool zeroed = false;
     if (phase != 2) {
-        if (slot >= 0 && h->bound[slot].pending) {     // initialised in the background during the previous assembly
-            CK(h, cudaStreamWaitEvent(st, h->bound[slot].ready, 0));
-            h->bound[slot].pending = 0;
-        }
         // A := A_pre streamed ONCE from the bitmap-compressed copy (zero-fill + packed non-zeros); into a bound matrix
         // only the rows that the cell kernels scatter into are rewritten, and nothing at all when it is still CLEAN
-        if (use_compressed && slot >= 0 && h->bound[slot].state == BOUND_CLEAN) {
+        if (use_compressed && slot >= 0 && (h->bound[slot].state == BOUND_CLEAN || h->bound[slot].state == BOUND_ZEROED)) {
             ;
         } else if (use_compressed) {
             const bool partial = slot >= 0 && h->tmask && h->bound[slot].state == BOUND_USED;
@@ -274,42 +341,28 @@ int launch_jacobian(tfsi_handle* h, const double* x, const double* x1, const dou
         }
     }
     if (phase == 1) return 0;
-    if (slot >= 0) h->bound[slot].state = (h->bound[slot].state == BOUND_CLEAN) ? BOUND_USED : BOUND_STALE;
-    // pair mode: the OTHER matrix of the pair is re-initialised in the background, under the FP64-bound kernel over
-    // the fluid cells (lowest-priority stream; the cell kernels move to a highest-priority stream so that the block
-    // scheduler always prefers them and the background blocks only fill the registers they leave free)
-    const int other = (slot >= 0 && h->nbound == 2) ? 1 - slot : -1;
-    const bool bg = other >= 0 && use_compressed && h->tmask && h->pair_apre && h->bound[other].state == BOUND_USED && !h->bound[other].pending &&
-                    !h->suppress_bg && !getenv("TFSI_NO_BACKGROUND_INIT");
-    cudaStream_t ks = st;
-    if (bg) {
-        CK(h, cudaEventRecord(h->ev_fork, st));
-        CK(h, cudaStreamWaitEvent(h->hi_stream, h->ev_fork, 0));
-        CK(h, cudaStreamWaitEvent(h->bg_stream, h->ev_fork, 0));
-        ks = h->hi_stream;
+    if (slot >= 0) {
+        zeroed = h->bound[slot].state == BOUND_ZEROED;
+        h->bound[slot].state = (h->bound[slot].state == BOUND_CLEAN || h->bound[slot].state == BOUND_ZEROED) ? BOUND_USED : BOUND_STALE;
     }
-    bool kicked = false;
+    // pair mode: the OTHER matrix of the pair is zero-filled by this assembly's fluid launch, under its FP64 loops
+    const int other = (slot >= 0 && h->nbound == 2) ? 1 - slot : -1;
+    FusedWork fw;
+    fw.fill_dst = (can_fuse && other >= 0 && h->bound[other].state == BOUND_USED && !h->suppress_bg) ? h->bound[other].A : nullptr;
+    fw.zeroed = zeroed;
+    fw.used = false;
     for (const Region& r : h->regions) {
         if (r.ncells == 0) continue;
         if (r.rc.kind == TFSI_KIND_FLUID ? !r.rc.fluid_on : !r.rc.solid_on) continue;
-        if (bg && !kicked) {
-            if (getenv("TFSI_BG_STATS"))
-                masked_copy_bg_kernel<true><<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, h->bg_smid);
-            else
-                masked_copy_bg_kernel<false><<<h->sm_count, 128, 0, h->bg_stream>>>(h->tmask, ngroups, h->nnz, h->pair_apre, h->bound[other].A, nullptr);
-            CK(h, cudaGetLastError());
-            CK(h, cudaEventRecord(h->bound[other].ready, h->bg_stream));
-            h->bound[other].state = BOUND_CLEAN;
-            h->bound[other].pending = 1;
-            h->launches++; h->bg_launches++;
-            kicked = true;
-        }
-        int rc = h->gdim == 3 ? launch_jacobian_region<3>(h, r, x, x1, A, ks) : launch_jacobian_region<2>(h, r, x, x1, A, ks);
+        int rc = h->gdim == 3 ? launch_jacobian_region<3>(h, r, x, x1, A, st, &fw) : launch_jacobian_region<2>(h, r, x, x1, A, st, &fw);
         if (rc) return rc;
     }
-    if (bg) {
-        CK(h, cudaEventRecord(h->ev_join, h->hi_stream));
-        CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    if (fw.fill_dst && !fw.used) return fail(h, TFSI_ERR_UNSUPPORTED, "internal: no fluid launch carried the fused re-initialisation");
+    if (fw.fill_dst) h->bound[other].state = BOUND_ZEROED;
+    if (zeroed && h->fo_n) {                 // facet-operator part of A_pre in the zero-filled rows
+        coo_add_flagged_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_pos, h->fo_vals, h->fo_rows, h->row_flag, h->fo_n, A);
+        h->launches++;
+        CK(h, cudaGetLastError());
     }
     return 0;
 }
@@ -451,13 +504,9 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->fo_rows); cudaFree(h->fo_cols); cudaFree(h->fo_pos); cudaFree(h->fo_vals);
     cudaFree(h->fp_rows); cudaFree(h->fp_cols); cudaFree(h->fp_vals); cudaFree(h->fl_dofs); cudaFree(h->fl_vals);
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val); cudaFree(h->tmask);
-    cudaFree(h->bg_smid);
-    if (h->bg_stream) cudaStreamDestroy(h->bg_stream);
-    if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    cudaFree(h->fill_pieces); cudaFree(h->fill_scalar); cudaFree(h->row_flag);
     for (auto& b : h->bound) if (b.ready) cudaEventDestroy(b.ready);
-    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); }
+    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
@@ -525,9 +574,10 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->fp_rows = h->fp_cols = nullptr; h->fp_vals = nullptr; h->fp_n = 0;
     h->fl_dofs = nullptr; h->fl_vals = nullptr; h->fl_n = 0; h->fl_scale = 1.0;
     h->cpre_src = nullptr; h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
-    h->nbound = 0; h->tmask = nullptr; h->bound_entries = 0; h->bg_launches = 0;
+    h->nbound = 0; h->tmask = nullptr; h->bound_entries = 0; h->fused_launches = 0;
     for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; b.ready = nullptr; }
-    h->bg_stream = h->hi_stream = nullptr; h->ev_fork = h->ev_join = nullptr; h->pair_apre = nullptr; h->bg_smid = nullptr; h->suppress_bg = 0;
+    h->fill_pieces = nullptr; h->fill_scalar = nullptr; h->n_fill = h->n_fill_scalar = 0; h->row_flag = nullptr; h->suppress_bg = 0;
+    h->apre_last = nullptr; h->apre_sumsq = 0.0; h->apre_own = 0;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     if (h->ext < 0 || h->ext > TFSI_EXT_ELASTIC) { delete h; return fail(nullptr, TFSI_ERR_ARG, "unknown extrapolation code %d", h->ext); }
@@ -600,6 +650,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
                 set_solid_model(r.rc, rg.material, rg.C01, rg.C10, rg.C11, rg.Jm, rg.viscoelasticity, rg.mu_visc, rg.lambda_visc);
             }
             r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
+            r.massJ = nullptr; r.rank_blk_v = nullptr; r.rank_v_elems = 0;
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
             if (!p->deterministic) {
@@ -722,6 +773,22 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
         h->launches++;
         CK(h, cudaGetLastError());
     }
+    // pair mode (tfsi_bind_matrix_pair): the frozen mass factors of fluid.py:33 at THIS state, so that the fluid kernel can
+    // add that part of A_pre itself into a zero-filled matrix; and the sum of squares of what was written, by which
+    // tfsi_compress_A_pre recognises the array
+    for (Region& r : h->regions) {
+        if (r.ncells == 0 || r.rc.kind != TFSI_KIND_FLUID || !r.rc.fluid_on) continue;
+        const int ncta = h->gdim == 3 ? FluidCfg<3>::L::NC : FluidCfg<2>::L::NC;
+        const int64_t total = (r.ncells + ncta - 1) / ncta * ncta * h->tabJ.nq;
+        if (!r.massJ) CK(h, cudaMalloc((void**)&r.massJ, (size_t)total * sizeof(double)));
+        CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, nullptr);
+        if (h->gdim == 3) mass_factor_kernel<3><<<grid_for(total, 128, h->sm_count), 128, 0, st>>>(a, ncta, r.rc.c1lin, r.massJ);
+        else mass_factor_kernel<2><<<grid_for(total, 128, h->sm_count), 128, 0, st>>>(a, ncta, r.rc.c1lin, r.massJ);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (int rc = tfsi_sumsq(h, Apre, h->nnz, &h->apre_sumsq, stream)) return rc;
+    h->apre_last = Apre;
     return 0;
 }
 
@@ -807,7 +874,7 @@ int tfsi_invalidate_A_pre(tfsi_handle* h) {
     h->cpre_bitmap = nullptr; h->cpre_base = nullptr; h->cpre_val = nullptr; h->cpre_nnz = 0; h->cpre_words = 0;
     mark_bound(h, BOUND_STALE);
     for (auto& b : h->bound) b.pending = 0;
-    h->pair_apre = nullptr;                   // the background copy must not read a dense A_pre that is being edited
+    h->apre_own = 0;
     return 0;
 }
 
@@ -841,6 +908,10 @@ int tfsi_compress_A_pre(tfsi_handle* h, const double* Apre, void* stream) {
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(st));
     h->cpre_src = Apre;
+    // is this the array tfsi_assemble_A_pre wrote (same address, same sum of squares up to the summation order)?
+    double ss = 0.0;
+    if (int rc = tfsi_sumsq(h, Apre, h->nnz, &ss, stream)) return rc;
+    h->apre_own = Apre == h->apre_last && fabs(ss - h->apre_sumsq) <= 1e-9 * h->apre_sumsq;
     return 0;
 }
 
@@ -871,7 +942,7 @@ int build_touched_mask(tfsi_handle* h, cudaStream_t st) {
     unsigned long long pairs = 0;
     CK(h, cudaMemcpyAsync(&pairs, cnt, sizeof pairs, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
-    cudaFree(flag);
+    h->row_flag = flag;
     h->bound_entries = std::min<int64_t>((int64_t)pairs * 64, h->nnz);
     return 0;
 }
@@ -895,53 +966,98 @@ int tfsi_bind_matrix(tfsi_handle* h, double* A, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = build_touched_mask(h, st)) return rc;
     CK(h, cudaDeviceSynchronize());                       // a background initialisation of an earlier pair may be in flight
-    h->nbound = 1; h->bound[1].A = nullptr; h->pair_apre = nullptr;
+    h->nbound = 1; h->bound[1].A = nullptr;
     return bind_one(h, 0, A, st);
 }
 
-int tfsi_bind_matrix_pair(tfsi_handle* h, double* A0, double* A1, const double* Apre_dense, void* stream) {
+namespace {
+// pair mode set-up: (1) the zero-fill lists = the entries of every maximal run of rows J_nl scatters into, as 16-byte
+// aligned pieces of <= 4 KB for the TMA bulk stores plus the odd entries at the ends of the runs (host pass over the
+// row pointers), (2) the scatter ranks of the velocity columns of the solid regions (mass block).
+int build_fused_lists(tfsi_handle* h, cudaStream_t st) {
+    if (!h->fill_pieces) {
+        std::vector<int64_t> rp((size_t)h->N + 1);
+        std::vector<uint8_t> fl((size_t)h->N);
+        CK(h, cudaMemcpyAsync(rp.data(), h->rowptr, rp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaMemcpyAsync(fl.data(), h->row_flag, fl.size(), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        std::vector<FillPiece> pieces;
+        std::vector<int64_t> scalars;
+        const int64_t step = FILL_BLOCK / 8;
+        int64_t r = 0;
+        while (r < h->N) {
+            if (!fl[(size_t)r]) { ++r; continue; }
+            int64_t r1 = r;
+            while (r1 < h->N && fl[(size_t)r1]) ++r1;
+            int64_t e0 = rp[(size_t)r], e1 = rp[(size_t)r1];
+            if (e0 < e1 && (e0 & 1)) scalars.push_back(e0++);
+            if (e0 < e1 && (e1 & 1)) scalars.push_back(--e1);
+            for (int64_t e = e0; e < e1; e += step) {
+                FillPiece pc; pc.entry = e; pc.nbytes = (int32_t)(std::min(step, e1 - e) * 8); pc.pad_ = 0;
+                pieces.push_back(pc);
+            }
+            r = r1;
+        }
+        h->n_fill = (int64_t)pieces.size();
+        h->n_fill_scalar = (int64_t)scalars.size();
+        CK(h, cudaMalloc((void**)&h->fill_pieces, std::max<size_t>(pieces.size(), 1) * sizeof(FillPiece)));
+        CK(h, cudaMalloc((void**)&h->fill_scalar, std::max<size_t>(scalars.size(), 1) * sizeof(int64_t)));
+        if (!pieces.empty()) CK(h, cudaMemcpy(h->fill_pieces, pieces.data(), pieces.size() * sizeof(FillPiece), cudaMemcpyHostToDevice));
+        if (!scalars.empty()) CK(h, cudaMemcpy(h->fill_scalar, scalars.data(), scalars.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    int* derr = reinterpret_cast<int*>(h->scratch + 1);
+    for (Region& r : h->regions) {
+        if (r.ncells == 0 || r.rc.kind != TFSI_KIND_SOLID || !r.rc.solid_on || r.rank_blk_v) continue;
+        if (!h->colidx) return 0;            // column array released: the pair stays correct through the foreground path
+        const int ncta = h->gdim == 3 ? SolidCfg<3>::L::NC : SolidCfg<2>::L::NC, rks = ncta + 1, ncols = h->gdim * h->n2;
+        const size_t rbytes = ((size_t)h->n2 * ncols * rks * sizeof(uint16_t) + 15) / 16 * 16;
+        const int64_t nb = (r.ncells + ncta - 1) / ncta;
+        r.rank_v_elems = rbytes / sizeof(uint16_t);
+        CK(h, cudaMalloc((void**)&r.rank_blk_v, (size_t)nb * rbytes));
+        CK(h, cudaMemsetAsync(r.rank_blk_v, 0, (size_t)nb * rbytes, st));
+        CK(h, cudaMemsetAsync(derr, 0, sizeof(int), st));
+        build_rank_blocked_kernel<<<grid_for(nb * h->n2 * ncols * ncta, 256, h->sm_count), 256, 0, st>>>(
+            h->cell_dofs, h->rowptr, h->colidx, r.cell_list, r.ncells, h->ndof, h->n2, ncols, ncta, rks, r.rank_v_elems,
+            r.rank_blk_v, derr, ncols);
+        int herr = 0;
+        CK(h, cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        if (herr) return fail(h, TFSI_ERR_PATTERN, "%d velocity-column ranks of a solid region are missing from the CSR pattern", herr);
+    }
+    return 0;
+}
+}  // namespace
+
+// Two persistent matrices used alternately (A0 in one assembly, A1 in the next): the rows of the idle one that the
+// cell kernels scatter into are zero-filled DURING the assembly into the other, by the fluid kernel itself (TMA bulk
+// stores between its tasks); the A_pre part of those rows — the mass blocks of fluid.py:33 and solid.py:41, registered
+// facet operators — is added by the cell kernels of the next assembly into that matrix. This needs A_pre to be what
+// tfsi_assemble_A_pre wrote (checked by address and sum of squares at tfsi_compress_A_pre); with any other A_pre, without
+// an active fluid region, with "Form2" viscoelasticity or in the deterministic mode the pair falls back to the
+// foreground masked initialisation. Apre: the array given to tfsi_compress_A_pre, or TFSI_APRE_COMPRESSED.
+int tfsi_bind_matrix_pair(tfsi_handle* h, double* A0, double* A1, const double* Apre, void* stream) {
     if (!h || !A0 || !A1 || A0 == A1) return fail(h, TFSI_ERR_ARG, "two distinct matrices are needed");
-    if (!Apre_dense || Apre_dense != h->cpre_src)
-        return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix_pair needs the dense A_pre that was given to tfsi_compress_A_pre");
     if (!h->cpre_bitmap) return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix_pair needs a compressed A_pre (tfsi_compress_A_pre)");
+    if (!Apre || (Apre != TFSI_APRE_COMPRESSED && Apre != h->cpre_src))
+        return fail(h, TFSI_ERR_ARG, "tfsi_bind_matrix_pair needs the A_pre that was given to tfsi_compress_A_pre (or TFSI_APRE_COMPRESSED)");
     DeviceGuard dg(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = build_touched_mask(h, st)) return rc;
     CK(h, cudaDeviceSynchronize());
-    if (!h->bg_stream) {
-        int least = 0, greatest = 0;
-        CK(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        const char* pe = getenv("TFSI_BG_PRIO");            // experiments: "same" = no priorities
-        if (pe && !strcmp(pe, "same")) greatest = least;
-        // the background copy is ONE persistent block per SM on the HIGHER-priority stream, launched first on the idle
-        // device: the work distributor hands a later grid's blocks out only after those of an earlier / higher one
-        CK(h, cudaStreamCreateWithPriority(&h->bg_stream, cudaStreamNonBlocking, greatest));
-        CK(h, cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, least));
-        CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        CK(h, cudaMalloc((void**)&h->bg_smid, 256 * sizeof(int)));
-        CK(h, cudaMemset(h->bg_smid, 0, 256 * sizeof(int)));
-    }
+    if (int rc = build_fused_lists(h, st)) return rc;
     h->nbound = 2;
-    h->pair_apre = Apre_dense;
     if (int rc = bind_one(h, 0, A0, st)) return rc;
     return bind_one(h, 1, A1, st);
 }
 
-int tfsi_debug_bg_placement(tfsi_handle* h, int32_t* out256) {
-    if (!h || !out256 || !h->bg_smid) return fail(h, TFSI_ERR_ARG, "no matrix pair bound");
-    DeviceGuard dg(h);
-    CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(out256, h->bg_smid, 256 * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(h, cudaMemset(h->bg_smid, 0, 256 * sizeof(int)));
-    return 0;
-}
+// number of fluid launches that carried re-initialisation work for a matrix pair so far
+int64_t tfsi_fused_launches(const tfsi_handle* h) { return h ? h->fused_launches : -1; }
 
 int tfsi_unbind_matrix(tfsi_handle* h) {
     if (!h) return TFSI_ERR_ARG;
     DeviceGuard dg(h);
     CK(h, cudaDeviceSynchronize());
-    h->nbound = 0; h->pair_apre = nullptr;
+    h->nbound = 0;
     for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; }
     return 0;
 }

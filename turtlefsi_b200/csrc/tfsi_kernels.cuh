@@ -23,6 +23,7 @@ namespace tfsi {
 
 __constant__ QuadTab<MAXQ_J> c_tabJ;
 __constant__ QuadTab<MAXQ_R> c_tabR;
+__constant__ double c_mass2[10][10];      // sum_q w_q phi_i phi_j of the Jacobian rule (P2 reference mass matrix)
 
 constexpr int CELLS_PER_CTA = 32;
 #ifndef TFSI_JAC_WARPS
@@ -30,6 +31,13 @@ constexpr int CELLS_PER_CTA = 32;
 #endif
 #ifndef TFSI_JAC_NGRP
 #define TFSI_JAC_NGRP 3
+#endif
+#ifndef TFSI_SMALL_UNROLL         // quadrature loop of the small tasks of the fluid kernel (fully unrolled it doubles the
+#define TFSI_SMALL_UNROLL 1       // kernel's code size: instruction-cache misses on code that runs once per CTA)
+#endif
+constexpr int SMALL_UNROLL = TFSI_SMALL_UNROLL;
+#ifndef TFSI_TASK_ORDER
+#define TFSI_TASK_ORDER 2
 #endif
 #ifndef TFSI_JAC_CTAS
 #define TFSI_JAC_CTAS 1
@@ -42,6 +50,9 @@ constexpr int JAC_THREADS = JAC_WARPS * 32;
 #endif
 constexpr int RES_WARPS = TFSI_RES_WARPS;
 constexpr int RES_THREADS = RES_WARPS * 32;
+
+struct FillPiece { int64_t entry; int32_t nbytes; int32_t pad_; };   // A[entry .. entry + nbytes/8) := 0, 16-byte aligned
+constexpr int FILL_BLOCK = 4096;                                     // bytes of the zero block (largest bulk store)
 
 struct CellArgs {
     const double* coords;          // [nv][G]
@@ -61,6 +72,17 @@ struct CellArgs {
     const double* x;
     const double* x1;
     double* out;                   // A values or b
+    // fused re-initialisation of a matrix pair (tfsi_bind_matrix_pair).
+    // (1) carried by ONE fluid launch per assembly: zero-fill of the rows of the OTHER matrix that J_nl scatters into
+    const FillPiece* fill_pieces;  // runs of <= 4 KB, 16-byte aligned (TMA bulk stores from a zero block in shared memory)
+    int64_t n_fill;
+    const int64_t* fill_scalar;    // odd entries at the ends of the row runs (plain 8-byte stores)
+    int64_t n_fill_scalar;
+    double* fill_dst;              // null = nothing to fill
+    // (2) assembly INTO a zero-filled matrix: the cell kernels add the A_pre part of those rows themselves
+    const double* massJ;           // fluid: frozen factor of fluid.py:33 per (batch, q, cell slot), see mass_factor_kernel
+    const uint16_t* rank_v;        // solid: scatter ranks of the velocity columns (mass block of solid.py:41), per CTA
+                                   //   batch in the layout of rank_blk
 };
 
 template <int G>
@@ -140,6 +162,9 @@ struct JacSmem {
     static __host__ __device__ size_t off_counter(int nq) { return (off_cell(nq) + (size_t)NC * sizeof(int32_t) + 15) / 16 * 16; }
     static __host__ __device__ size_t off_mbar(int nq) { return off_counter(nq) + 16; }
     static __host__ __device__ size_t bytes(int nq) { return off_mbar(nq) + 16; }
+    static __host__ __device__ size_t off_zero(int nq) { return bytes(nq); }                // fluid kernel, pair mode only
+    static __host__ __device__ size_t bytes_with_zero(int nq) { return off_zero(nq) + FILL_BLOCK; }
+    static __host__ __device__ size_t bytes_with_rank_v(int nq) { return off_zero(nq) + RANK_BYTES; }   // solid kernel, pair mode
     static constexpr size_t DOFS_BLK = (size_t)NCOEF * NC;   // int32 per CTA batch in dofs_blk
 };
 
@@ -175,11 +200,11 @@ __device__ __forceinline__ int64_t find_col(const int32_t* colidx, int64_t lo, i
 // ONE bulk copy) and per-batch copies of the cell dofs (so that the gather of the batch is coalesced).
 // rank(cell, node I, col j) = position of column cell_dofs[cell][col_map(j)] inside the CSR row of the first dof
 // (d_0) living on node I, found by binary search. err[0] counts misses / overflows (> 65535).
-// The batch's trial columns are the local dofs [0, ncols) (fluid: d, v, p; solid: d).
+// The batch's trial columns are the local dofs [col0, col0 + ncols) (fluid: d, v, p; solid: d; solid mass block: v).
 __global__ void build_rank_blocked_kernel(const int32_t* cell_dofs, const int64_t* rowptr, const int32_t* colidx,
                                           const int32_t* cell_list, int64_t ncells, int ndof,
                                           int n2, int ncols, int nc_cta, int rks, size_t blk_elems,
-                                          uint16_t* out, int* err)
+                                          uint16_t* out, int* err, int col0 = 0)
 {
     const int64_t nb = (ncells + nc_cta - 1) / nc_cta;
     const int64_t total = nb * n2 * ncols * nc_cta;
@@ -193,7 +218,7 @@ __global__ void build_rank_blocked_kernel(const int32_t* cell_dofs, const int64_
         if (idx >= ncells) idx = ncells - 1;
         const int64_t cell = cell_list[idx];
         const int32_t row = cell_dofs[cell * ndof + i];
-        const int32_t cj = cell_dofs[cell * ndof + col];
+        const int32_t cj = cell_dofs[cell * ndof + col0 + col];
         const int64_t lo = rowptr[row], hi = rowptr[row + 1];
         const int64_t pos = find_col(colidx, lo, hi, cj);
         uint16_t rk = 0;
@@ -249,6 +274,36 @@ __device__ __forceinline__ void scatter_p2p2(const CellArgs& a, const int64_t* r
             atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * RKS], Z[i][jj]);
 #endif
         }
+    }
+}
+
+// one batch of the fused re-initialisation (called by a whole warp between two tasks): FILL_LANES pieces are zero-filled
+// by bulk stores shared -> global from the zero block (one lane each, asynchronous), 32 single entries by plain stores
+#ifndef TFSI_FILL_LANES
+#define TFSI_FILL_LANES 32        // all pieces of a CTA go out with its first round of task fetches (8: 15.0, 32: 14.0 ms)
+#endif
+constexpr int FILL_LANES = TFSI_FILL_LANES;
+__device__ __forceinline__ void fused_init_batch(const CellArgs& a, int* counter, const double* zbuf, int64_t fill0, int nfill,
+                                                 int64_t sc0, int nsc, int lane)
+{
+    volatile int* vc = counter;
+    if (vc[1] < nfill) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter + 1, FILL_LANES);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < FILL_LANES && base + lane < nfill) {
+            const FillPiece pc = a.fill_pieces[fill0 + base + lane];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(a.fill_dst + pc.entry), "r"(smem_u32(zbuf)), "r"(pc.nbytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (vc[2] < nsc) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter + 2, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + lane < nsc) a.fill_dst[a.fill_scalar[sc0 + base + lane]] = 0.0;
     }
 }
 
@@ -326,6 +381,29 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
     if (threadIdx.x < 16) s_phase_clk[threadIdx.x] = 0;
 #endif
     if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
+    // pair mode (see CellArgs): this CTA's share of the zero-fill pieces and of the fix-up entries, handed out to the
+    // warps in batches whenever they fetch a task (counter[1], counter[2]); the work runs beside the FP64 loops of
+    // the other warps instead of as a separate HBM-bound pass
+    const bool fused = a.fill_dst != nullptr;
+    double* zbuf = reinterpret_cast<double*>(smem_raw + SM::off_zero(nq));
+    int64_t fill0 = 0, sc0 = 0;
+    int nfill = 0, nsc = 0;
+    if (fused) {
+        for (int i = threadIdx.x; i < FILL_BLOCK / 8; i += JAC_THREADS) zbuf[i] = 0.0;
+        fill0 = a.n_fill * blockIdx.x / gridDim.x;
+        nfill = (int)(a.n_fill * (blockIdx.x + 1) / gridDim.x - fill0);
+        sc0 = a.n_fill_scalar * blockIdx.x / gridDim.x;
+        nsc = (int)(a.n_fill_scalar * (blockIdx.x + 1) / gridDim.x - sc0);
+        if (threadIdx.x == 0) { counter[1] = 0; counter[2] = 0; }
+    }
+    // frozen mass factors of this thread's (cell, q) items of phase 0, fetched before the gather so that their
+    // latency is hidden (rounds beyond the second load them in place)
+    double mj0 = 0.0, mj1 = 0.0;
+    if (a.massJ) {
+        const double* mjp = a.massJ + ((size_t)blockIdx.x * c_tabJ.nq + q0) * NC;
+        if ((int)threadIdx.x < nq * NC) mj0 = mjp[threadIdx.x];
+        if ((int)threadIdx.x + JAC_THREADS < nq * NC) mj1 = mjp[threadIdx.x + JAC_THREADS];
+    }
     stage_cells<G, L>(a, scell, sgeo);
     {   // gather of the batch: dofs are pre-blocked [k][cell] (coalesced), the state gathers hit L2
         const int32_t* dblk = a.dofs_blk + (size_t)blockIdx.x * SM::DOFS_BLK;
@@ -369,7 +447,9 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
         auto cf1 = [&](int k) { return coef1[k * NC + c]; };
         double* dstb = base + ((size_t)q * NC + c) * STRIDE;
         auto out = [&](int item, double v) { dstb[item] = v; };
-        fluid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, cf1, out);
+        const double mj = (t < JAC_THREADS) ? mj0 : (t < 2 * JAC_THREADS) ? mj1
+                        : (a.massJ ? a.massJ[((size_t)blockIdx.x * c_tabJ.nq + q0) * NC + t] : 0.0);
+        fluid_base<G>(c_tabJ, q0 + q, K, adet, a.rc, cf, cf1, out, mj);
     }
     PCLK(t_p0done);
     __syncthreads();
@@ -391,12 +471,25 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
 #endif
     for (;;) {
         int t = 0;
+        if (fused) fused_init_batch(a, counter, zbuf, fill0, nfill, sc0, nsc, lane);
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= NTASK) break;
+        // queue order (TFSI_TASK_ORDER): 0 = big tasks then small; 1 = the small tasks FIRST (they run beside the first
+        // big tasks instead of as an underfilled last round: 13.86 -> 13.30 ms); 2 = a third of the small tasks in
+        // front of every third of the big ones
+#if TFSI_TASK_ORDER == 1
+        t = (t < NGRP * 3) ? NBIG + t : t - NGRP * 3;
+#elif TFSI_TASK_ORDER == 2
+        {
+            constexpr int SEG = NBIG / 3 + NGRP;            // NGRP small + NBIG/3 big per segment
+            const int seg = t / SEG, r = t % SEG;
+            t = (r < NGRP) ? NBIG + seg * NGRP + r : seg * (NBIG / 3) + (r - NGRP);
+        }
+#endif
 #ifdef TFSI_PHASE_CLOCKS
         if (t >= NBIG && t_big_end == 0) t_big_end = clock64();
 #endif
-        if (t >= NTASK) break;
         if (t < NBIG) {
             const int grp = t % NGRP, r = t / NGRP;
             // half-major order: the warps that run concurrently execute the same code variant (the two
@@ -423,6 +516,7 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
                 for (int i = 0; i < N2; ++i)
 #pragma unroll
                     for (int m = 0; m < N1; ++m) Z[i][m] = 0.0;
+#pragma unroll SMALL_UNROLL
                 for (int q = 0; q < nq; ++q) {
                     auto bv = [&](int item) { return basec[q * QSTR + item]; };
                     double cc[G];
@@ -446,6 +540,7 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
                 for (int m = 0; m < N1; ++m)
 #pragma unroll
                     for (int j = 0; j < N2; ++j) Z[m][j] = 0.0;
+#pragma unroll SMALL_UNROLL
                 for (int q = 0; q < nq; ++q) {
                     auto bv = [&](int item) { return basec[q * QSTR + item]; };
                     double cc[G];
@@ -465,6 +560,11 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
                 }
             }
         }
+    }
+    if (fused) {      // whatever is left of the CTA's share (short CTAs), then wait for the bulk stores of this thread
+        volatile int* vc = counter;
+        while (vc[1] < nfill || vc[2] < nsc) fused_init_batch(a, counter, zbuf, fill0, nfill, sc0, nsc, lane);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 #ifdef TFSI_PHASE_CLOCKS
     {
@@ -525,13 +625,32 @@ __device__ __forceinline__ void solid_big_task(const CellArgs& a, const double* 
     if (valid) scatter_p2p2<G, typename SolidJac<G, MAT>::L, SolidJac<G, MAT>::NCOEF, HALF>(a, rowst, srank, c, ca * N2, cb * N2, Z);
 }
 
+// mass block psi_b x delta v_b (half the columns) of one cell: rho_s / k |detJgeo| M_ref, scattered with the staged
+// ranks of the velocity columns
+template <int G, class L, int HALF>
+__device__ __forceinline__ void solid_mass_task(const CellArgs& a, const int64_t* rowst, const uint16_t* srank_v, uint64_t* mbar,
+                                                double adet, int c, bool valid, int cb)
+{
+    constexpr int N2 = Dim<G>::N2, NC = L::NC, RKS = L::RKS, NJ = HalfCols<G, HALF>::NJ, NCOLS = G * N2;
+    const double scale = a.rc.rho_s_k * adet;
+    mbar_wait(mbar, 0);
+    if (!valid) return;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        double* dst = a.out + rowst[(cb * N2 + i) * NC + c];
+        const uint16_t* rk = srank_v + ((i * NCOLS) + cb * N2) * RKS + c;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+            atomicAdd(dst + rk[HalfCols<G, HALF>::col(jj) * RKS], scale * c_mass2[i][HalfCols<G, HALF>::col(jj)]);
+    }
+}
+
 template <int G, int NQ, int MAT = 0>
 // 160 registers as the fluid kernel: the background copy keeps running beside the three 4-warp CTAs per SM
 __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
     typedef typename SolidJac<G, MAT>::SM SM;
-    constexpr int NCOEF = SolidJac<G, MAT>::NCOEF;
     typedef typename SolidJac<G, MAT>::L L;
     constexpr int JAC_THREADS = SolidJac<G, MAT>::THREADS;
     constexpr int NC = L::NC, CPW = L::CPW, NGRP = L::NGRP, STRIDE = SM::STRIDE;
@@ -545,6 +664,7 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
     int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + SM::off_cell(nq));
     int* counter = reinterpret_cast<int*>(smem_raw + SM::off_counter(nq));
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + SM::off_mbar(nq));
+    uint16_t* srank_v = reinterpret_cast<uint16_t*>(smem_raw + SM::off_zero(nq));       // pair mode only (a.rank_v)
 
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { *counter = 0; mbar_init(mbar, 1); }
@@ -590,18 +710,30 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(mbar, (uint32_t)SM::RANK_BYTES);
+        mbar_expect_tx(mbar, (uint32_t)(SM::RANK_BYTES * (a.rank_v ? 2 : 1)));
         bulk_g2s(srank, a.rank_blk + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
+        if (a.rank_v) bulk_g2s(srank_v, a.rank_v + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
     }
     const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
     const int lcomp = lane % G;
     const bool lane_on = lane < CPW * G;
     constexpr int NTASK = NGRP * 2 * G;                 // group x a x half ; b = lane
+    // assembly into a zero-filled matrix of a pair: + the mass block psi_b x delta v_b of solid.py:41 (part of A_pre),
+    // rho_s / k |detJgeo| sum_q w_q phi_i phi_j with the Jacobian rule, as lin_jacobian_kernel integrates it
+    const int ntask = NTASK + ((a.rank_v && q0 == 0) ? NGRP * 2 : 0);
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= NTASK) break;
+        if (t >= ntask) break;
+        if (t >= NTASK) {
+            const int grp = (t - NTASK) % NGRP, half = (t - NTASK) / NGRP;
+            const int c = grp * CPW + cw;
+            const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
+            if (half == 0) solid_mass_task<G, L, 0>(a, rowst, srank_v, mbar, sgeo[G * G * NC + c], c, valid, lcomp);
+            else solid_mass_task<G, L, 1>(a, rowst, srank_v, mbar, sgeo[G * G * NC + c], c, valid, lcomp);
+            continue;
+        }
         const int grp = t % NGRP, r = t / NGRP;
         const int ca = r >> 1, half = r & 1;
         const int c = grp * CPW + cw;
@@ -1291,6 +1423,52 @@ __global__ void count_pairs_kernel(const uint32_t* tmask, int64_t ngroups, unsig
         c += __popc((tm | (tm >> 1)) & 0x55555555u);
     }
     if (c) atomicAdd(out, c);
+}
+
+// pair mode: the FROZEN mass factor of fluid.py:33 per (CTA batch, quadrature point, cell slot) of a fluid region,
+// cm J(d1)(x_q) w_q |detJgeo| with d1 = the previous-level displacement handed to tfsi_assemble_A_pre — exactly what
+// lin_jacobian_kernel (mass_kind 2) integrates into A_pre. One thread per (batch slot, q).
+template <int G>
+__global__ void mass_factor_kernel(CellArgs a, int nc_cta, double cm, double* out)
+{
+    constexpr int N2 = Dim<G>::N2;
+    const int nq = c_tabJ.nq;
+    const int64_t nb = (a.ncell_region + nc_cta - 1) / nc_cta;
+    const int64_t total = nb * nq * nc_cta;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % nc_cta);
+        const int q = (int)((t / nc_cta) % nq);
+        const int64_t b = t / ((int64_t)nc_cta * nq);
+        int64_t idx = b * nc_cta + c;
+        if (idx >= a.ncell_region) idx = a.ncell_region - 1;
+        const int64_t cell = a.cell_list[idx];
+        double K[G][G];
+        const double adet = load_geometry<G>(a, cell, K);
+        const int32_t* dofs = a.cell_dofs + cell * a.ndof;
+        double F1[G][G];
+        for (int aa = 0; aa < G; ++aa) {
+            double Gd[G];
+            for (int s = 0; s < G; ++s) Gd[s] = 0;
+            for (int j = 0; j < N2; ++j) {
+                const double d1j = a.x1[dofs[aa * N2 + j]];
+                for (int s = 0; s < G; ++s) Gd[s] += d1j * c_tabJ.dphi2[q][j][s];
+            }
+            for (int bb = 0; bb < G; ++bb) {
+                double s = (aa == bb) ? 1.0 : 0.0;
+                for (int u = 0; u < G; ++u) s += Gd[u] * K[u][bb];
+                F1[aa][bb] = s;
+            }
+        }
+        out[t] = (cm * det<G>(F1)) * (c_tabJ.w[q] * adet);
+    }
+}
+
+// facet-operator entries (COO positions) that lie in rows J_nl scatters into: added to a zero-filled matrix of a pair
+__global__ void coo_add_flagged_kernel(const int64_t* pos, const double* vals, const int32_t* rows, const uint8_t* flag,
+                                       int64_t n, double* A)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (flag[rows[i]]) atomicAdd(A + pos[i], vals[i]);
 }
 
 // ---- fixed linear facet operator (COO): A_pre += A_f ; b -= A_f x  (biharmonic.py:38-41 ds terms)

@@ -144,14 +144,16 @@ template <int G> struct FluidBase {
     static constexpr int XJ = BUJ + G;              // Jw * (c1 (v - v1) + H u)
     static constexpr int PJ = XJ + G;               // Jw * (theta0 B sigma - p B)        G*G
     static constexpr int RJ = PJ + G * G;           // k4 * B H                           G*G
-    static constexpr int COUNT = RJ + G * G;        // 49 (3-D), 24 (2-D)
+    static constexpr int MASSJ = RJ + G * G;        // pair mode: the FROZEN mass factor rho_f theta1 / k J(d1_setup) w |detJgeo|
+                                                    // of fluid.py:33 (part of A_pre; 0 when A_pre is already in the matrix)
+    static constexpr int COUNT = MASSJ + 1;         // 50 (3-D), 25 (2-D): same padded stride as 49 / 24
 };
 
 // coefficient access: cf(k) returns local dof k of the cell at time n, cf1(k) at n-1
 // (local layout [d comps | v comps | p | w comps]); out(item, value) stores a base item.
 template <int G, class Tab, class CF, class CF1, class OUT>
 TFSI_HD void fluid_base(const Tab& tab, int q, const double (&K)[G][G], double adet,
-                        const RegionConst& rc, CF cf, CF1 cf1, OUT out)
+                        const RegionConst& rc, CF cf, CF1 cf1, OUT out, double massj = 0.0)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
     typedef FluidBase<G> I;
@@ -216,6 +218,7 @@ TFSI_HD void fluid_base(const Tab& tab, int q, const double (&K)[G][G], double a
     const double Jw = J * tab.w[q] * adet;
     const double k4 = rc.th0 * rc.mu * Jw;
     out(I::JW, Jw);
+    out(I::MASSJ, massj);
 #pragma unroll
     for (int t = 0; t < G; ++t) {
         double bu = 0, hu = 0;
@@ -254,7 +257,7 @@ TFSI_HD void fluid_C_psi_dv(BV bv, const RegionConst& rc, int a, int b, double (
     typedef FluidBase<G> I;
     const double Jw = bv(I::JW);
     const double dab = (a == b) ? 1.0 : 0.0;
-    C[0][0] = Jw * (rc.c1 * dab + rc.th0rho * bv(I::H + a * G + b));
+    C[0][0] = Jw * (rc.c1 * dab + rc.th0rho * bv(I::H + a * G + b)) + dab * bv(I::MASSJ);
     const double k4 = Jw * rc.th0 * rc.mu;
     double kBa[G];
 #pragma unroll

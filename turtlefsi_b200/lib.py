@@ -15,7 +15,7 @@ EXPORTS = [
     "tfsi_sumsq", "tfsi_newton_assemble_host", "tfsi_halo_pack", "tfsi_halo_unpack",
     "tfsi_launch_count", "tfsi_probe_fp64_peak", "tfsi_expand_node_pattern", "tfsi_set_profiling", "tfsi_kernel_time", "tfsi_compress_A_pre", "tfsi_compressed_nnz", "tfsi_set_facet_operator", "tfsi_set_facet_operator_prev", "tfsi_set_facet_load", "tfsi_set_facet_load_scale", "tfsi_csr_matvec",
     "tfsi_invalidate_A_pre", "tfsi_bind_matrix", "tfsi_unbind_matrix", "tfsi_bound_init_entries", "tfsi_release_pattern",
-    "tfsi_num_colours", "tfsi_assemble_jacobian_phase", "tfsi_bind_matrix_pair", "tfsi_debug_bg_placement",
+    "tfsi_num_colours", "tfsi_assemble_jacobian_phase", "tfsi_bind_matrix_pair", "tfsi_fused_launches",
 ]
 
 APRE_COMPRESSED = 1     # TFSI_APRE_COMPRESSED sentinel (include/turtlefsi_b200.h)
@@ -116,7 +116,8 @@ def load():
     lib.tfsi_invalidate_A_pre.argtypes = [vp]
     lib.tfsi_bind_matrix.argtypes = [vp, vp, vp]
     lib.tfsi_unbind_matrix.argtypes = [vp]
-    lib.tfsi_debug_bg_placement.argtypes = [vp, vp]
+    lib.tfsi_fused_launches.argtypes = [vp]
+    lib.tfsi_fused_launches.restype = i64
     lib.tfsi_bind_matrix_pair.argtypes = [vp, vp, vp, vp, vp]
     lib.tfsi_bound_init_entries.argtypes = [vp]
     lib.tfsi_bound_init_entries.restype = i64
