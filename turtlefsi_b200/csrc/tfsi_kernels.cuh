@@ -36,6 +36,9 @@ constexpr int CELLS_PER_CTA = 32;
 #define TFSI_SMALL_UNROLL 1       // kernel's code size: instruction-cache misses on code that runs once per CTA)
 #endif
 constexpr int SMALL_UNROLL = TFSI_SMALL_UNROLL;
+#ifndef TFSI_SOLID_MASS_FIRST
+#define TFSI_SOLID_MASS_FIRST 0
+#endif
 #ifndef TFSI_TASK_ORDER
 #define TFSI_TASK_ORDER 2
 #endif
@@ -351,10 +354,9 @@ __device__ __forceinline__ void fluid_big_task(const int FLD, const CellArgs& a,
 
 template <int G, int NQ>
 #ifndef TFSI_FLUID_MAXREG
-#define TFSI_FLUID_MAXREG 160
+#define TFSI_FLUID_MAXREG 168
 #endif
-// 160 registers (no spills): 3 warps x 32 x 160 = 15360 of the 16384 registers of an SM sub-partition, so that one
-// 32-register warp of the background initialisation kernel (bitmap_expand_bg_kernel) fits beside them
+// 168 registers (no spills): 12 warps x 32 x 168 = 64512 of the 65536 registers of an SM (160: 13.99, 168: 13.76 ms)
 __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2, N1 = Dim<G>::N1;
@@ -646,7 +648,7 @@ __device__ __forceinline__ void solid_mass_task(const CellArgs& a, const int64_t
 }
 
 template <int G, int NQ, int MAT = 0>
-// 160 registers as the fluid kernel: the background copy keeps running beside the three 4-warp CTAs per SM
+// same register limit as the fluid kernel: three 4-warp CTAs per SM
 __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
 {
     constexpr int N2 = Dim<G>::N2;
@@ -726,6 +728,9 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= ntask) break;
+#if TFSI_SOLID_MASS_FIRST
+        t = (t < ntask - NTASK) ? NTASK + t : t - (ntask - NTASK);      // the (FP64-free) mass tasks first
+#endif
         if (t >= NTASK) {
             const int grp = (t - NTASK) % NGRP, half = (t - NTASK) / NGRP;
             const int c = grp * CPW + cw;
