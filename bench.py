@@ -559,7 +559,9 @@ def roofline_of(w, m, steps):
         w.mesh.num_cells * (64 * 4 + 10 * 64 * 2 + 2 * 8.4 * 8 + 100)
     traffic = None
     tnote = "no ncu capture of this launch is committed"
-    tp = os.path.join(ROOT, "profiles", "r2_fluid_traffic.json")
+    # the capture that matches the mode of this run: r3 = matrix pair (the fluid launch also zero-fills the idle matrix),
+    # r2 = single matrix
+    tp = os.path.join(ROOT, "profiles", "r3_fluid_traffic.json" if w.pair else "r2_fluid_traffic.json")
     if os.path.exists(tp):
         t = json.load(open(tp))
         traffic = t["dram_bytes_per_cell"] * n_fluid
