@@ -54,6 +54,8 @@ def test_tf_fsi_file_default_biharmonic():
     assert abs(ns["drag_list"][-1] / g["drag"] - 1) < 1e-10            # reference golden, round-off level
     assert abs(ns["displacement_x_list"][-1] / g["dis_x"] - 1) < 1e-9
     assert abs(ns["lift_list"][-1] / g["lift"] - 1) < 1e-7
+    # the Newton loop alternated between the two matrices of a pair, re-initialised from inside the fluid kernel
+    assert ns["A_pair"] is not None and ns["assembler"].fused_launches() >= 5
 
 
 def test_tf_fsi_laplace_constant():
@@ -117,6 +119,7 @@ def test_tf_csm():
     _compare(ns, hist["tf_csm"], ("dis_x", "dis_y"), rtol=1e-7)
     assert np.isclose(ns["displacement_x_list"][-1], gold["TF_csm"]["dis_x"])
     assert np.isclose(ns["displacement_y_list"][-1], gold["TF_csm"]["dis_y"])
+    assert ns["A_pair"] is not None and ns["assembler"].fused_launches() == 0      # no fluid cells: foreground path
 
 
 def test_tube3d_newton_matches_oracle():

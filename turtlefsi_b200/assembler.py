@@ -240,6 +240,14 @@ class FSIAssembler:
         self._bound = (A0, A1)
         return int(self.lib.tfsi_bound_init_entries(self.h))
 
+    def pair_fits(self):
+        """a second matrix (plus the zero-fill lists) fits into the free HBM; TFSI_MATRIX_PAIR=0 switches the pair off."""
+        import os
+        if os.environ.get("TFSI_MATRIX_PAIR", "1") == "0":
+            return False
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return 8 * self.nnz * 1.35 < free
+
     def fused_launches(self):
         """fluid launches that carried re-initialisation work for the matrix pair so far."""
         return int(self.lib.tfsi_fused_launches(self.h))

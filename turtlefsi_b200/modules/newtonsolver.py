@@ -49,11 +49,17 @@ def solver_setup(F_fluid_linear, F_fluid_nonlinear, F_solid_linear, F_solid_nonl
         assembler.compress_A_pre(A_pre)           # A_pre is final here (problem files edit the forms before)
     A = assembler.new_matrix()
     assembler.copy(A, A_pre)                  # A = Matrix(A_pre)
-    if hasattr(assembler, "bind_matrix"):
+    A_pair = None
+    if hasattr(assembler, "bind_matrix_pair") and assembler.pair_fits():
+        # two persistent matrices used alternately by the re-assemblies (the previous Jacobian is dead once the next one
+        # is assembled): the idle one is re-initialised from inside the fluid kernel of the running assembly
+        A_pair = (A, assembler.new_matrix())
+        assembler.bind_matrix_pair(A_pair[0], A_pair[1], "compressed")
+    elif hasattr(assembler, "bind_matrix"):
         assembler.bind_matrix(A)              # persistent solver matrix: re-assemblies rewrite only the rows J_nl touches
     b = None
     return dict(F=F, J_nonlinear="derivative(F_nonlin, dvp_n): hand-derived in the kernels", A_pre=A_pre, A=A, b=b,
-                up_sol=up_sol, bc_plan=bc_plan, facet_loads=loads)
+                up_sol=up_sol, bc_plan=bc_plan, facet_loads=loads, A_pair=A_pair)
 
 
 def _update_facet_loads(assembler, facet_loads, mesh, DVP, boundaries, compiler_parameters):
@@ -70,7 +76,7 @@ def _update_facet_loads(assembler, facet_loads, mesh, DVP, boundaries, compiler_
 
 def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_tstep, compiler_parameters,
                  dvp_, up_sol, dvp_res, rtol, atol, max_it, counter, first_step_num, verbose, assembler,
-                 residual_history=None, bc_plan=None, facet_loads=None, **namespace):
+                 residual_history=None, bc_plan=None, facet_loads=None, A_pair=None, **namespace):
     """Newton scheme with the reference's Jacobian-reuse predicates (newtonsolver.py:44-113)."""
     # Initial values
     iter = 0
@@ -109,6 +115,8 @@ def newtonsolver(F, J_nonlinear, A_pre, A, b, bcs, lmbda, recompute, recompute_t
         if recompute_for_timestep or recompute_frequency or recompute_residual or recompute_initialize:
             if verbose:
                 print("Compute Jacobian matrix")
+            if A_pair is not None:                            # the other matrix of the pair: the one in use is dead from here on
+                A = A_pair[1] if A is A_pair[0] else A_pair[0]
             assembler.assemble_jacobian(x, x1, A_pre, A)      # J_nonlinear + A_pre
             assembler.ident_zeros(A)
             assembler.apply_bc_matrix(A)
