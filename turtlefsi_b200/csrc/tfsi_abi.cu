@@ -30,6 +30,7 @@ struct Region {
     int32_t* dofs_blk;    // device, per CTA batch
     int32_t* res_dofs_blk; // device, per residual CTA batch: [ndof][res_nc]
     size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
+    std::vector<int32_t> res_pmax;   // host entry: prefix maximum of the largest dof of every residual batch
     double* massJ;        // pair mode, fluid: frozen mass factors [batch][q][NC] (tfsi_assemble_A_pre)
     uint16_t* rank_blk_v; // pair mode, solid: ranks of the velocity columns per CTA batch (tfsi_bind_matrix_pair)
     size_t rank_v_elems;
@@ -86,6 +87,8 @@ struct tfsi_handle {
     int apre_own;                             // the compressed A_pre is that array (pair mode relies on its structure)
     int64_t fused_launches;                   // fluid launches that carried fill / fix-up work (tests, bench)
     int suppress_bg;                          // host entry: A := A_pre already runs under the H2D copy
+    const std::vector<std::pair<int64_t, int64_t>>* res_ranges;   // host entry: residual batches [b0, b1) per region of the next launch
+    std::vector<cudaEvent_t> ev_chunk;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 jac_fluid, 1 jac_solid, 2 residual
     std::string err;
     int id;
@@ -425,16 +428,22 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
     typedef ResCfg<G, BIH> R;
     const size_t smem = R::bytes(h->tabR.nq, NC);
     CK(h, cudaFuncSetAttribute(residual_kernel<G, BIH, NC, LIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (const Region& r : h->regions) {
+    for (size_t ri = 0; ri < h->regions.size(); ++ri) {
+        const Region& r = h->regions[ri];
         if (r.ncells == 0) continue;
         const RegionConst& rc = r.rc;
         if (general_solid(rc) != (LIFT == LIFT_SOLID_GENERAL)) continue;
         if (rc.kind == TFSI_KIND_FLUID && !rc.fluid_on && rc.ext == 0) continue;
         if (rc.kind == TFSI_KIND_SOLID && !rc.solid_on) continue;
+        int64_t b0 = 0, b1 = (r.ncells + NC - 1) / NC;
+        if (h->res_ranges) { b0 = (*h->res_ranges)[ri].first; b1 = std::min(b1, (*h->res_ranges)[ri].second); }
+        if (b0 >= b1) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
-        a.dofs_blk = r.res_dofs_blk;
+        a.dofs_blk = r.res_dofs_blk + (size_t)b0 * h->ndof * NC;         // batches [b0, b1) of the region
+        a.cell_list = r.cell_list + b0 * NC;
+        a.ncell_region = std::min<int64_t>(r.ncells - b0 * NC, (b1 - b0) * NC);
         KernelTimer kt(h, 2, st);
-        residual_kernel<G, BIH, NC, LIFT><<<(unsigned)((r.ncells + NC - 1) / NC), NC * 8, smem, st>>>(a);
+        residual_kernel<G, BIH, NC, LIFT><<<(unsigned)(b1 - b0), NC * 8, smem, st>>>(a);
         h->launches++;
         CK(h, cudaGetLastError());
     }
@@ -485,6 +494,27 @@ int launch_residual(tfsi_handle* h, const double* x, const double* x1, double* b
     return h->biharmonic ? launch_residual_t<2, true>(h, x, x1, b, st) : launch_residual_t<2, false>(h, x, x1, b, st);
 }
 
+// the fixed facet operators and the facet load of the residual (b -= A_f x, b -= A_p x1, b -= p(t) l)
+int residual_facet_terms(tfsi_handle* h, const double* x, const double* x1, double* b, cudaStream_t st) {
+    if (h->fo_n) {
+        coo_sub_matvec_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_rows, h->fo_cols, h->fo_vals, h->fo_n, x, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (h->fp_n) {
+        coo_sub_matvec_kernel<<<grid_for(h->fp_n, 256, h->sm_count), 256, 0, st>>>(h->fp_rows, h->fp_cols, h->fp_vals, h->fp_n, x1, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    if (h->fl_n && h->fl_scale != 0.0) {
+        sparse_sub_scaled_kernel<<<grid_for(h->fl_n, 256, h->sm_count), 256, 0, st>>>(h->fl_dofs, h->fl_vals, h->fl_n, h->fl_scale, b);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -506,6 +536,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->cpre_bitmap); cudaFree(h->cpre_base); cudaFree(h->cpre_val); cudaFree(h->tmask);
     cudaFree(h->fill_pieces); cudaFree(h->fill_scalar); cudaFree(h->row_flag);
     for (auto& b : h->bound) if (b.ready) cudaEventDestroy(b.ready);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
@@ -577,7 +608,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
     h->nbound = 0; h->tmask = nullptr; h->bound_entries = 0; h->fused_launches = 0;
     for (auto& b : h->bound) { b.A = nullptr; b.state = BOUND_STALE; b.pending = 0; b.ready = nullptr; }
     h->fill_pieces = nullptr; h->fill_scalar = nullptr; h->n_fill = h->n_fill_scalar = 0; h->row_flag = nullptr; h->suppress_bg = 0;
-    h->apre_last = nullptr; h->apre_sumsq = 0.0; h->apre_own = 0;
+    h->apre_last = nullptr; h->apre_sumsq = 0.0; h->apre_own = 0; h->res_ranges = nullptr;
     h->fluid_on = p->fluid_on; h->solid_on = p->solid_on; h->ext = p->extrapolation; h->ext_sub = p->extrapolation_sub_type;
     if (h->ext == TFSI_EXT_BIHARMONIC && !h->biharmonic) { delete h; return fail(nullptr, TFSI_ERR_ARG, "biharmonic lifting needs the 4-field space"); }
     if (h->ext < 0 || h->ext > TFSI_EXT_ELASTIC) { delete h; return fail(nullptr, TFSI_ERR_ARG, "unknown extrapolation code %d", h->ext); }
@@ -1071,22 +1102,7 @@ int tfsi_assemble_residual(tfsi_handle* h, const double* x, const double* x1, do
     if (int rc = bind_tables(h, st)) return rc;
     CK(h, cudaMemsetAsync(b, 0, (size_t)h->N * sizeof(double), st));
     if (int rc = launch_residual(h, x, x1, b, st)) return rc;
-    if (h->fo_n) {
-        coo_sub_matvec_kernel<<<grid_for(h->fo_n, 256, h->sm_count), 256, 0, st>>>(h->fo_rows, h->fo_cols, h->fo_vals, h->fo_n, x, b);
-        h->launches++;
-        CK(h, cudaGetLastError());
-    }
-    if (h->fp_n) {
-        coo_sub_matvec_kernel<<<grid_for(h->fp_n, 256, h->sm_count), 256, 0, st>>>(h->fp_rows, h->fp_cols, h->fp_vals, h->fp_n, x1, b);
-        h->launches++;
-        CK(h, cudaGetLastError());
-    }
-    if (h->fl_n && h->fl_scale != 0.0) {
-        sparse_sub_scaled_kernel<<<grid_for(h->fl_n, 256, h->sm_count), 256, 0, st>>>(h->fl_dofs, h->fl_vals, h->fl_n, h->fl_scale, b);
-        h->launches++;
-        CK(h, cudaGetLastError());
-    }
-    return 0;
+    return residual_facet_terms(h, x, x1, b, st);
 }
 
 int tfsi_ident_zeros(tfsi_handle* h, double* A, void* stream) {
@@ -1180,25 +1196,79 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
         CK(h, cudaMalloc((void**)&h->hx1, nb));
         CK(h, cudaMalloc((void**)&h->hb, nb));
     }
-    // Two streams: `io` carries the host<->device copies, `st` the kernels. The x-independent A := A_pre
-    // runs under the H2D copy of x; the residual is assembled BEFORE the Jacobian so that its D2H copy
-    // and norm run under the Jacobian kernels. Both streams start after everything the caller has
-    // queued on `stream` (A_pre, A are the caller's buffers).
+    // Two streams: `io` carries the host<->device copies, `st` the kernels. The x-independent A := A_pre (if this
+    // matrix needs one: not in pair mode) runs under the H2D copy of x; the residual is assembled BEFORE the Jacobian
+    // so that its D2H copy and norm run under the Jacobian kernels. Both streams start after everything the caller
+    // has queued on `stream` (A_pre, A are the caller's buffers).
     cudaStream_t st = h->main_stream, io = h->copy_stream;
     const bool bcs = h->nbc && g_host;
     CK(h, cudaEventRecord(h->ev_entry, (cudaStream_t)stream));
     CK(h, cudaStreamWaitEvent(st, h->ev_entry, 0));
     CK(h, cudaStreamWaitEvent(io, h->ev_entry, 0));
-    CK(h, cudaMemcpyAsync(h->hx, x_host, nb, cudaMemcpyHostToDevice, io));
-    if (x1_host) { CK(h, cudaMemcpyAsync(h->hx1, x1_host, nb, cudaMemcpyHostToDevice, io)); h->hx1_valid = 1; }
+    // The iterate goes up in CHUNKS of consecutive dofs, and the residual batches of every region start as soon as the
+    // chunks they read have arrived (prefix maximum of the largest dof per batch: cells and dofs of a locality-ordered
+    // mesh run in parallel, so the residual kernel trails the copy by one chunk; on an arbitrary numbering everything
+    // simply waits for the last chunk).
     if (bcs) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, io));
+    static const int max_chunks = getenv("TFSI_H2D_CHUNKS") ? atoi(getenv("TFSI_H2D_CHUNKS")) : 8;
+    const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(max_chunks, h->N / (1 << 20)));
+    if (h->res_nc && nchunk > 1) {
+        for (Region& r : h->regions) {
+            if (r.ncells == 0 || !r.res_pmax.empty() || !r.res_dofs_blk) continue;
+            const int64_t nbr = (r.ncells + h->res_nc - 1) / h->res_nc;
+            int32_t* dm = nullptr;
+            CK(h, cudaMalloc((void**)&dm, (size_t)nbr * sizeof(int32_t)));
+            batch_max_dof_kernel<<<grid_for(nbr, 128, h->sm_count), 128, 0, st>>>(r.res_dofs_blk, nbr, h->ndof * h->res_nc, dm);
+            r.res_pmax.resize((size_t)nbr);
+            CK(h, cudaMemcpyAsync(r.res_pmax.data(), dm, (size_t)nbr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(h, cudaStreamSynchronize(st));
+            cudaFree(dm);
+            for (size_t i = 1; i < r.res_pmax.size(); ++i) r.res_pmax[i] = std::max(r.res_pmax[i], r.res_pmax[i - 1]);
+        }
+    }
+    while ((int)h->ev_chunk.size() < nchunk) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        const int64_t lo = h->N * k / nchunk, hi = h->N * (k + 1) / nchunk;
+        CK(h, cudaMemcpyAsync(h->hx + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, io));
+        if (x1_host) CK(h, cudaMemcpyAsync(h->hx1 + lo, x1_host + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, io));
+        CK(h, cudaEventRecord(h->ev_chunk[(size_t)k], io));
+    }
+    if (x1_host) h->hx1_valid = 1;
     CK(h, cudaEventRecord(h->ev_in, io));
+    if (int rc = bind_tables(h, st)) return rc;
     if (recompute) {
-        if (int rc = bind_tables(h, st)) return rc;
         if (int rc = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 1)) return rc;
     }
+    CK(h, cudaMemsetAsync(h->hb, 0, nb, st));
+    {
+        std::vector<std::pair<int64_t, int64_t>> ranges(h->regions.size(), std::make_pair((int64_t)0, (int64_t)0));
+        for (int k = 0; k < nchunk; ++k) {
+            const int64_t hi = h->N * (k + 1) / nchunk;
+            bool any = false;
+            for (size_t ri = 0; ri < h->regions.size(); ++ri) {
+                const Region& r = h->regions[ri];
+                const int64_t nbr = h->res_nc ? (r.ncells + h->res_nc - 1) / h->res_nc : 0;
+                int64_t upto = nbr;
+                if (k + 1 < nchunk)
+                    upto = r.res_pmax.empty() ? 0 : (int64_t)(std::lower_bound(r.res_pmax.begin(), r.res_pmax.end(), (int32_t)hi) - r.res_pmax.begin());
+                ranges[ri].first = ranges[ri].second;
+                ranges[ri].second = std::max(ranges[ri].second, upto);
+                any = any || ranges[ri].second > ranges[ri].first;
+            }
+            if (!any) continue;
+            CK(h, cudaStreamWaitEvent(st, h->ev_chunk[(size_t)k], 0));
+            h->res_ranges = &ranges;
+            const int rc = launch_residual(h, h->hx, h->hx1, h->hb, st);
+            h->res_ranges = nullptr;
+            if (rc) return rc;
+        }
+    }
     CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
-    if (int rc = tfsi_assemble_residual(h, h->hx, h->hx1, h->hb, st)) return rc;
+    if (int rc = residual_facet_terms(h, h->hx, h->hx1, h->hb, st)) return rc;
     if (bcs) if (int rc = tfsi_apply_bc_rhs(h, h->hb, h->hx, h->hg, h->nbc, st)) return rc;
     CK(h, cudaEventRecord(h->ev_b, st));
     CK(h, cudaStreamWaitEvent(io, h->ev_b, 0));
@@ -1208,10 +1278,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
     h->launches++;
     CK(h, cudaGetLastError());
     if (recompute) {
-        h->suppress_bg = 1;        // the initialisation of this call ran under the H2D copy: nothing to hide, and a
-        int rc2 = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 2);   // background copy would only slow the kernels down
-        h->suppress_bg = 0;
-        if (rc2) return rc2;
+        if (int rc2 = launch_jacobian(h, h->hx, h->hx1, Apre, A, st, 2)) return rc2;
         if (int rc = tfsi_ident_zeros(h, A, st)) return rc;
         if (int rc = tfsi_apply_bc_matrix(h, A, st)) return rc;
     }

@@ -1468,6 +1468,17 @@ __global__ void mass_factor_kernel(CellArgs a, int nc_cta, double cm, double* ou
     }
 }
 
+// largest dof index of every residual batch ([ndof][res_nc] ints per batch): the host entry starts a batch as soon as
+// the chunks of the iterate it reads have arrived
+__global__ void batch_max_dof_kernel(const int32_t* dofs_blk, int64_t nb, int elems, int32_t* out)
+{
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        int32_t m = 0;
+        for (int k = 0; k < elems; ++k) m = max(m, dofs_blk[b * elems + k]);
+        out[b] = m;
+    }
+}
+
 // facet-operator entries (COO positions) that lie in rows J_nl scatters into: added to a zero-filled matrix of a pair
 __global__ void coo_add_flagged_kernel(const int64_t* pos, const double* vals, const int32_t* rows, const uint8_t* flag,
                                        int64_t n, double* A)
