@@ -497,10 +497,17 @@ def measure(w, args, device, world, dist, local_rank, steps, warmup, full=True):
     # the same step with the masked re-initialisation in the FOREGROUND (what a single bound matrix costs)
     os.environ["TFSI_NO_FUSED_INIT"] = "1"
     asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A)
+    asm.set_profiling(True)
     t_both = timed(lambda: asm.assemble_jacobian(w.xd, w.x1d, "compressed", w.A))          # foreground init + kernels
+    kf1_ms, kf1_n = asm.kernel_time(0)
+    ks1_ms, ks1_n = asm.kernel_time(1)
+    asm.set_profiling(False)
     del os.environ["TFSI_NO_FUSED_INIT"]
     out["ms_step_foreground_init"] = t_both
-    out["ms_init"] = t_both - out["kf_ms"] - out["ks_ms"]
+    # the cell kernels WITHOUT the pair's extra work (zero-fill of the idle matrix, in-kernel mass blocks)
+    out["kf_alone_ms"] = kf1_ms / max(kf1_n, 1) * max(out["kf_n"], 1)
+    out["ks_alone_ms"] = ks1_ms / max(ks1_n, 1) * max(out["ks_n"], 1)
+    out["ms_init"] = t_both - out["kf_alone_ms"] - out["ks_alone_ms"]
     out["ms_ident"] = timed(lambda: asm.ident_zeros(w.A))
     xs = w.xd.clone()                                   # bc.apply(x) writes the iterate: time it on a copy
     out["ms_bc"] = timed(lambda: (asm.apply_bc_matrix(w.A), asm.apply_bc_rhs(w.b, xs, gd), asm.apply_bc_vec(xs, gd)))
@@ -575,13 +582,19 @@ def roofline_of(w, m, steps):
         "flops_per_cell": flops_fluid, "cells_per_launch": n_fluid, "launches_per_step": m["kf_n"],
         "ms_per_launch": m["kf_ms"] / max(m["kf_n"], 1),
         "traffic": traffic, "traffic_note": tnote,
+        # matrix pair: the launch above also zero-fills the idle matrix; the same kernel on a single matrix (what the
+        # separate masked A := A_pre pass of that mode then costs is breakdown_ms.init_A_pre_rows_if_foreground)
+        "fluid_kernel_single_matrix": {"ms_per_launch": m.get("kf_alone_ms", 0.0) / max(m["kf_n"], 1),
+                                       "achieved": flops_fluid * n_fluid / (m["kf_alone_ms"] * 1e-3) / 1e12,
+                                       "frac": flops_fluid * n_fluid / (m["kf_alone_ms"] * 1e-3) / 1e12 / peak_tf}
+        if m.get("kf_alone_ms") else None,
         # the same launch against SURVEY.md 8(d)'s counting model (dense sum factorisation, 23.8 kFLOP per point = 0.333
         # MFLOP per fluid tet at 14 points): the kernels integrate the same forms with 34 % fewer operations (sparse P2
         # reference gradients), so `frac` above is quoted on the SMALLER count they actually need
         "survey_model": {"flops_per_cell": 23800 * NQ_J, "achieved": 23800 * NQ_J * n_fluid / (m["kf_ms"] * 1e-3) / 1e12,
                          "frac": 23800 * NQ_J * n_fluid / (m["kf_ms"] * 1e-3) / 1e12 / peak_tf},
         "step": {"achieved": step_flops / (m["ms_step"] * 1e-3) / 1e12, "frac": step_flops / (m["ms_step"] * 1e-3) / 1e12 / peak_tf,
-                 "what": "(fluid + solid algorithmic FLOPs of this rank) / whole step time incl. A := A_pre"},
+                 "what": "(fluid + solid algorithmic FLOPs of this rank) / whole step time incl. the re-initialisation of A (fused into the cell kernels with the matrix pair, a separate masked pass without)"},
         "hbm": {"achieved": alg_bytes_step / (m["ms_step"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes_step / (m["ms_step"] * 1e-3) / 1e9 / hbm_peak,
                 "algorithmic_bytes_per_cell": alg_bytes_step / w.mesh.num_cells,
