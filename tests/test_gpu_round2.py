@@ -120,6 +120,66 @@ def test_matrix_pair_fused_reinitialisation(tube_params):
     assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), rp) < 1e-14
 
 
+@pytest.mark.parametrize("case", ["degree6_chunks", "materials", "form2_fallback", "facet_operator", "2d_biharmonic", "no_fluid_fallback"])
+def test_matrix_pair_variants(case, tube_params):
+    """the fused re-initialisation of the pair next to everything that changes what A_pre holds in the rewritten rows or how
+    the cell kernels are launched: a quadrature rule run in chunks, several regions with energy-based / viscoelastic solids
+    ("Form2" has a block in A_pre: foreground fallback), a facet operator on velocity rows (Robin term), the 2-D
+    biharmonic space, a run without fluid cells (fallback). Alternating assemblies must equal the plain path."""
+    import torch
+    from tests.helpers import square_mesh
+    from turtlefsi_b200.assembler import FSIAssembler
+    from turtlefsi_b200.mesh import synthetic_state, tube_mesh
+    from turtlefsi_b200.space import MixedSpace
+    common, regions = tube_params
+    regions = [dict(r) for r in regions]
+    kw, gdim, bih, expect_fused = {}, 3, False, True
+    if case == "degree6_chunks":
+        kw = dict(quad_degree_jacobian=6)
+    elif case == "materials":
+        regions += [dict(regions[1], marker=3, material_model="NeoHookean", viscoelasticity="Form1", mu_visc_s=1.0e4, lambda_visc_s=2.0e4),
+                    dict(regions[0], marker=1001, rho=1100.0, mu=7.0e-3)]
+    elif case == "form2_fallback":
+        regions[1].update(viscoelasticity="Form2", mu_visc_s=1.0e2, lambda_visc_s=3.0e2)
+        expect_fused = False
+    elif case == "2d_biharmonic":
+        gdim, bih, kw = 2, True, dict(extrapolation="biharmonic", quad_degree_jacobian=5, quad_degree_residual=10)
+    elif case == "no_fluid_fallback":
+        kw, expect_fused = dict(fluid="no_fluid"), False
+    mesh = tube_mesh(5) if gdim == 3 else square_mesh(8)
+    if case == "materials":
+        zc = mesh.coords[mesh.cells].mean(axis=1)[:, 2]
+        mesh.markers = np.where(mesh.markers == 1, np.where(zc > 2.0, 1001, 1), np.where(zc > 2.0, 3, 2)).astype(np.int32)
+    space = MixedSpace(mesh, biharmonic=bih)
+    h = 2.0 / 5 if gdim == 3 else 0.5
+    x, x1 = synthetic_state(mesh, space, 2024, h=h), synthetic_state(mesh, space, 2025, h=h)
+    asm = FSIAssembler(mesh, space, regions, common["dt"], common["theta"], **kw)
+    rng = np.random.default_rng(3)
+    asm.set_bc_dofs(rng.choice(space.num_dofs, size=200, replace=False).astype(np.int32))
+    if case == "facet_operator":                     # entries on velocity rows (rewritten) and displacement rows (kept)
+        rp, ci = asm.rowptr.cpu().numpy(), asm.colidx.cpu().numpy()
+        rows = rng.choice(space.num_dofs, size=400, replace=False).astype(np.int32)
+        cols = np.array([ci[rp[r] + rng.integers(0, rp[r + 1] - rp[r])] for r in rows], dtype=np.int32)
+        asm.set_facet_operator(rows, cols, rng.uniform(1.0, 2.0, len(rows)) * 1e3)
+    xd, x1d = torch.as_tensor(x).cuda(), torch.as_tensor(x1).cuda()
+    A_pre = asm.assemble_A_pre(xd, x1d)
+    asm.compress_A_pre(A_pre)
+    A0, A1 = asm.new_matrix(), asm.new_matrix()
+    asm.bind_matrix_pair(A0, A1, "compressed")
+    rp = asm.rowptr.cpu().numpy()
+    f0 = asm.fused_launches()
+    for it, A in enumerate([A0, A1, A0, A1, A0]):
+        xi = xd + 1e-3 * (it + 1) * torch.cos(torch.arange(space.num_dofs, device="cuda", dtype=torch.float64))
+        asm.assemble_jacobian(xi, x1d, "compressed", A)
+        asm.ident_zeros(A)
+        asm.apply_bc_matrix(A)
+        ref = asm.assemble_jacobian(xi, x1d, A_pre)               # unbound buffer, full path
+        asm.ident_zeros(ref)
+        asm.apply_bc_matrix(ref)
+        assert _row_rel_err(A.cpu().numpy(), ref.cpu().numpy(), rp) < 1e-13, (case, it)
+    assert (asm.fused_launches() - f0 >= 3) == expect_fused, case
+
+
 @pytest.mark.parametrize("degJ,npts", [(5, 15), (6, 24)])
 def test_jacobian_rule_in_chunks(degJ, npts, tube_params):
     """compiler_parameters["quadrature_degree"] is user-settable (problems/__init__.py:16-17, argpar.py:224-229):

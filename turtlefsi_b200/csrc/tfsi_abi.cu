@@ -179,9 +179,9 @@ int grid_for(int64_t n, int block, int sm) {
 }
 
 // largest chunk of quadrature points whose per-point table fits the shared memory of one CTA
-template <class SM> int max_points(int nq) {
+template <class SM> int max_points(int nq, size_t extra = 0) {
     int m = nq;
-    while (m > 1 && SM::bytes(m) > 227 * 1024) --m;
+    while (m > 1 && SM::bytes(m) + extra > 227 * 1024) --m;
     return m;
 }
 
@@ -203,8 +203,10 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
     const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
     const int grid = (int)((r.ncells + ncta - 1) / ncta);
     const bool energy = !is_fluid && r.rc.mat != MAT_SVK;        // energy-based solid model: tangent-table variant
+    // (solid: sized as if the second rank table of the pair mode were always staged)
     const int chunk = is_fluid ? max_points<typename FluidJac<G>::SM>(nq)
-                               : (energy ? max_points<typename SolidJac<G, 1>::SM>(nq) : max_points<typename SolidJac<G>::SM>(nq));
+                               : (energy ? max_points<typename SolidJac<G, 1>::SM>(nq, SolidJac<G, 1>::SM::RANK_BYTES)
+                                         : max_points<typename SolidJac<G>::SM>(nq, SolidJac<G>::SM::RANK_BYTES));
     const int nchunk = (nq + chunk - 1) / chunk;
     for (int c = 0; c < nchunk; ++c) {
         a.q0 = (int)((int64_t)nq * c / nchunk);
@@ -234,12 +236,17 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
                 jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
             }
         } else if (energy) {
-            const size_t smem = SolidJac<G, 1>::SM::bytes(a.nq);
+            if (c > 0) a.rank_v = nullptr;                       // the mass block goes with the first chunk only
+            const size_t smem = a.rank_v ? SolidJac<G, 1>::SM::bytes_with_rank_v(a.nq) : SolidJac<G, 1>::SM::bytes(a.nq);
+            if (smem > 227 * 1024)
+                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
             CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             jac_solid_kernel<G, 0, 1><<<grid, SolidJac<G, 1>::THREADS, smem, st>>>(a);
         } else {
             if (c > 0) a.rank_v = nullptr;                       // the mass block goes with the first chunk only
             const size_t smem = a.rank_v ? SolidJac<G>::SM::bytes_with_rank_v(a.nq) : SolidJac<G>::SM::bytes(a.nq);
+            if (smem > 227 * 1024)
+                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
             if (G == 3 && nq == 14) {
                 CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
