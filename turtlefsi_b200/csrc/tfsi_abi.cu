@@ -187,6 +187,24 @@ template <class SM> int max_points(int nq, size_t extra = 0) {
 
 // J_nl of one region: one launch per chunk of the quadrature rule (the REDs of the chunks add up). The rule of the
 // headline config (Keast 14-point, 3-D) runs in one launch of the compile-time-sized instantiation.
+template <int G, int NQ>
+int launch_fluid(tfsi_handle* h, const CellArgs& a, int grid, size_t smem, cudaStream_t st) {
+    CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jac_fluid_kernel<G, NQ><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
+    return 0;
+}
+
+template <int G, int NQ, int MAT, int MASS>
+int launch_solid(tfsi_handle* h, const CellArgs& a, int grid, cudaStream_t st) {
+    typedef typename SolidJac<G, MAT>::SM SM;
+    const size_t smem = MASS ? SM::bytes_with_rank_v(a.nq) : SM::bytes(a.nq);
+    if (smem > 227 * 1024)
+        return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
+    CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, NQ, MAT, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jac_solid_kernel<G, NQ, MAT, MASS><<<grid, SolidJac<G, MAT>::THREADS, smem, st>>>(a);
+    return 0;
+}
+
 // what ONE fluid launch of an assembly carries for the matrix pair (see CellArgs)
 struct FusedWork { double* fill_dst; bool zeroed; bool used; };
 
@@ -228,32 +246,13 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
                 fw->used = true;
                 h->fused_launches++;
             }
-            if (G == 3 && nq == 14) {
-                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_fluid_kernel<G, 14><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
-            } else {
-                CK(h, cudaFuncSetAttribute(jac_fluid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_fluid_kernel<G, 0><<<grid, FluidJac<G>::THREADS, smem, st>>>(a);
-            }
-        } else if (energy) {
-            if (c > 0) a.rank_v = nullptr;                       // the mass block goes with the first chunk only
-            const size_t smem = a.rank_v ? SolidJac<G, 1>::SM::bytes_with_rank_v(a.nq) : SolidJac<G, 1>::SM::bytes(a.nq);
-            if (smem > 227 * 1024)
-                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
-            CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            jac_solid_kernel<G, 0, 1><<<grid, SolidJac<G, 1>::THREADS, smem, st>>>(a);
+            if (int rc = (G == 3 && nq == 14) ? launch_fluid<G, 14>(h, a, grid, smem, st) : launch_fluid<G, 0>(h, a, grid, smem, st)) return rc;
         } else {
             if (c > 0) a.rank_v = nullptr;                       // the mass block goes with the first chunk only
-            const size_t smem = a.rank_v ? SolidJac<G>::SM::bytes_with_rank_v(a.nq) : SolidJac<G>::SM::bytes(a.nq);
-            if (smem > 227 * 1024)
-                return fail(h, TFSI_ERR_UNSUPPORTED, "Jacobian chunk of %d points needs %zu B of shared memory", a.nq, smem);
-            if (G == 3 && nq == 14) {
-                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_solid_kernel<G, 14><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
-            } else {
-                CK(h, cudaFuncSetAttribute(jac_solid_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                jac_solid_kernel<G, 0><<<grid, SolidJac<G>::THREADS, smem, st>>>(a);
-            }
+            if (int rc = energy ? (a.rank_v ? launch_solid<G, 0, 1, 1>(h, a, grid, st) : launch_solid<G, 0, 1, 0>(h, a, grid, st))
+                       : (G == 3 && nq == 14) ? (a.rank_v ? launch_solid<G, 14, 0, 1>(h, a, grid, st) : launch_solid<G, 14, 0, 0>(h, a, grid, st))
+                                              : (a.rank_v ? launch_solid<G, 0, 0, 1>(h, a, grid, st) : launch_solid<G, 0, 0, 0>(h, a, grid, st)))
+                return rc;
         }
         h->launches++;
         CK(h, cudaGetLastError());

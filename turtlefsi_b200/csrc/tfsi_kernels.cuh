@@ -36,9 +36,6 @@ constexpr int CELLS_PER_CTA = 32;
 #define TFSI_SMALL_UNROLL 1       // kernel's code size: instruction-cache misses on code that runs once per CTA)
 #endif
 constexpr int SMALL_UNROLL = TFSI_SMALL_UNROLL;
-#ifndef TFSI_SOLID_MASS_FIRST
-#define TFSI_SOLID_MASS_FIRST 0
-#endif
 #ifndef TFSI_TASK_ORDER
 #define TFSI_TASK_ORDER 2
 #endif
@@ -138,7 +135,10 @@ template <int G, int NGRP_> struct LB {
 // 12 warps: its per-point base fills the shared memory); the solid kernel's base is half as big and
 // it runs best as THREE small CTAs per SM (10 cells, 4 warps each) whose phases overlap.
 template <int G> struct FluidCfg { static constexpr int NGRP = TFSI_JAC_NGRP, WARPS = TFSI_JAC_WARPS, CTAS = TFSI_JAC_CTAS; typedef LB<G, NGRP> L; };
-template <int G> struct SolidCfg { static constexpr int NGRP = 1, WARPS = 4, CTAS = 3; typedef LB<G, NGRP> L; };
+#ifndef TFSI_SOLID_WARPS
+#define TFSI_SOLID_WARPS 4
+#endif
+template <int G> struct SolidCfg { static constexpr int NGRP = 1, WARPS = TFSI_SOLID_WARPS, CTAS = 12 / TFSI_SOLID_WARPS; typedef LB<G, NGRP> L; };
 
 // item stride of the per-point base: >= n and == G (mod 16) so that lanes (cell, b) reading items
 // (X + b) of cells c fall into distinct 8-byte banks
@@ -386,7 +386,7 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_fluid_kernel(CellArgs a)
     // pair mode (see CellArgs): this CTA's share of the zero-fill pieces and of the fix-up entries, handed out to the
     // warps in batches whenever they fetch a task (counter[1], counter[2]); the work runs beside the FP64 loops of
     // the other warps instead of as a separate HBM-bound pass
-    const bool fused = a.fill_dst != nullptr;
+    const bool fused = a.fill_dst != nullptr;     // (a run-time flag: as a template flag the filling instantiation spills, 16.9 vs 13.8 ms)
     double* zbuf = reinterpret_cast<double*>(smem_raw + SM::off_zero(nq));
     int64_t fill0 = 0, sc0 = 0;
     int nfill = 0, nsc = 0;
@@ -647,7 +647,9 @@ __device__ __forceinline__ void solid_mass_task(const CellArgs& a, const int64_t
     }
 }
 
-template <int G, int NQ, int MAT = 0>
+// MASS = 1: the instantiation for an assembly into a zero-filled matrix of a pair (mass tasks, second rank table); a
+// template flag so that the plain instantiation keeps its code and register allocation (3.88 vs 4.13 ms with a run-time flag)
+template <int G, int NQ, int MAT = 0, int MASS = 0>
 // same register limit as the fluid kernel: three 4-warp CTAs per SM
 __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
 {
@@ -712,9 +714,9 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(mbar, (uint32_t)(SM::RANK_BYTES * (a.rank_v ? 2 : 1)));
+        mbar_expect_tx(mbar, (uint32_t)(SM::RANK_BYTES * (MASS ? 2 : 1)));
         bulk_g2s(srank, a.rank_blk + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
-        if (a.rank_v) bulk_g2s(srank_v, a.rank_v + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
+        if (MASS) bulk_g2s(srank_v, a.rank_v + (size_t)blockIdx.x * (SM::RANK_BYTES / sizeof(uint16_t)), (uint32_t)SM::RANK_BYTES, mbar);
     }
     const int cw = (lane / G < CPW) ? lane / G : CPW - 1;
     const int lcomp = lane % G;
@@ -722,16 +724,13 @@ __global__ void __maxnreg__(TFSI_FLUID_MAXREG) jac_solid_kernel(CellArgs a)
     constexpr int NTASK = NGRP * 2 * G;                 // group x a x half ; b = lane
     // assembly into a zero-filled matrix of a pair: + the mass block psi_b x delta v_b of solid.py:41 (part of A_pre),
     // rho_s / k |detJgeo| sum_q w_q phi_i phi_j with the Jacobian rule, as lin_jacobian_kernel integrates it
-    const int ntask = NTASK + ((a.rank_v && q0 == 0) ? NGRP * 2 : 0);
+    constexpr int ntask = NTASK + (MASS ? NGRP * 2 : 0);
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= ntask) break;
-#if TFSI_SOLID_MASS_FIRST
-        t = (t < ntask - NTASK) ? NTASK + t : t - (ntask - NTASK);      // the (FP64-free) mass tasks first
-#endif
-        if (t >= NTASK) {
+        if (MASS && t >= NTASK) {
             const int grp = (t - NTASK) % NGRP, half = (t - NTASK) / NGRP;
             const int c = grp * CPW + cw;
             const bool valid = lane_on && ((int64_t)blockIdx.x * NC + c < a.ncell_region);
