@@ -214,7 +214,7 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
     const int nq = h->tabJ.nq;
     CellArgs a = cell_args(h, r, nq, x, x1, A);
     const bool is_fluid = r.rc.kind == TFSI_KIND_FLUID;
-    if (fw && fw->zeroed && !getenv("TFSI_EXP_NOMASS")) {   // the matrix holds zeros in the rows J_nl scatters into: + the A_pre part
+    if (fw && fw->zeroed) {                  // the matrix holds zeros in the rows J_nl scatters into: + the A_pre part
         if (is_fluid) a.massJ = r.massJ;
         else a.rank_v = r.rank_blk_v;
     }
@@ -241,8 +241,6 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
                 smem = FluidJac<G>::SM::bytes_with_zero(a.nq);
                 a.fill_dst = fw->fill_dst; a.fill_pieces = h->fill_pieces; a.n_fill = h->n_fill;
                 a.fill_scalar = h->fill_scalar; a.n_fill_scalar = h->n_fill_scalar;
-                if (getenv("TFSI_EXP_NOSCALAR")) a.n_fill_scalar = 0;          // timing experiments (wrong results)
-                if (getenv("TFSI_EXP_NOPIECES")) a.n_fill = 0;
                 fw->used = true;
                 h->fused_launches++;
             }
