@@ -233,7 +233,9 @@ int tfsi_sumsq(tfsi_handle* h, const double* v, int64_t n, double* out_sumsq, vo
  * g_host: BC values [nbc] or NULL. x1_host may be NULL: the previous time level uploaded by the last call is
  * re-used (it changes once per time step, not per Newton iteration). Synchronous: ordered after the work queued on
  * `stream` (the stream on which the caller produced A_pre / A), runs on two internal streams (copies under
- * kernels), returns when b_host and A_vals are final. */
+ * kernels: the iterate goes up in chunks of consecutive dofs and the residual batches start as soon as the chunks
+ * they read have arrived; b goes back under the Jacobian kernels), returns when b_host and A_vals are final.
+ * Pinned host buffers are needed for the copies to overlap. */
 int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double* x1_host,
                               const double* g_host, const double* Apre_vals, double* A_vals,
                               double* b_host, double* out_sumsq_b, int32_t recompute_jacobian, void* stream);
