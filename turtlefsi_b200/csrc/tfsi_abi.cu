@@ -31,6 +31,8 @@ struct Region {
     int32_t* res_dofs_blk; // device, per residual CTA batch: [ndof][res_nc]
     size_t rank_blk_elems, dofs_blk_elems;   // elements per batch
     std::vector<int32_t> res_pmax;   // host entry: prefix maximum of the largest dof of every residual batch
+    double* geo_blk;      // device, per CTA batch of the Jacobian kernels: [g*g+1][NC] inverse Jacobian and |det|
+    double* res_geo_blk;  // the same per residual batch
     double* massJ;        // pair mode, fluid: frozen mass factors [batch][q][NC] (tfsi_assemble_A_pre)
     uint16_t* rank_blk_v; // pair mode, solid: ranks of the velocity columns per CTA batch (tfsi_bind_matrix_pair)
     size_t rank_v_elems;
@@ -159,10 +161,18 @@ CellArgs cell_args(const tfsi_handle* h, const Region& r, int nq, const double* 
     CellArgs a;
     a.coords = h->coords; a.cell_vertices = h->cell_vertices; a.cell_dofs = h->cell_dofs;
     a.colidx = h->colidx; a.rowptr = h->rowptr; a.cell_list = r.cell_list; a.rank_blk = r.rank_blk; a.dofs_blk = r.dofs_blk;
+    a.geo_blk = r.geo_blk;
     a.ncell_region = r.ncells; a.ndof = h->ndof; a.q0 = 0; a.nq = nq; a.rc = r.rc; a.x = x; a.x1 = x1; a.out = out;
     a.fill_pieces = nullptr; a.n_fill = 0; a.fill_scalar = nullptr; a.n_fill_scalar = 0; a.fill_dst = nullptr;
     a.massJ = nullptr; a.rank_v = nullptr;
     return a;
+}
+
+// cells per batch of the Jacobian kernel that runs the region (layout of rank_blk / dofs_blk / geo_blk / massJ)
+int region_ncta(const tfsi_handle* h, const Region& r) {
+    const bool fl = r.rc.kind == TFSI_KIND_FLUID;
+    if (h->gdim == 3) return fl ? FluidCfg<3>::L::NC : SolidCfg<3>::L::NC;
+    return fl ? FluidCfg<2>::L::NC : SolidCfg<2>::L::NC;
 }
 
 struct KernelTimer {
@@ -218,7 +228,7 @@ int launch_jacobian_region(tfsi_handle* h, const Region& r, const double* x, con
         if (is_fluid) a.massJ = r.massJ;
         else a.rank_v = r.rank_blk_v;
     }
-    const int ncta = is_fluid ? FluidCfg<G>::L::NC : SolidCfg<G>::L::NC;
+    const int ncta = region_ncta(h, r);
     const int grid = (int)((r.ncells + ncta - 1) / ncta);
     const bool energy = !is_fluid && r.rc.mat != MAT_SVK;        // energy-based solid model: tangent-table variant
     // (solid: sized as if the second rank table of the pair mode were always staged)
@@ -444,6 +454,7 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
         if (b0 >= b1) continue;
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
         a.dofs_blk = r.res_dofs_blk + (size_t)b0 * h->ndof * NC;         // batches [b0, b1) of the region
+        a.geo_blk = r.res_geo_blk ? r.res_geo_blk + (size_t)b0 * (G * G + 1) * NC : nullptr;
         a.cell_list = r.cell_list + b0 * NC;
         a.ncell_region = std::min<int64_t>(r.ncells - b0 * NC, (b1 - b0) * NC);
         KernelTimer kt(h, 2, st);
@@ -541,7 +552,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->fill_pieces); cudaFree(h->fill_scalar); cudaFree(h->row_flag);
     for (auto& b : h->bound) if (b.ready) cudaEventDestroy(b.ready);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
-    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); }
+    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); cudaFree(r.geo_blk); cudaFree(r.res_geo_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
@@ -685,7 +696,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
                 set_solid_model(r.rc, rg.material, rg.C01, rg.C10, rg.C11, rg.Jm, rg.viscoelasticity, rg.mu_visc, rg.lambda_visc);
             }
             r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
-            r.massJ = nullptr; r.rank_blk_v = nullptr; r.rank_v_elems = 0;
+            r.massJ = nullptr; r.rank_blk_v = nullptr; r.rank_v_elems = 0; r.geo_blk = nullptr; r.res_geo_blk = nullptr;
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
             if (!p->deterministic) {
@@ -750,7 +761,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         if (r.ncells == 0) continue;
         const int g3 = (g == 3);
         const bool fl = r.rc.kind == TFSI_KIND_FLUID;
-        const int ncta = g3 ? (fl ? FluidCfg<3>::L::NC : SolidCfg<3>::L::NC) : (fl ? FluidCfg<2>::L::NC : SolidCfg<2>::L::NC);
+        const int ncta = region_ncta(h, r);
         const int rks = ncta + 1;
         const int ncols = fl ? (2 * g * h->n2 + h->n1) : g * h->n2;
         const int ncoef = fl ? (2 * g * h->n2 + h->n1) : 2 * g * h->n2;
@@ -765,11 +776,27 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
             h->cell_dofs, h->rowptr, h->colidx, r.cell_list, r.ncells, h->ndof, h->n2, ncols, ncta, rks, r.rank_blk_elems, r.rank_blk, derr);
         build_dofs_blocked_kernel<<<grid_for(nb * ncoef * ncta, 256, h->sm_count), 256>>>(
             h->cell_dofs, r.cell_list, r.ncells, h->ndof, ncoef, ncta, r.dofs_blk);
+        {                                                    // staged geometry of the Jacobian kernels (80 B per tet)
+            double* gb = nullptr;
+            CKC(cka(cudaMalloc((void**)&gb, (size_t)nb * (g * g + 1) * ncta * sizeof(double))));
+            CellArgs ga = cell_args(h, r, 0, nullptr, nullptr, nullptr);
+            if (g3) build_geo_blocked_kernel<3><<<grid_for(nb * ncta, 128, h->sm_count), 128>>>(ga, ncta, gb);
+            else build_geo_blocked_kernel<2><<<grid_for(nb * ncta, 128, h->sm_count), 128>>>(ga, ncta, gb);
+            r.geo_blk = gb;
+        }
         if (h->res_nc) {                                     // residual kernel: [ndof][res_nc] per batch
             const int64_t nbr = (r.ncells + h->res_nc - 1) / h->res_nc;
             CKC(cka(cudaMalloc((void**)&r.res_dofs_blk, (size_t)nbr * h->ndof * h->res_nc * sizeof(int32_t))));
             build_dofs_blocked_kernel<<<grid_for(nbr * h->ndof * h->res_nc, 256, h->sm_count), 256>>>(
                 h->cell_dofs, r.cell_list, r.ncells, h->ndof, h->ndof, h->res_nc, r.res_dofs_blk);
+            {
+                double* gb = nullptr;
+                CKC(cka(cudaMalloc((void**)&gb, (size_t)nbr * (g * g + 1) * h->res_nc * sizeof(double))));
+                CellArgs ga = cell_args(h, r, 0, nullptr, nullptr, nullptr);
+                if (g3) build_geo_blocked_kernel<3><<<grid_for(nbr * h->res_nc, 128, h->sm_count), 128>>>(ga, h->res_nc, gb);
+                else build_geo_blocked_kernel<2><<<grid_for(nbr * h->res_nc, 128, h->sm_count), 128>>>(ga, h->res_nc, gb);
+                r.res_geo_blk = gb;
+            }
         }
     }
     {
@@ -813,7 +840,7 @@ int tfsi_assemble_A_pre(tfsi_handle* h, const double* x, const double* x1, doubl
     // tfsi_compress_A_pre recognises the array
     for (Region& r : h->regions) {
         if (r.ncells == 0 || r.rc.kind != TFSI_KIND_FLUID || !r.rc.fluid_on) continue;
-        const int ncta = h->gdim == 3 ? FluidCfg<3>::L::NC : FluidCfg<2>::L::NC;
+        const int ncta = region_ncta(h, r);
         const int64_t total = (r.ncells + ncta - 1) / ncta * ncta * h->tabJ.nq;
         if (!r.massJ) CK(h, cudaMalloc((void**)&r.massJ, (size_t)total * sizeof(double)));
         CellArgs a = cell_args(h, r, h->tabJ.nq, x, x1, nullptr);

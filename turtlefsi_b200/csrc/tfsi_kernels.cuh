@@ -63,6 +63,7 @@ struct CellArgs {
     const int32_t* cell_list;      // cells of this region
     const uint16_t* rank_blk;      // per CTA batch: [N2][NCOLS][RKS] ranks in the shared-memory layout
     const int32_t* dofs_blk;       // per CTA batch: [NCOEF][NC] dofs
+    const double* geo_blk;         // per CTA batch: [G*G+1][NC] K = J_geo^-1 and |det J_geo| (Jacobian kernels), or null
     int64_t ncell_region;
     int32_t ndof;                  // dofs per cell (27/39/64/94)
     int32_t q0;                    // first point of the quadrature chunk this launch integrates (rules larger than
@@ -177,6 +178,10 @@ __device__ __forceinline__ void stage_cells(const CellArgs& a, int32_t* scell, d
 {
     constexpr int NC = L::NC;
     const int c = threadIdx.x;
+    if (a.geo_blk) {       // pre-blocked at set-up: one coalesced load instead of cell list -> vertices -> coordinates
+        for (int i = c; i < (G * G + 1) * NC; i += blockDim.x) sgeo[i] = a.geo_blk[(size_t)blockIdx.x * ((G * G + 1) * NC) + i];
+        return;
+    }
     if (c < NC) {
         const int64_t idx = (int64_t)blockIdx.x * NC + c;
         const int32_t cell = a.cell_list[idx < a.ncell_region ? idx : a.ncell_region - 1];
@@ -230,6 +235,24 @@ __global__ void build_rank_blocked_kernel(const int32_t* cell_dofs, const int64_
         out[(size_t)b * blk_elems + ((size_t)i * ncols + col) * rks + c] = rk;
     }
 }
+// per-batch geometry [G*G+1][NC] of the cells of a region (reference configuration: constant for the run)
+template <int G>
+__global__ void build_geo_blocked_kernel(CellArgs a, int nc_cta, double* out)
+{
+    const int64_t nb = (a.ncell_region + nc_cta - 1) / nc_cta;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nb * nc_cta; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % nc_cta);
+        const int64_t b = t / nc_cta;
+        const int64_t idx = t < a.ncell_region ? t : a.ncell_region - 1;
+        double K[G][G];
+        const double adet = load_geometry<G>(a, a.cell_list[idx], K);
+        double* o = out + (size_t)b * ((G * G + 1) * nc_cta);
+        for (int s = 0; s < G; ++s)
+            for (int u = 0; u < G; ++u) o[(s * G + u) * nc_cta + c] = K[s][u];
+        o[G * G * nc_cta + c] = adet;
+    }
+}
+
 __global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells,
                                           int ndof, int ncoef, int nc_cta, int32_t* out)
 {
@@ -975,7 +998,10 @@ __global__ void __launch_bounds__(NC * 8, (NC == 32 ? 1 : 2)) residual_kernel(Ce
         double xv[PER], x1v[PER];
 #pragma unroll
         for (int u = 0; u < PER; ++u) { xv[u] = a.x[dof[u]]; x1v[u] = a.x1[dof[u]]; }
-        if (threadIdx.x < NC) {
+        if (a.geo_blk) {     // pre-blocked at set-up: one coalesced load instead of cell list -> vertices -> coordinates
+            for (int i = threadIdx.x; i < (G * G + 1) * NC; i += NC * 8)
+                sgeo[i] = a.geo_blk[(size_t)blockIdx.x * ((G * G + 1) * NC) + i];
+        } else if (threadIdx.x < NC) {
             const int c = threadIdx.x;
             const int64_t ci = (int64_t)blockIdx.x * NC + c;
             const int64_t cell = a.cell_list[ci < a.ncell_region ? ci : a.ncell_region - 1];
