@@ -253,3 +253,35 @@ def test_form_language_functionals_and_loads():
         df.assemble(form)                                       # vectors belong to the kernels
     with pytest.raises(NotImplementedError):
         df.derivative(form, f)
+
+
+def test_problem_file_writes_its_own_xdmf_series(tmp_path):
+    """a problem file that stores fields itself (`XDMFFile(...).write(f, t)` in post_solve, as the reference's
+    save_files_visualization does, problems/__init__.py:232-237,319-323) gets a readable time series of vertex values."""
+    from turtlefsi_b200.compat import load_problem_file
+    from turtlefsi_b200.utils.xdmf import read_series
+    mod = load_problem_file(os.path.join(HERE, "dolfin_dialect", "turek_flag.py"))
+    files = {k: mod.XDMFFile(mod.MPI.comm_world, str(tmp_path / (k + ".xdmf"))) for k in ("v", "p", "dy")}
+    files["v"].parameters["flush_output"] = True
+    orig, last = mod.mod.post_solve, {}                  # the file's own hook (the wrapper hands it the DOLFIN-flavoured namespace)
+
+    def post_solve(**ns):
+        out = orig(**ns)
+        dvp = ns["dvp_"]["n"]
+        v = dvp.sub(1, deepcopy=True)
+        v.rename("Velocity", "v")
+        files["v"].write(v, ns["t"])
+        files["p"].write(dvp.sub(2, deepcopy=True), ns["t"])
+        files["dy"].write(dvp.sub(0).sub(1), ns["t"])
+        last["x"] = np.array(dvp.vector().get_local())
+        return out
+    mod.mod.post_solve = post_solve
+    ns = _run_oracle(mod, dict(T=0.01, dt=0.01, verbose=False))
+    mesh, space, x = ns["mesh"], ns["DVP"], last["x"]
+    coords, cells, steps = read_series(str(tmp_path / "v.xdmf"))
+    assert np.array_equal(coords, mesh.coords) and np.array_equal(cells, mesh.cells) and len(steps) == 2
+    assert steps[-1][1] == "Velocity" and steps[-1][2].shape == (mesh.num_vertices, 3)
+    for a in range(2):
+        assert np.array_equal(steps[-1][2][:, a], x[space.node_dof(1, a)[space.vertex_node]])
+    assert np.array_equal(read_series(str(tmp_path / "p.xdmf"))[2][-1][2][:, 0], x[space.vertex_dof_p()])
+    assert np.array_equal(read_series(str(tmp_path / "dy.xdmf"))[2][-1][2][:, 0], x[space.node_dof(0, 1)[space.vertex_node]])

@@ -275,3 +275,64 @@ def test_translation_of_the_displacement_changes_nothing():
     assert np.abs(b - bs).max() < 1e-12 * np.abs(b).max()
     A, As = ora.assemble_jacobian(x, x1), ora.assemble_jacobian(xs, x1s)
     assert np.abs(A - As).max() < 1e-12 * np.abs(A).max()
+
+
+def test_visualization_output_is_a_readable_xdmf_series(tmp_path):
+    """problems/__init__.py:222-323 + monolithic.py:192-194: displacement / velocity / pressure series, one stored step
+    per `save_step` steps; save_deg 1 = vertex values, save_deg 2 = the P2 fields as P1 fields on the refined mesh (the
+    pressure stays on the original mesh). Heavy data is raw binary (no h5py here); read back with utils.xdmf.read_series."""
+    from turtlefsi_b200.utils.xdmf import read_series
+    for save_deg in (1, 2):
+        folder = str(tmp_path / ("viz%d" % save_deg))
+        ns = _run(4, T=0.03, visualization_folder=folder, save_step=2, save_deg=save_deg)
+        mesh, space = ns["mesh"], ns["DVP"]
+        x = np.asarray(ns["dvp_"]["n"])
+        series = {k: read_series(os.path.join(folder, k + ".xdmf")) for k in ("displacement", "velocity", "pressure")}
+        for k, (coords, cells, steps) in series.items():
+            assert [round(t / 0.01) for t, _, _ in steps] == [1, 3]            # counters 0 and 2 of the four steps
+            assert {name for _, name, _ in steps} == {k.capitalize()}
+        coords, cells, steps = series["velocity"]
+        if save_deg == 1:
+            assert np.array_equal(coords, mesh.coords) and np.array_equal(cells, mesh.cells)
+            nodes = space.vertex_node
+        else:
+            assert coords.shape[0] == space.num_nodes and cells.shape[0] == 4 * mesh.num_cells
+            assert np.allclose(coords, space.node_coords(mesh))
+            X = coords[cells]                                               # the sub-triangles tile every cell
+            area = 0.5 * np.abs(np.linalg.det(X[:, 1:] - X[:, :1]))
+            assert abs(area.sum() - 4.0) < 1e-12 and area.min() > 0.24 * area.max()
+            nodes = np.arange(space.num_nodes)
+        # ns holds the LAST step (counter 3); the stored ones are earlier, so compare structure and magnitudes only ...
+        assert steps[-1][2].shape == (len(nodes), 3) and np.all(steps[-1][2][:, 2] == 0.0)
+        assert np.abs(steps[-1][2][:, :2]).max() < 2 * np.abs(x[space.sub_dofs(1)]).max() + 1e-12
+        pc, pcells, psteps = series["pressure"]
+        assert np.array_equal(pc, mesh.coords) and np.array_equal(pcells, mesh.cells) and psteps[0][2].shape == (mesh.num_vertices, 1)
+    # ... and the values exactly on a run whose last step IS a stored one
+    folder = str(tmp_path / "exact")
+    ns = _run(4, T=0.02, visualization_folder=folder, save_step=2, save_deg=2)
+    x, space = np.asarray(ns["dvp_"]["n"]), ns["DVP"]
+    _, _, steps = read_series(os.path.join(folder, "velocity.xdmf"))
+    assert len(steps) == 2
+    for a in range(2):
+        assert np.array_equal(steps[-1][2][:, a], x[space.node_dof(1, a)])
+    _, _, psteps = read_series(os.path.join(folder, "pressure.xdmf"))
+    assert np.array_equal(psteps[-1][2][:, 0], x[space.vertex_dof_p()])
+    import pytest
+    with pytest.raises(ValueError, match="save_deg"):
+        _run(4, T=0.01, visualization_folder=str(tmp_path / "bad"), save_step=1, save_deg=3)
+
+
+def test_refined_visualization_cells_tile_the_p2_cells_in_3d():
+    """save_deg = 2 in 3-D: every P2 tetrahedron becomes eight P1 tetrahedra on its ten nodes, each an eighth of it."""
+    from turtlefsi_b200.mesh import box_mesh
+    from turtlefsi_b200.space import MixedSpace
+    from turtlefsi_b200.utils.xdmf import p2_refined_cells
+    mesh = box_mesh(2)
+    space = MixedSpace(mesh)
+    sub = p2_refined_cells(space.cell_nodes, 3)
+    X = space.node_coords(mesh)[sub]
+    vol = np.abs(np.linalg.det(X[:, 1:] - X[:, :1])) / 6
+    Xp = mesh.coords[mesh.cells]
+    parent = np.abs(np.linalg.det(Xp[:, 1:] - Xp[:, :1])) / 6
+    assert sub.shape == (8 * mesh.num_cells, 4) and abs(vol.sum() - 1.0) < 1e-13
+    assert np.allclose(vol.reshape(8, -1), parent[None, :] / 8, rtol=1e-12)

@@ -9,7 +9,7 @@ residual / Jacobian assembly — never goes through here. It is put on `sys.path
 INTEGRATION.md §A applies instead.
 
 Not provided (raise NotImplementedError): C++ string `Expression`s, symbolic `derivative`, `solve`, `project`,
-XDMF output, MPI-parallel meshes (multi-GPU runs shard through turtlefsi_b200.distributed instead)."""
+XDMF `write_checkpoint`, MPI-parallel meshes (multi-GPU runs shard through turtlefsi_b200.distributed instead)."""
 import copy as _copy
 import os as _os
 
@@ -315,6 +315,8 @@ class XDMFFile:
     def __init__(self, *args):
         self.path = str(args[-1])
         self._data = None
+        self._series = None
+        self.parameters = {}          # flush_output / rewrite_function_mesh (problems/__init__.py:235-237): always so here
 
     def _load(self):
         if self._data is None:
@@ -344,7 +346,27 @@ class XDMFFile:
     def __exit__(self, *a):
         pass
 
-    write = write_checkpoint = _unsupported("XDMFFile.write", "visualisation output is out of scope (SURVEY 8f-4)")
+    def write(self, f, t=0.0):
+        """XDMFFile.write(function, t) (problems/__init__.py:319-323): the VERTEX values of a sub-function (d, v, p or one
+        component) as a step of a time series — DOLFIN's `write` stores CG2 functions by their vertex values too. Heavy
+        data is raw binary beside the .xdmf file (turtlefsi_b200.utils.xdmf; no h5py in this image)."""
+        from turtlefsi_b200.utils.xdmf import XDMFSeries
+        if not isinstance(f, Function) or f.field is None:
+            raise NotImplementedError("XDMFFile.write of %r: write the sub-functions of the mixed function" % type(f).__name__)
+        space, x = f.space, np.asarray(f._host(), dtype=float)
+        if self._series is None:
+            m = f._V.mesh().native
+            _os.makedirs(_os.path.dirname(self.path) or ".", exist_ok=True)
+            self._series = XDMFSeries(self.path, m.coords, m.cells)
+        if f.field == 2:
+            vals = x[space.vertex_dof_p()]
+        elif f.comp is not None:
+            vals = x[space.node_dof(f.field, f.comp)[space.vertex_node]]
+        else:
+            vals = np.stack([x[space.node_dof(f.field, a)[space.vertex_node]] for a in range(space.gdim)], axis=1)
+        self._series.write(getattr(f, "_name", "f"), vals, t)
+
+    write_checkpoint = _unsupported("XDMFFile.write_checkpoint", "checkpoints are numpy files (turtlefsi_b200/problems/__init__.py)")
 
 
 HDF5File = _unsupported("HDF5File", "mesh/field storage goes through numpy files (turtlefsi_b200/problems/__init__.py)")
@@ -730,8 +752,8 @@ class Function(_u.FieldExpr):
         f._store(np.array(self._host(), dtype=float))
         return f
 
-    def rename(self, *a):
-        pass
+    def rename(self, name, *a):
+        self._name = str(name)
 
     def __call__(self, *x):
         if len(x) == 1 and isinstance(x[0], str):

@@ -130,7 +130,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
     # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them
-    from .problems import checkpoint, start_from_checkpoint
+    from .problems import checkpoint, save_files_visualization, start_from_checkpoint
     if ns.get("restart_folder") is not None:
         start_from_checkpoint(**ns)
     if ns.get("results_folder") is not None:
@@ -156,6 +156,9 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
         if ns.get("checkpoint_folder") is not None and counter % ns["checkpoint_step"] == 0:               # :193-195
             ns.update(t=t, counter=counter)
             checkpoint(**ns)
+        if ns.get("visualization_folder") is not None and counter % ns["save_step"] == 0:                 # :192-194
+            ns.update(t=t, counter=counter)
+            ns.update(save_files_visualization(**ns))
         counter += 1
         if max_steps is not None and counter >= max_steps:
             stop = True

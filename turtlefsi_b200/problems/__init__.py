@@ -1,7 +1,8 @@
 """turtleFSI/problems/__init__.py counterpart: `default_variables` (same keys and values:
 reference :41-117), the default problem-file hooks (reference :465-523) and checkpoint / restart
-(reference :183-219, :361-381) with numpy files instead of XDMF/HDF5. Visualisation output and the
-kill/pause files are out of scope of this repository."""
+(reference :183-219, :361-381) with numpy files instead of XDMF/HDF5, and the visualisation output
+(reference :222-323) as XDMF time series with raw binary heavy data (turtlefsi_b200.utils.xdmf; h5py is not in
+this image). The kill/pause files are out of scope of this repository."""
 import json
 import os
 
@@ -109,3 +110,45 @@ def start_from_checkpoint(dvp_, restart_folder, assembler, **namespace):
     xd = assembler.to_device(x1)
     assembler.copy(dvp_["n-1"], xd)
     assembler.copy(dvp_["n"], xd)
+
+
+def save_files_visualization(visualization_folder, dvp_, t, save_deg, v_deg, p_deg, mesh, DVP, assembler, **namespace):
+    """reference :222-305: displacement.xdmf, velocity.xdmf and pressure.xdmf in the Visualization folder, one stored
+    step per call. save_deg == 1 stores the values at the mesh vertices; save_deg == 2 stores the P2 fields d and v as
+    P1 fields on the uniformly refined mesh (the reference interpolates with a transfer matrix onto `refine(mesh)`: for
+    nodal P2 fields those are the dof values at the vertices and edge mid-points themselves) and the pressure, whose
+    degree is below save_deg, on the original mesh (reference :293-298). Returns the file handles on the first call
+    (the driver merges them into its namespace, monolithic.py:193-194), {} afterwards."""
+    from ..utils.xdmf import XDMFSeries, p2_refined_cells
+    if save_deg > v_deg:
+        raise ValueError("save_deg must be less than or equal to v_deg")
+    x = np.asarray(assembler.to_host(dvp_["n"]), dtype=np.float64)        # gathered global vector (collective)
+    if getattr(assembler, "rank", 0) != 0:
+        return {}
+    g = mesh.gdim
+    refined = save_deg > 1 and v_deg >= save_deg
+    return_dict = {}
+    if "d_file" not in namespace:
+        os.makedirs(str(visualization_folder), exist_ok=True)
+        if refined:
+            coords_dv, cells_dv = DVP.node_coords(mesh), p2_refined_cells(DVP.cell_nodes, g)
+        else:
+            coords_dv, cells_dv = mesh.coords, mesh.cells
+        names = dict(d_file="displacement.xdmf", v_file="velocity.xdmf", p_file="pressure.xdmf")
+        return_dict = {k: XDMFSeries(os.path.join(str(visualization_folder), f),
+                                     *((mesh.coords, mesh.cells) if k == "p_file" else (coords_dv, cells_dv)))
+                       for k, f in names.items()}
+        namespace.update(return_dict)
+    nodes = np.arange(DVP.num_nodes) if refined else DVP.vertex_node
+    d = np.stack([x[DVP.node_dof(0, a)[nodes]] for a in range(g)], axis=1)
+    v = np.stack([x[DVP.node_dof(1, a)[nodes]] for a in range(g)], axis=1)
+    p = x[DVP.vertex_dof_p()]
+    write_solution(d, v, p, namespace["d_file"], namespace["v_file"], namespace["p_file"], t)
+    return return_dict
+
+
+def write_solution(d, v, p, d_file, v_file, p_file, t):
+    """reference :308-323: the names ParaView shows."""
+    d_file.write("Displacement", d, t)
+    v_file.write("Velocity", v, t)
+    p_file.write("Pressure", p, t)
