@@ -336,3 +336,27 @@ def test_refined_visualization_cells_tile_the_p2_cells_in_3d():
     parent = np.abs(np.linalg.det(Xp[:, 1:] - Xp[:, :1])) / 6
     assert sub.shape == (8 * mesh.num_cells, 4) and abs(vol.sum() - 1.0) < 1e-13
     assert np.allclose(vol.reshape(8, -1), parent[None, :] / 8, rtol=1e-12)
+
+
+def test_kill_and_pause_files_stop_and_hold_the_run(tmp_path):
+    """problems/__init__.py:326-358 + monolithic.py:203-212: `killturtle` in the results folder (or `killtime`) ends the
+    run cleanly behind a checkpoint, `pauseturtle` holds it until the file is removed."""
+    import threading
+    import time
+    folder = tmp_path / "run"
+    folder.mkdir()
+    (folder / "killturtle").write_text("")
+    ns = _run(4, T=0.05, results_folder=str(folder), checkpoint_step=1000)
+    assert len(ns["error_v_list"]) == 1 and not (folder / "killturtle").exists()
+    assert os.path.exists(folder / "Checkpoint" / "checkpoint_fields.npy")          # written by the kill, not by the step count
+    again = _run(4, T=0.02, restart_folder=str(folder))
+    assert again["first_step_num"] == 1
+    timed = _run(4, T=0.05, results_folder=str(tmp_path / "timed"), killtime=0.0)
+    assert len(timed["error_v_list"]) == 1
+    hold = tmp_path / "hold"
+    hold.mkdir()
+    (hold / "pauseturtle").write_text("")
+    threading.Timer(0.6, lambda: (hold / "pauseturtle").unlink()).start()
+    t0 = time.time()
+    ns = _run(4, T=0.005, results_folder=str(hold), pause_poll_seconds=0.05)
+    assert time.time() - t0 > 0.5 and len(ns["error_v_list"]) == 1

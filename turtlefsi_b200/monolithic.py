@@ -5,6 +5,7 @@ physics modules (selected BY NAME with the same --fluid/--solid/--extrapolation/
 post_solve) -> finished. Every hook is called as f(**namespace) and its returned dict is merged
 back, as the reference does with vars().update(...)."""
 import copy
+import time
 import importlib
 
 from .problems import default_variables as _defaults
@@ -130,7 +131,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
     # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them
-    from .problems import checkpoint, save_files_visualization, start_from_checkpoint
+    from .problems import check_if_kill, check_if_pause, checkpoint, save_files_visualization, start_from_checkpoint
     if ns.get("restart_folder") is not None:
         start_from_checkpoint(**ns)
     if ns.get("results_folder") is not None:
@@ -141,6 +142,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     counter = ns["counter"]
     ns["first_step_num"] = counter                                                                    # :168
     stop = False
+    t_start = time.time()
     while t <= T + dt / 10 and not stop:                                                              # :169
         t += dt
         ns.update(t=t, counter=counter)
@@ -160,6 +162,13 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
             ns.update(t=t, counter=counter)
             ns.update(save_files_visualization(**ns))
         counter += 1
+        if ns.get("results_folder") is not None:                                                      # :203-212
+            while check_if_pause(ns["results_folder"]):
+                time.sleep(ns.get("pause_poll_seconds", 5))
+            if check_if_kill(ns["results_folder"], ns.get("killtime"), time.time() - t_start):
+                ns.update(t=t, counter=counter)
+                checkpoint(**ns)
+                stop = True
         if max_steps is not None and counter >= max_steps:
             stop = True
     ns.update(t=t, counter=counter)

@@ -2,7 +2,7 @@
 reference :41-117), the default problem-file hooks (reference :465-523) and checkpoint / restart
 (reference :183-219, :361-381) with numpy files instead of XDMF/HDF5, and the visualisation output
 (reference :222-323) as XDMF time series with raw binary heavy data (turtlefsi_b200.utils.xdmf; h5py is not in
-this image). The kill/pause files are out of scope of this repository."""
+this image), and the kill / pause files (reference :326-358)."""
 import json
 import os
 
@@ -152,3 +152,47 @@ def write_solution(d, v, p, d_file, v_file, p_file, t):
     d_file.write("Displacement", d, t)
     v_file.write("Velocity", v, t)
     p_file.write("Pressure", p, t)
+
+
+def _any_rank(found):
+    """MPI.sum(MPI.comm_world, found) > 0 of the reference (:331,:352): every rank takes the same decision."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            import torch
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([int(bool(found))], device=dev)
+            dist.all_reduce(t)
+            return int(t.item()) > 0
+    except ImportError:
+        pass
+    return bool(found)
+
+
+def check_if_kill(folder, killtime, elapsed_time):
+    """reference :326-345: a file named `killturtle` in the results folder (removed by rank 0), or `killtime` seconds
+    of wall time, stop the run cleanly (the driver writes a checkpoint first, monolithic.py:209-212).
+    `elapsed_time`: seconds since the start of the run (the reference passes its DOLFIN Timer)."""
+    from pathlib import Path
+    kill = Path(folder) / "killturtle"
+    if _any_rank(kill.exists()):
+        if int(os.environ.get("RANK", "0")) == 0 and kill.exists():
+            kill.unlink()
+            print("killturtle Found! Stopping simulations cleanly...")
+        return True
+    if _any_rank(killtime is not None and killtime <= float(elapsed_time)):
+        if int(os.environ.get("RANK", "0")) == 0:
+            print("Given killtime reached! Stopping simulations cleanly...")
+        return True
+    return False
+
+
+def check_if_pause(folder):
+    """reference :348-358: a file named `pauseturtle` in the results folder pauses the run until it is removed."""
+    from pathlib import Path
+    pause = Path(folder) / "pauseturtle"
+    if _any_rank(pause.exists()):
+        if int(os.environ.get("RANK", "0")) == 0:
+            print("pauseturtle Found! Simulations paused. Remove " + str(pause) + " to resume simulations...")
+        return True
+    return False
