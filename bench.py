@@ -568,7 +568,7 @@ def roofline_of(w, m, steps):
     tnote = "no ncu capture of this launch is committed"
     # the capture that matches the mode of this run: r3 = matrix pair (the fluid launch also zero-fills the idle matrix),
     # r2 = single matrix
-    tp = os.path.join(ROOT, "profiles", "r3_fluid_traffic.json" if w.pair else "r2_fluid_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r4_fluid_traffic.json" if w.pair else "r2_fluid_traffic.json")
     if os.path.exists(tp):
         t = json.load(open(tp))
         traffic = t["dram_bytes_per_cell"] * n_fluid
