@@ -26,6 +26,7 @@ struct Region {
     int32_t colour;       // colour class (deterministic mode), else 0
     int64_t ncells;
     int32_t* cell_list;   // device
+    int32_t* res_cell_list; // device: the same cells ordered by their largest dof (residual batches; null = cell_list)
     uint16_t* rank_blk;   // device, per CTA batch (Jacobian kernels)
     int32_t* dofs_blk;    // device, per CTA batch
     int32_t* res_dofs_blk; // device, per residual CTA batch: [ndof][res_nc]
@@ -455,7 +456,7 @@ int launch_residual_nc(tfsi_handle* h, const double* x, const double* x1, double
         CellArgs a = cell_args(h, r, h->tabR.nq, x, x1, b);
         a.dofs_blk = r.res_dofs_blk + (size_t)b0 * h->ndof * NC;         // batches [b0, b1) of the region
         a.geo_blk = r.res_geo_blk ? r.res_geo_blk + (size_t)b0 * (G * G + 1) * NC : nullptr;
-        a.cell_list = r.cell_list + b0 * NC;
+        a.cell_list = (r.res_cell_list ? r.res_cell_list : r.cell_list) + b0 * NC;
         a.ncell_region = std::min<int64_t>(r.ncells - b0 * NC, (b1 - b0) * NC);
         KernelTimer kt(h, 2, st);
         residual_kernel<G, BIH, NC, LIFT><<<(unsigned)(b1 - b0), NC * 8, smem, st>>>(a);
@@ -552,7 +553,7 @@ void tfsi_destroy(tfsi_handle* h) {
     cudaFree(h->fill_pieces); cudaFree(h->fill_scalar); cudaFree(h->row_flag);
     for (auto& b : h->bound) if (b.ready) cudaEventDestroy(b.ready);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
-    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); cudaFree(r.geo_blk); cudaFree(r.res_geo_blk); }
+    for (Region& r : h->regions) { cudaFree(r.cell_list); cudaFree(r.res_cell_list); cudaFree(r.rank_blk); cudaFree(r.dofs_blk); cudaFree(r.res_dofs_blk); cudaFree(r.massJ); cudaFree(r.rank_blk_v); cudaFree(r.geo_blk); cudaFree(r.res_geo_blk); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
@@ -695,7 +696,7 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
                 }
                 set_solid_model(r.rc, rg.material, rg.C01, rg.C10, rg.C11, rg.Jm, rg.viscoelasticity, rg.mu_visc, rg.lambda_visc);
             }
-            r.cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
+            r.cell_list = nullptr; r.res_cell_list = nullptr; r.rank_blk = nullptr; r.dofs_blk = nullptr; r.res_dofs_blk = nullptr; r.rank_blk_elems = r.dofs_blk_elems = 0;
             r.massJ = nullptr; r.rank_blk_v = nullptr; r.rank_v_elems = 0; r.geo_blk = nullptr; r.res_geo_blk = nullptr;
             std::vector<int32_t> list;
             for (int64_t c = 0; c < h->nc; ++c) if (marker[(size_t)c] == rg.marker) list.push_back((int32_t)c);
@@ -786,13 +787,34 @@ int tfsi_create(const tfsi_problem* p, tfsi_handle** out) {
         }
         if (h->res_nc) {                                     // residual kernel: [ndof][res_nc] per batch
             const int64_t nbr = (r.ncells + h->res_nc - 1) / h->res_nc;
+            if (!p->deterministic) {
+                // The residual batches take the region's cells in the order of their LARGEST dof: the host entry uploads the
+                // iterate in chunks of consecutive dofs and starts a batch when the chunk holding its largest dof has
+                // arrived. In the region's own (Morton) order a single cell across a high-order Morton boundary raises the
+                // prefix maximum for every later batch, and the residual then waits for late chunks (6.0 ms of wall time
+                // for 5.5 ms of kernels in the end-to-end call). Neighbouring cells still sit in neighbouring batches.
+                int32_t *keys = nullptr, *keys_out = nullptr;
+                void* tmp = nullptr;
+                size_t tmp_bytes = 0;
+                CKC(cka(cudaMalloc((void**)&keys, (size_t)r.ncells * sizeof(int32_t))));
+                CKC(cka(cudaMalloc((void**)&keys_out, (size_t)r.ncells * sizeof(int32_t))));
+                CKC(cka(cudaMalloc((void**)&r.res_cell_list, (size_t)r.ncells * sizeof(int32_t))));
+                cell_max_dof_kernel<<<grid_for(r.ncells, 256, h->sm_count), 256>>>(h->cell_dofs, r.cell_list, r.ncells, h->ndof, keys);
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, r.cell_list, r.res_cell_list, (int)r.ncells);
+                CKC(cka(cudaMalloc(&tmp, tmp_bytes)));
+                cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, r.cell_list, r.res_cell_list, (int)r.ncells);
+                CKC(cka(cudaDeviceSynchronize()));
+                cudaFree(tmp); cudaFree(keys); cudaFree(keys_out);
+            }
+            const int32_t* rlist = r.res_cell_list ? r.res_cell_list : r.cell_list;
             CKC(cka(cudaMalloc((void**)&r.res_dofs_blk, (size_t)nbr * h->ndof * h->res_nc * sizeof(int32_t))));
             build_dofs_blocked_kernel<<<grid_for(nbr * h->ndof * h->res_nc, 256, h->sm_count), 256>>>(
-                h->cell_dofs, r.cell_list, r.ncells, h->ndof, h->ndof, h->res_nc, r.res_dofs_blk);
+                h->cell_dofs, rlist, r.ncells, h->ndof, h->ndof, h->res_nc, r.res_dofs_blk);
             {
                 double* gb = nullptr;
                 CKC(cka(cudaMalloc((void**)&gb, (size_t)nbr * (g * g + 1) * h->res_nc * sizeof(double))));
                 CellArgs ga = cell_args(h, r, 0, nullptr, nullptr, nullptr);
+                ga.cell_list = rlist;
                 if (g3) build_geo_blocked_kernel<3><<<grid_for(nbr * h->res_nc, 128, h->sm_count), 128>>>(ga, h->res_nc, gb);
                 else build_geo_blocked_kernel<2><<<grid_for(nbr * h->res_nc, 128, h->sm_count), 128>>>(ga, h->res_nc, gb);
                 r.res_geo_blk = gb;
@@ -1243,6 +1265,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
     if (bcs) CK(h, cudaMemcpyAsync(h->hg, g_host, (size_t)h->nbc * sizeof(double), cudaMemcpyHostToDevice, io));
     static const int max_chunks = getenv("TFSI_H2D_CHUNKS") ? atoi(getenv("TFSI_H2D_CHUNKS")) : 8;
     const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(max_chunks, h->N / (1 << 20)));
+    auto chunk_end = [&](int k) -> int64_t { return h->N * (k + 1) / nchunk; };    // (doubling chunk sizes: no gain)
     if (h->res_nc && nchunk > 1) {
         for (Region& r : h->regions) {
             if (r.ncells == 0 || !r.res_pmax.empty() || !r.res_dofs_blk) continue;
@@ -1263,7 +1286,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
         h->ev_chunk.push_back(e);
     }
     for (int k = 0; k < nchunk; ++k) {
-        const int64_t lo = h->N * k / nchunk, hi = h->N * (k + 1) / nchunk;
+        const int64_t lo = k ? chunk_end(k - 1) : 0, hi = chunk_end(k);
         CK(h, cudaMemcpyAsync(h->hx + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, io));
         if (x1_host) CK(h, cudaMemcpyAsync(h->hx1 + lo, x1_host + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, io));
         CK(h, cudaEventRecord(h->ev_chunk[(size_t)k], io));
@@ -1278,7 +1301,7 @@ int tfsi_newton_assemble_host(tfsi_handle* h, const double* x_host, const double
     {
         std::vector<std::pair<int64_t, int64_t>> ranges(h->regions.size(), std::make_pair((int64_t)0, (int64_t)0));
         for (int k = 0; k < nchunk; ++k) {
-            const int64_t hi = h->N * (k + 1) / nchunk;
+            const int64_t hi = chunk_end(k);
             bool any = false;
             for (size_t ri = 0; ri < h->regions.size(); ++ri) {
                 const Region& r = h->regions[ri];

@@ -253,6 +253,17 @@ __global__ void build_geo_blocked_kernel(CellArgs a, int nc_cta, double* out)
     }
 }
 
+// largest global dof of every cell of a region (sort key of the residual's own cell order, see tfsi_create)
+__global__ void cell_max_dof_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells, int ndof, int32_t* out)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t* d = cell_dofs + (int64_t)cell_list[t] * ndof;
+        int32_t m = 0;
+        for (int k = 0; k < ndof; ++k) m = max(m, d[k]);
+        out[t] = m;
+    }
+}
+
 __global__ void build_dofs_blocked_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells,
                                           int ndof, int ncoef, int nc_cta, int32_t* out)
 {
