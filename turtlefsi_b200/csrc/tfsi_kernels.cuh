@@ -1388,56 +1388,6 @@ __global__ void bitmap_stream_kernel(const uint32_t* bitmap, int64_t nwords, con
     }
 }
 
-// BACKGROUND re-initialisation of the idle matrix of a pair (tfsi_bind_matrix_pair) while the FP64-bound Jacobian
-// kernels run: dst[k] = src[k] (src = the dense A_pre) for the 64-entry word pairs of the rows the cell kernels scatter
-// into. A plain masked copy: loads are independent of each other (no bitmap / prefix / packed-value chain as in the
-// expansion above), so that ONE 32-register warp per SM sub-partition — what the 3 x 160-register warps of the Jacobian
-// CTAs leave free — keeps enough bytes in flight. A warp owns 32 consecutive groups (lane l fetches the mask of group l),
-// copies BG_BATCH pairs (512 B each) per round trip; many short blocks on a lowest-priority stream fill the gap on every SM.
-constexpr int BG_GROUPS_PER_WARP = 32;
-#ifndef BG_BATCH
-#define BG_BATCH 4
-#endif
-template <bool STATS>
-__global__ void __launch_bounds__(128, 16) masked_copy_bg_kernel(const uint32_t* tmask, int64_t ngroups, int64_t nnz,
-                                                                 const double* src, double* dst, int* smid_count)
-{
-    const int lane = threadIdx.x & 31;
-    if (STATS && threadIdx.x == 0) {               // placement statistics: blocks per SM (tfsi_debug_bg_placement)
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        atomicAdd(smid_count + (smid & 255), 1);
-    }
-    // persistent: the grid is ONE block per SM (launched on an idle device, before the Jacobian kernel, on a stream of
-    // higher priority), every warp strides over chunks of 32 groups. 32-bit group arithmetic (ngroups < 2^31) and a
-    // running pointer keep the kernel inside its 32 registers without spills.
-    const int ng = (int)ngroups, stride = (int)gridDim.x * 4 * BG_GROUPS_PER_WARP;
-    const int64_t nlim = nnz - 1;
-    for (int g0 = ((int)blockIdx.x * 4 + (int)(threadIdx.x >> 5)) * BG_GROUPS_PER_WARP; g0 < ng; g0 += stride) {
-        const uint32_t mytm = (g0 + lane < ng) ? tmask[g0 + lane] : 0u;
-        // pair mask of my group: bit j = word pair j (entries 64 j .. 64 j + 63 of the group) is to be copied
-        uint32_t pm = (mytm | (mytm >> 1)) & 0x55555555u;      // bit 2j set if either word of pair j is
-        pm = (pm | (pm >> 1)) & 0x33333333u; pm = (pm | (pm >> 2)) & 0x0f0f0f0fu;
-        pm = (pm | (pm >> 4)) & 0x00ff00ffu; pm = (pm | (pm >> 8)) & 0x0000ffffu;          // compacted to 16 bits
-        for (int g = 0; g < BG_GROUPS_PER_WARP; ++g) {
-            uint32_t p = __shfl_sync(0xffffffffu, pm, g);         // warp-uniform
-            int64_t k = (int64_t)(g0 + g) * 1024 + 2 * lane;
-            for (; p != 0u; p >>= BG_BATCH, k += BG_BATCH * 64) {
-                if ((p & ((1u << BG_BATCH) - 1u)) == 0u) continue;
-                double2 v[BG_BATCH];
-#pragma unroll
-                for (int j = 0; j < BG_BATCH; ++j)
-                    if (((p >> j) & 1u) && k + j * 64 < nlim) v[j] = __ldcs(reinterpret_cast<const double2*>(src + k + j * 64));
-#pragma unroll
-                for (int j = 0; j < BG_BATCH; ++j)
-                    if (((p >> j) & 1u) && k + j * 64 < nlim) __stcs(reinterpret_cast<double2*>(dst + k + j * 64), v[j]);
-            }
-        }
-    }
-    // the last (odd) entry of the matrix, if any, is not covered by the 16-byte copies
-    if (blockIdx.x == 0 && threadIdx.x == 0 && (nnz & 1)) dst[nnz - 1] = src[nnz - 1];
-}
-
 // rows that the non-linear Jacobian kernels scatter into: the local dofs [lo, hi) of every cell of a region
 __global__ void mark_rows_kernel(const int32_t* cell_dofs, const int32_t* cell_list, int64_t ncells, int ndof,
                                  int lo, int hi, uint8_t* flag)
