@@ -41,13 +41,20 @@ def make_asm(mesh, space, regions, ns):
         mk = lambda view: OracleAssembler(view.mesh, view.space, regions, common, degJ, 10, use_c_port=True)
     return make_distributed(mesh, space, mk, biharmonic=space.biharmonic, use_gpu_halo=gpu)
 
-ns = monolithic.run("TF_fsi", make_asm, GatheredLU, overrides=dict(T=%(T)r, dt=0.01, theta=0.51, verbose=False))
+ns = monolithic.run("TF_fsi", make_asm, GatheredLU, overrides=dict(T=%(T)r, dt=0.01, theta=0.51, verbose=False,
+                                                                   visualization_folder=%(viz)r, save_step=1))
+x_global = np.asarray(ns["assembler"].to_host(ns["dvp_"]["n"]))          # collective
 if rank == 0:
+    from turtlefsi_b200.utils.xdmf import read_series
+    coords, cells, steps = read_series(os.path.join(%(viz)r, "velocity.xdmf"))
+    sp = ns["DVP"]
+    viz_ok = (len(steps) == len(ns["drag_list"]) and cells.shape[0] == ns["mesh"].num_cells
+              and all(np.array_equal(steps[-1][2][:, a], x_global[sp.node_dof(1, a)[sp.vertex_node]]) for a in range(2)))
     view = ns["assembler"].view
     out = dict(drag=ns["drag_list"], lift=ns["lift_list"], dis_x=ns["displacement_x_list"], dis_y=ns["displacement_y_list"],
                iters=[list(r[:2]) for r in ns["residual_history"]], residuals=[r[2] for r in ns["residual_history"]],
                owned_cells=int(view.cell_owned.sum()), local_cells=int(view.mesh.num_cells),
-               factorizations=ns["up_sol"].factorizations)
+               factorizations=ns["up_sol"].factorizations, viz_ok=bool(viz_ok))
     json.dump(out, open(%(out)r, "w"))
 dist.barrier()
 dist.destroy_process_group()
@@ -58,7 +65,7 @@ print("rank", rank, "ok")
 def _run(tmp_path, gpu, T, port):
     out = tmp_path / "result.json"
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % dict(root=ROOT, gpu=gpu, T=T, out=str(out)))
+    script.write_text(WORKER % dict(root=ROOT, gpu=gpu, T=T, out=str(out), viz=str(tmp_path / "viz")))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=1500)
@@ -72,6 +79,7 @@ def test_tf_fsi_two_ranks_oracle_gloo(tmp_path):
     h = json.load(open(os.path.join(ROOT, "tests", "golden", "turek_oracle_histories.json")))["tf_fsi_biharmonic_default"]
     n = len(r["drag"])
     assert n == 3 and 0 < r["owned_cells"] < r["local_cells"] < 2474            # really partitioned, with ghosts
+    assert r["viz_ok"]            # the XDMF series rank 0 wrote holds the GATHERED global fields of every step
     assert np.allclose(r["drag"], h["drag"][:n], rtol=1e-11, atol=0)
     assert np.allclose(r["dis_x"], h["dis_x"][:n], rtol=1e-9, atol=0)
     assert np.allclose(r["lift"], h["lift"][:n], rtol=1e-8, atol=0)
