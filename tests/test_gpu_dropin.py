@@ -56,3 +56,8 @@ def test_command_line_entry_point_on_the_cuda_path(tmp_path, monkeypatch):
     ref = json.load(open(os.path.join(HERE, "golden", "turek_oracle_histories.json")))["tf_cfd"]
     assert np.allclose(ns["drag_list"], ref["drag"][:len(ns["drag_list"])], rtol=1e-8)
     assert (tmp_path / "TF_cfd_results" / "r" / "Drag.txt").exists()
+    # the visualisation series of the first step (save_step = 10), read back from the raw-binary XDMF files
+    from turtlefsi_b200.utils.xdmf import read_series
+    coords, cells, steps = read_series(str(tmp_path / "TF_cfd_results" / "r" / "Visualization" / "velocity.xdmf"))
+    assert cells.shape[0] == ns["mesh"].num_cells and len(steps) == 1 and np.isfinite(steps[0][2]).all()
+    assert np.abs(steps[0][2]).max() > 0

@@ -360,3 +360,27 @@ def test_kill_and_pause_files_stop_and_hold_the_run(tmp_path):
     t0 = time.time()
     ns = _run(4, T=0.005, results_folder=str(hold), pause_poll_seconds=0.05)
     assert time.time() - t0 > 0.5 and len(ns["error_v_list"]) == 1
+
+
+def test_restart_keeps_and_merges_the_visualization_series(tmp_path):
+    """problems/__init__.py:147-170, 414-461 + monolithic.py:224-227: a restarted run renames the series it finds
+    (`*_run_1`), writes its own and joins both at the end: one file per field, steps in time order, the step the restart
+    recomputed taken from the restarted run, equal to an uninterrupted run to the Newton tolerance."""
+    from tests.test_turek_pin import _run_oracle
+    from turtlefsi_b200.utils.xdmf import read_series
+    ov = dict(N=4, dt=0.01, folder=str(tmp_path / "res"), sub_folder="a", save_step=1, checkpoint_step=2)
+    _run_oracle("TaylorGreen2D", dict(ov, T=0.03), create_results_folder=True)                  # steps t = .01 ... .04
+    viz = tmp_path / "res" / "a" / "Visualization"
+    assert len(read_series(str(viz / "velocity.xdmf"))[2]) == 4
+    again = _run_oracle("TaylorGreen2D", dict(ov, T=0.05, restart_folder=str(tmp_path / "res" / "a")), create_results_folder=True)
+    assert again["run_number"] == 1 and again["first_step_num"] == 2       # checkpoint of counter 2: t = .03 is recomputed
+    assert sorted(f.name for f in viz.iterdir()) == ["displacement.bin", "displacement.xdmf", "displacement_run_1.bin",
+                                                     "pressure.bin", "pressure.xdmf", "pressure_run_1.bin",
+                                                     "velocity.bin", "velocity.xdmf", "velocity_run_1.bin"]
+    coords, cells, steps = read_series(str(viz / "velocity.xdmf"))
+    assert np.allclose([t for t, _, _ in steps], [0.01, 0.02, 0.03, 0.04, 0.05, 0.06])
+    full = _run_oracle("TaylorGreen2D", dict(N=4, dt=0.01, T=0.05, visualization_folder=str(tmp_path / "full"), save_step=1))
+    ref = read_series(str(tmp_path / "full" / "velocity.xdmf"))[2]
+    for (t, _, v), (tr, _, vr) in zip(steps, ref):
+        assert abs(t - tr) < 1e-12 and np.abs(v - vr).max() < 1e-7 * np.abs(vr).max()
+    assert len(read_series(str(viz / "pressure.xdmf"))[2]) == 6

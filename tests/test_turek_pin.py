@@ -28,7 +28,7 @@ def _histories():
     return json.load(open(os.path.join(HERE, "golden", "turek_oracle_histories.json")))
 
 
-def _run_oracle(problem, overrides, made=None):
+def _run_oracle(problem, overrides, made=None, **run_kw):
     from oracle.backend import OracleAssembler
     from turtlefsi_b200 import monolithic
     from turtlefsi_b200.linear_solver import HostLU
@@ -47,7 +47,7 @@ def _run_oracle(problem, overrides, made=None):
         return lu
     ov = dict(T=0.05, dt=0.01, verbose=False)
     ov.update(overrides)
-    return monolithic.run(problem, make_asm, make_solver, overrides=ov)
+    return monolithic.run(problem, make_asm, make_solver, overrides=ov, **run_kw)
 
 
 def test_oracle_reproduces_tf_fsi_file_default_golden():

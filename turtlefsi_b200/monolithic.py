@@ -131,7 +131,8 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
     # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them
-    from .problems import check_if_kill, check_if_pause, checkpoint, save_files_visualization, start_from_checkpoint
+    from .problems import (check_if_kill, check_if_pause, checkpoint, merge_visualization_files,
+                           save_files_visualization, start_from_checkpoint)
     if ns.get("restart_folder") is not None:
         start_from_checkpoint(**ns)
     if ns.get("results_folder") is not None:
@@ -172,5 +173,8 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
         if max_steps is not None and counter >= max_steps:
             stop = True
     ns.update(t=t, counter=counter)
+    if ns.get("restart_folder") is not None and ns.get("visualization_folder") is not None \
+            and getattr(assembler, "rank", 0) == 0:                                                   # :224-227
+        merge_visualization_files(**ns)
     mod.finished(**ns)
     return ns

@@ -77,11 +77,75 @@ def create_folders(folder, sub_folder, restart_folder, **namespace):
                                   " restart the simulation from.").format(restart_folder))
     checkpoint_folder = path.joinpath("Checkpoint")
     visualization_folder = path.joinpath("Visualization")
+    run_number = keep_previous_visualization(visualization_folder)
     if int(os.environ.get("RANK", "0")) == 0:
         checkpoint_folder.mkdir(parents=True, exist_ok=True)
         visualization_folder.mkdir(parents=True, exist_ok=True)
     return dict(checkpoint_folder=str(checkpoint_folder), visualization_folder=str(visualization_folder),
-                results_folder=str(path), run_number=0)
+                results_folder=str(path), run_number=run_number)
+
+
+def keep_previous_visualization(visualization_folder):
+    """reference :147-170: series left by an earlier run (a restart continues in its folder) are renamed
+    `<name>_run_<N>.xdmf` (+ their heavy-data file, here `.bin` instead of `.h5`, and the link inside the XML), so the
+    new run does not overwrite them; `merge_visualization_files` joins them again at the end. Returns the run number."""
+    from pathlib import Path
+    folder = Path(visualization_folder)
+    if not folder.is_dir() or not list(folder.glob("*")):
+        return 0
+    done = [int(f.stem.split("_")[-1]) for f in folder.glob("velocity_run_*.bin")]
+    run_number = max(done) + 1 if done else 1
+    if int(os.environ.get("RANK", "0")) == 0:
+        for name in ("displacement", "velocity", "pressure"):
+            if not folder.joinpath(name + ".bin").exists():
+                continue
+            new = name + "_run_" + str(run_number)
+            for suffix in (".bin", ".xdmf"):
+                folder.joinpath(name + suffix).rename(folder.joinpath(new + suffix))
+            xml = folder.joinpath(new + ".xdmf")
+            xml.write_text(xml.read_text().replace(">" + name + ".bin<", ">" + new + ".bin<"))
+    return run_number
+
+
+def merge_visualization_files(visualization_folder, **namespace):
+    """reference :414-461 (called after a restarted run, monolithic.py:224-227): the steps of the renamed earlier series
+    and of this run in ONE `<name>.xdmf`, ordered in time, steps the restart recomputed taken from the later run; the
+    heavy-data files stay where they are (every DataItem names its own)."""
+    import re
+    import xml.etree.ElementTree as ET
+    from pathlib import Path
+    folder = Path(visualization_folder)
+    for name in ("displacement", "velocity", "pressure"):
+        files = sorted(folder.glob(name + "*.xdmf"))
+        if len(files) < 2 or not folder.joinpath(name + ".xdmf").exists():
+            continue
+        runs = []
+        for f in files:
+            root = ET.fromstring(re.sub(r"<!DOCTYPE[^>]*>", "", f.read_text()))
+            grids = [g for g in root.iter("Grid") if g.get("GridType") == "Uniform"]
+            if grids:
+                runs.append((float(grids[0].find("Time").get("Value")), f, root, grids))
+        runs.sort(key=lambda r: r[0])
+        merged = []
+        for k, (_, f, root, grids) in enumerate(runs):
+            if k + 1 < len(runs):
+                cut = runs[k + 1][0]                                         # the next run starts here again
+                grids = [g for g in grids if float(g.find("Time").get("Value")) < cut - 1e-12 * max(1.0, abs(cut))]
+            merged += grids
+        base = runs[0][2]
+        collection = next(g for g in base.iter("Grid") if g.get("GridType") == "Collection")
+        for g in list(collection):
+            collection.remove(g)
+        for k, g in enumerate(merged):
+            g.set("Name", "step_%d" % k)
+            collection.append(g)
+        out = folder.joinpath(name + ".xdmf")
+        tmp = folder.joinpath(name + ".xdmf.tmp")
+        tmp.write_text('<?xml version="1.0"?>\n<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n' + ET.tostring(base, encoding="unicode") + "\n")
+        for _, f, _, _ in runs:
+            if f != out:
+                f.unlink()
+        os.replace(tmp, out)
 
 
 def checkpoint(dvp_, default_variables, checkpoint_folder, assembler, **namespace):
