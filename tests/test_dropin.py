@@ -285,3 +285,19 @@ def test_problem_file_writes_its_own_xdmf_series(tmp_path):
         assert np.array_equal(steps[-1][2][:, a], x[space.node_dof(1, a)[space.vertex_node]])
     assert np.array_equal(read_series(str(tmp_path / "p.xdmf"))[2][-1][2][:, 0], x[space.vertex_dof_p()])
     assert np.array_equal(read_series(str(tmp_path / "dy.xdmf"))[2][-1][2][:, 0], x[space.node_dof(0, 1)[space.vertex_node]])
+
+
+@needs_reference
+def test_reference_taylor_green_file_runs_unmodified(tmp_path):
+    """turtleFSI/problems/TaylorGreen2D.py as shipped (RectangleMesh / Point, UserExpression.eval with UFL math functions on
+    numbers, interpolate + assign into sub-functions, pointwise DirichletBC, errornorm, pickle in `finished`) against the
+    native twin turtlefsi_b200/problems/TaylorGreen2D.py: same errors against the analytic solution."""
+    import pickle
+    ov = dict(N=8, T=0.02, dt=0.01, verbose=False, results_folder=str(tmp_path))
+    ns = _run_oracle(os.path.join(REF, "TaylorGreen2D.py"), ov)
+    twin = _run_oracle("TaylorGreen2D", dict(N=8, T=0.02, dt=0.01, verbose=False))
+    assert ns["mesh"].num_cells == 128 and len(twin["error_v_list"]) == 3
+    assert abs(ns["total_error_v"] / twin["total_error_v"] - 1) < 1e-9
+    assert abs(ns["total_error_p"] / twin["total_error_p"] - 1) < 1e-9
+    saved = pickle.load(open(tmp_path / "taylorgreen_results.pkl", "rb"))
+    assert saved["total_error_v"] == ns["total_error_v"] and saved["dt"] == 0.01

@@ -140,3 +140,47 @@ def test_surface_traction_3d_constant_stress():
     H = A @ np.linalg.inv(np.eye(3) + B)
     sig = mu * (H + H.T) - p0 * np.eye(3)
     assert np.allclose(surface_traction(mesh, space, facets, x, mu, face), sig @ np.array([1.0, 0, 0]), rtol=0, atol=1e-13)
+
+
+def test_hdf5_reader_on_the_shipped_mesh_files():
+    """turtlefsi_b200.utils.hdf5_lite (no h5py in this image) on the reference's own HDF5 mesh files: the turtle_demo pair
+    (tests/golden/meshes, offsets known from SURVEY Appendix C) and, when the reference tree is here, the 3-D artery of
+    Test_Cylinder/problem_aneu.py:58-66 through the `dolfin` stand-in's HDF5File."""
+    import os
+    import numpy as np
+    from turtlefsi_b200.mesh import read_turtle_demo
+    from turtlefsi_b200.utils.hdf5_lite import read_datasets
+    folder = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "turtle_demo")
+    raw = open(os.path.join(folder, "mc.h5"), "rb").read()
+    d = read_datasets(os.path.join(folder, "mc.h5"))
+    assert d["/data0"].shape == (3350, 2) and d["/data1"].shape == (6578, 3) and d["/data2"].shape == (6578,)
+    assert np.array_equal(d["/data0"], np.frombuffer(raw, "<f8", 6700, 2048).reshape(3350, 2))       # SURVEY Appendix C offsets
+    assert np.array_equal(d["/data1"], np.frombuffer(raw, "<i8", 6578 * 3, 55648).reshape(6578, 3))
+    assert np.array_equal(d["/data2"], np.frombuffer(raw, "<i8", 6578, 213520))
+    mesh, fv, fm = read_turtle_demo(folder)
+    assert mesh.num_cells == 6578 and set(np.unique(mesh.markers)) == {1, 2} and set(np.unique(fm)) <= {11, 12, 13, 14, 15}
+    artery = "/root/reference/turtleFSI/problems/Test_Cylinder/mesh/artery_coarse_rescaled.h5"
+    if not os.path.exists(artery):
+        return
+    from turtlefsi_b200 import compat
+    if not compat.install():
+        return                                           # a real DOLFIN is importable: nothing to stand in for
+    import dolfin
+    m = dolfin.Mesh()
+    with dolfin.HDF5File(m.mpi_comm(), artery, "r") as hdf:
+        hdf.read(m, "/mesh", False)
+        boundaries = dolfin.MeshFunction("size_t", m, 2)
+        hdf.read(boundaries, "/boundaries")
+        domains = dolfin.MeshFunction("size_t", m, 3)
+        hdf.read(domains, "/domains")
+    assert (m.num_vertices(), m.num_cells()) == (624, 3057) and set(np.unique(domains.array())) == {1, 2}
+    ids = set(np.unique(boundaries.array()))
+    assert {0, 2, 3, 22, 33} <= ids                      # inlet / outlet / interface / outer wall of problem_aneu.py:23-30
+    fac = m.facets()
+    # the interface (22) separates fluid from solid; the outer wall (33) lies on the boundary of the mesh
+    f22 = np.nonzero(boundaries.array() == 22)[0]
+    assert (~fac.on_boundary[f22]).all()
+    assert (domains.array()[fac.cell0[f22]] != domains.array()[fac.cell1[f22]]).all()
+    assert fac.on_boundary[boundaries.array() == 33].all()
+    X = m.coordinates()[m.cells()]
+    assert (np.abs(np.linalg.det(X[:, 1:] - X[:, :1])) > 0).all()

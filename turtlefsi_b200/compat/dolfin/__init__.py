@@ -20,8 +20,8 @@ from turtlefsi_b200 import boundary as _bnd
 from turtlefsi_b200 import mesh as _mesh
 from turtlefsi_b200.space import MixedSpace as _MixedSpace
 from turtlefsi_b200.ufl_lite import (Identity, as_matrix, as_tensor, as_vector, derivative, det, dev, diff, div,  # noqa: F401
-                                     dot, exp, grad, inner, inv, ln, nabla_grad, outer, skew, sqrt, sym, tr,
-                                     transpose, variable)
+                                     cos, cosh, dot, exp, grad, inner, inv, ln, nabla_grad, outer, sin, sinh, skew, sqrt,
+                                     sym, tan, tanh, tr, transpose, variable)
 
 DOLFIN_EPS = 3.0e-16
 DOLFIN_PI = float(np.pi)
@@ -215,6 +215,37 @@ class Mesh:
         return self._facets
 
 
+class Point:
+    """Point(x, y[, z]) (TaylorGreen2D.py:123)."""
+
+    def __init__(self, *c):
+        self._c = np.asarray(c[0] if len(c) == 1 and np.ndim(c[0]) else c, dtype=float)
+
+    def array(self):
+        return self._c
+
+    def x(self):
+        return float(self._c[0])
+
+    def y(self):
+        return float(self._c[1])
+
+    def __getitem__(self, i):
+        return float(self._c[i])
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    """RectangleMesh(Point, Point, nx, ny, "right" | "left") in DOLFIN's vertex and cell order (TaylorGreen2D.py:123)."""
+    if isinstance(p0, _Comm):
+        raise NotImplementedError("RectangleMesh(comm, ...): meshes are built on every rank and cut by turtlefsi_b200.distributed")
+    a, b = Point(p0).array() if not isinstance(p0, Point) else p0.array(), Point(p1).array() if not isinstance(p1, Point) else p1.array()
+    return Mesh(_mesh.rectangle_mesh(tuple(a[:2]), tuple(b[:2]), int(nx), int(ny), diagonal))
+
+
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    return RectangleMesh(Point(0.0, 0.0), Point(1.0, 1.0), nx, ny, diagonal)
+
+
 def refine(mesh, *a, **k):
     """uniform Plaza refinement (TF_cfd.py:49, TF_csm.py:54)."""
     return Mesh(_mesh.refine(mesh.native))
@@ -369,7 +400,63 @@ class XDMFFile:
     write_checkpoint = _unsupported("XDMFFile.write_checkpoint", "checkpoints are numpy files (turtlefsi_b200/problems/__init__.py)")
 
 
-HDF5File = _unsupported("HDF5File", "mesh/field storage goes through numpy files (turtlefsi_b200/problems/__init__.py)")
+class HDF5File:
+    """HDF5File(comm, "mesh.h5", "r").read(mesh | MeshFunction, "/name"[, False]) — the DOLFIN mesh files problem files
+    read (Test_Cylinder/problem_aneu.py:58-66): `/mesh/{coordinates,topology}`, cell functions `/<name>/{cell_indices,
+    values}`, facet functions `/<name>/{topology,values}` (matched to the mesh facets by their vertices). Read-only: h5py is
+    not in this image (turtlefsi_b200.utils.hdf5_lite parses the file), fields are stored as numpy files."""
+
+    def __init__(self, comm, path, mode="r"):
+        if mode != "r":
+            raise NotImplementedError("HDF5File(%r): only reading (checkpoints are numpy files, turtlefsi_b200/problems/__init__.py)" % mode)
+        from turtlefsi_b200.utils.hdf5_lite import read_datasets
+        self._d = read_datasets(str(path))
+
+    def _get(self, name, key):
+        k = "/" + name.strip("/") + "/" + key
+        if k not in self._d:
+            raise KeyError("HDF5File: no dataset %s (file holds %s)" % (k, sorted(self._d)))
+        return self._d[k]
+
+    def has_dataset(self, name):
+        n = "/" + name.strip("/")
+        return any(k == n or k.startswith(n + "/") for k in self._d)
+
+    def read(self, obj, name, *a):
+        if isinstance(obj, Mesh):
+            X = np.array(self._get(name, "coordinates"), dtype=float)
+            cells = np.sort(np.asarray(self._get(name, "topology"), dtype=np.int64), axis=1).astype(np.int32)
+            obj.native = _mesh.Mesh(X, cells, np.zeros(len(cells), dtype=np.int32))
+            obj._facets = None
+        elif isinstance(obj, MeshFunction):
+            m = obj.mesh().native
+            vals = np.asarray(self._get(name, "values")).astype(np.int64)
+            topo = np.sort(np.asarray(self._get(name, "topology"), dtype=np.int64), axis=1)
+            nv = m.num_vertices
+            key = lambda v: sum(v[:, c] * nv ** (v.shape[1] - 1 - c) for c in range(v.shape[1]))
+            ents = np.asarray(m.cells, dtype=np.int64) if obj.dim() == m.gdim else np.asarray(obj.facets.vertices, dtype=np.int64)
+            if topo.shape[1] != ents.shape[1]:
+                raise ValueError("HDF5File.read: %s holds entities of %d vertices, the MeshFunction has dimension %d"
+                                 % (name, topo.shape[1], obj.dim()))
+            ekey = key(ents)
+            order = np.argsort(ekey)
+            pos = np.minimum(np.searchsorted(ekey[order], key(topo)), len(order) - 1)
+            if (ekey[order][pos] != key(topo)).any():
+                raise RuntimeError("HDF5File.read: an entity of %s is not an entity of the mesh" % name)
+            obj.array()[order[pos]] = vals
+        else:
+            raise TypeError("HDF5File.read(%r)" % type(obj).__name__)
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    write = _unsupported("HDF5File.write", "fields are stored as numpy files (turtlefsi_b200/problems/__init__.py)")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -805,8 +892,29 @@ def TrialFunction(V):
     return None          # only ever handed to derivative(), which the kernels replace
 
 
-def assign(*a, **k):
-    raise NotImplementedError("assign(): write through dvp_[...].vector().set_local(...)")
+def assign(dst, src):
+    """assign(dvp_["n"].sub(i), f) (TaylorGreen2D.py:189-192): the dofs of sub-space i of the mixed function := those of f
+    (a function of the collapsed sub-space, as interpolate() returns it)."""
+    if not isinstance(dst, Function) or dst.field is None or dst._parent is None:
+        raise NotImplementedError("assign(): the target must be a sub-function view, e.g. dvp_['n'].sub(1)")
+    if not isinstance(src, Function) or src.field != dst.field or src.comp != dst.comp:
+        raise NotImplementedError("assign(): source and target must be the same sub-space")
+    dofs = dst.space.sub_dofs(dst.field, dst.comp)
+    x = np.array(dst._parent._host(), dtype=float)
+    x[dofs] = np.asarray(src._host(), dtype=float)[dofs]
+    dst._parent._store(x)
+
+
+def errornorm(u, uh, norm_type="L2", degree_rise=3, mesh=None):
+    """errornorm(ue, uh, "L2") (TaylorGreen2D.py:222-223) for two functions of the SAME sub-space: sqrt(int |ue - uh|^2 dx)
+    with the exact element mass matrices. (DOLFIN first interpolates both into a space of higher degree; for two
+    members of one Lagrange space the difference is a member of it and the norm is the same.)"""
+    if str(norm_type).upper() != "L2":
+        raise NotImplementedError("errornorm: only the L2 norm")
+    if not (isinstance(u, Function) and isinstance(uh, Function)) or u.field is None or u.field != uh.field:
+        raise NotImplementedError("errornorm: two functions of the same sub-space (interpolate the exact solution first)")
+    space = uh.space
+    return float(_bnd.l2_norm(uh._V.mesh().native, space, np.asarray(u._host(), dtype=float) - np.asarray(uh._host(), dtype=float), uh.field))
 
 
 def interpolate(expr, V):

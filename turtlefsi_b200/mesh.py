@@ -76,23 +76,23 @@ def read_dolfin_xml(path):
 
 def read_turtle_demo(folder):
     """The default problem's mesh (turtleFSI/mesh/turtle_demo/{mc,mf}.h5, read by
-    turtleFSI/problems/turtle_demo.py:58-87 through DOLFIN's XDMFFile [dep]). h5py is not available;
-    the files are plain HDF5 with contiguous, uncompressed datasets whose byte offsets are fixed
-    (SURVEY Appendix C): mc.h5 = coordinates f8[3350,2] @2048, triangles i8[6578,3] @55648, cell markers
-    i8[6578] @213520; mf.h5 = marked facets i8[137,2] @55648 and their markers i8[137] @57840.
+    turtleFSI/problems/turtle_demo.py:58-87 through DOLFIN's XDMFFile [dep]). h5py is not available; the files are
+    plain HDF5 (turtlefsi_b200.utils.hdf5_lite): mc.h5 = /data0 coordinates f8[3350,2], /data1 triangles i8[6578,3],
+    /data2 cell markers i8[6578]; mf.h5 = /data1 marked facets i8[137,2], /data2 their markers i8[137].
     Returns (Mesh, facet_vertices [137, 2], facet_markers [137])."""
     import os
-    mc = open(os.path.join(folder, "mc.h5"), "rb").read()
-    mf = open(os.path.join(folder, "mf.h5"), "rb").read()
-    if mc[:8] != b"\x89HDF\r\n\x1a\n" or len(mc) != 266144 or len(mf) != 58936:
+    from .utils.hdf5_lite import read_datasets
+    mc = read_datasets(os.path.join(folder, "mc.h5"))
+    mf = read_datasets(os.path.join(folder, "mf.h5"))
+    coords = np.array(mc["/data0"], dtype=np.float64)
+    cells = np.asarray(mc["/data1"]).astype(np.int32)
+    markers = np.asarray(mc["/data2"]).astype(np.int32)
+    fverts = np.asarray(mf["/data1"]).astype(np.int64)
+    fmark = np.asarray(mf["/data2"]).astype(np.int64)
+    if coords.ndim != 2 or cells.shape != (len(markers), coords.shape[1] + 1) or fverts.shape != (len(fmark), coords.shape[1]):
         raise RuntimeError("unexpected turtle_demo mesh files")
-    coords = np.frombuffer(mc, dtype="<f8", count=3350 * 2, offset=2048).reshape(3350, 2).copy()
-    cells = np.frombuffer(mc, dtype="<i8", count=6578 * 3, offset=55648).reshape(6578, 3).astype(np.int32)
-    markers = np.frombuffer(mc, dtype="<i8", count=6578, offset=213520).astype(np.int32)
-    fverts = np.frombuffer(mf, dtype="<i8", count=137 * 2, offset=55648).reshape(137, 2).astype(np.int64)
-    fmark = np.frombuffer(mf, dtype="<i8", count=137, offset=57840).astype(np.int64)
-    assert cells.min() == 0 and cells.max() == 3349 and set(np.unique(markers)) == {1, 2}
-    assert fverts.max() < 3350 and set(np.unique(fmark)) <= {11, 12, 13, 14, 15}
+    if cells.min() != 0 or cells.max() != len(coords) - 1 or fverts.max() >= len(coords):
+        raise RuntimeError("turtle_demo mesh files: vertex indices out of range")
     cells = np.sort(cells, axis=1)
     return Mesh(coords, cells, markers.copy(), meta=dict(kind="turtle_demo")), fverts, fmark
 

@@ -608,16 +608,48 @@ def as_matrix(rows):
     return as_tensor(rows)
 
 
+def _math(fn, a):
+    """UFL's math functions evaluate plain numbers at once (UserExpression.eval of a problem file does
+    `value[0] = sin(pi * x[0]) * exp(-t)`, TaylorGreen2D.py:143-144) and build an expression node otherwise."""
+    if isinstance(a, (int, float, np.integer, np.floating)):
+        return float(fn(a))
+    return MathFunction(fn, as_expr(a))
+
+
 def sqrt(a):
-    return MathFunction(np.sqrt, as_expr(a))
+    return _math(np.sqrt, a)
 
 
 def exp(a):
-    return MathFunction(np.exp, as_expr(a))
+    return _math(np.exp, a)
 
 
 def ln(a):
-    return MathFunction(np.log, as_expr(a))
+    return _math(np.log, a)
+
+
+def sin(a):
+    return _math(np.sin, a)
+
+
+def cos(a):
+    return _math(np.cos, a)
+
+
+def tan(a):
+    return _math(np.tan, a)
+
+
+def sinh(a):
+    return _math(np.sinh, a)
+
+
+def cosh(a):
+    return _math(np.cosh, a)
+
+
+def tanh(a):
+    return _math(np.tanh, a)
 
 
 def _no_symbolic(name):
