@@ -80,7 +80,7 @@ def load_problem(problem):
     return importlib.import_module("turtlefsi_b200.problems." + problem)
 
 
-def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, create_results_folder=False):
+def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, create_results_folder=False, progress=False):
     """problem: see load_problem. make_assembler(mesh, space, regions, ns) -> assembler;
     make_solver(assembler) -> up_sol. Returns the final namespace (what the reference keeps in its module globals)."""
     mod = load_problem(problem)
@@ -131,7 +131,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     ns.update(solver.solver_setup(**ns))
     ns["dvp_res"] = assembler.new_vector()                                                            # :157
     # restart data are loaded AFTER solver_setup (:160-162): A_pre stays frozen at the state before them
-    from .problems import (check_if_kill, check_if_pause, checkpoint, merge_visualization_files,
+    from .problems import (check_if_kill, check_if_pause, checkpoint, merge_visualization_files, print_information,
                            save_files_visualization, start_from_checkpoint)
     if ns.get("restart_folder") is not None:
         start_from_checkpoint(**ns)
@@ -143,7 +143,7 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
     counter = ns["counter"]
     ns["first_step_num"] = counter                                                                    # :168
     stop = False
-    t_start = time.time()
+    t_start = t_step = time.time()
     while t <= T + dt / 10 and not stop:                                                              # :169
         t += dt
         ns.update(t=t, counter=counter)
@@ -163,6 +163,10 @@ def run(problem, make_assembler, make_solver, overrides=None, max_steps=None, cr
             ns.update(t=t, counter=counter)
             ns.update(save_files_visualization(**ns))
         counter += 1
+        if progress and getattr(assembler, "rank", 0) == 0:                                            # :199-201
+            now = time.time()
+            print_information(counter=counter, t=t, T=T, dt=dt, elapsed_time=now - t_step, verbose=ns["verbose"])
+            t_step = now
         if ns.get("results_folder") is not None:                                                      # :203-212
             while check_if_pause(ns["results_folder"]):
                 time.sleep(ns.get("pause_poll_seconds", 5))

@@ -260,3 +260,13 @@ def check_if_pause(folder):
             print("pauseturtle Found! Simulations paused. Remove " + str(pause) + " to resume simulations...")
         return True
     return False
+
+
+def print_information(counter, t, T, dt, elapsed_time, verbose, **namespace):
+    """reference :400-411: one line per time step (verbose) or a progress bar."""
+    if verbose:
+        print("Solved for timestep {:d}, t = {:2.08f} in {:3.1f} s".format(counter, t, elapsed_time))
+    else:
+        j = counter / int(T / dt + 1)
+        print("Progress: [{:<20s}] {:2.1f}%, last solve took {:3.1f} s".format("=" * int(20 * j - 1) + ">", 100 * j, elapsed_time),
+              end="\r")

@@ -56,7 +56,7 @@ def main(argv=None):
         make_assembler, make_solver = make_b200(overrides.get("linear_solver", "mumps"))
     else:
         make_assembler, make_solver = make_oracle()
-    ns = monolithic.run(problem, make_assembler, make_solver, overrides=overrides, create_results_folder=True)
+    ns = monolithic.run(problem, make_assembler, make_solver, overrides=overrides, create_results_folder=True, progress=True)
     return ns
 
 
