@@ -120,11 +120,9 @@ class _File:
                 p = o + 8
                 for _ in range(nf):
                     fid, nlen, ncv = self.u16(p), self.u16(p + 2), self.u16(p + 6)
-                    if fid == 1:
-                        deflate = True
-                    elif fid != 2 or True:
-                        if fid not in (1,):
-                            raise NotImplementedError("HDF5 filter %d" % fid)
+                    if fid != 1:
+                        raise NotImplementedError("HDF5 filter %d (only deflate is read here)" % fid)
+                    deflate = True
                     p += 8 + (nlen + 7) // 8 * 8 + 4 * ncv + (4 if ncv % 2 else 0)
         if shape is None or dtype is None or layout is None:
             return None
