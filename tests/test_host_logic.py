@@ -184,3 +184,38 @@ def test_hdf5_reader_on_the_shipped_mesh_files():
     assert fac.on_boundary[boundaries.array() == 33].all()
     X = m.coordinates()[m.cells()]
     assert (np.abs(np.linalg.det(X[:, 1:] - X[:, :1])) > 0).all()
+
+
+def test_sass_of_the_hot_kernels_keeps_its_properties():
+    """properties of the shipped SASS that the measured performance depends on (cuobjdump, no GPU needed):
+    every scatter add is a fire-and-forget REDG.E.ADD.F64 — a fence behind the scatter makes ptxas emit ATOMG, whose warp
+    then waits for an L2 round trip per add (DESIGN.md 4, the pipelined experiment); the Jacobian kernels do not spill;
+    the scatter ranks arrive by TMA bulk copy; no tensor-core instruction (north_star design point 2)."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+    from turtlefsi_b200 import lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not here")
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    mangled = re.findall(r"Function : (\S+)", sass)
+    names = subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.split("\n")
+    blocks = re.split(r"\n\s*Function : \S+\n", sass)[1:]
+    seen = {}
+    for name, body in zip(names, blocks):
+        ops = collections.Counter(m.group(1).split(".")[0] for m in
+                                  re.finditer(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", body))
+        seen[name] = ops
+        assert ops["HMMA"] + ops["UTCMMA"] + ops["DMMA"] == 0, name
+    def one(sub):
+        hit = [v for k, v in seen.items() if sub in k]
+        assert len(hit) == 1, (sub, [k for k in seen if sub in k])
+        return hit[0]
+    fluid, solid, solid_pair = one("jac_fluid_kernel<3, 14>"), one("jac_solid_kernel<3, 14, 0, 0>"), one("jac_solid_kernel<3, 14, 0, 1>")
+    residual = one("residual_kernel<3, false, 16, 0>")
+    assert fluid["REDG"] == 180 and solid["REDG"] == 100 and solid_pair["REDG"] == 200 and residual["REDG"] >= 1
+    for ops in (fluid, solid, solid_pair, residual):
+        assert ops["ATOMG"] == 0 and ops["DFMA"] > 400
+    for ops in (fluid, solid, solid_pair):
+        assert ops["LDL"] == 0 and ops["STL"] == 0 and ops["UBLKCP"] >= 1 and ops["SYNCS"] >= 1
