@@ -195,6 +195,7 @@ def test_sass_of_the_hot_kernels_keeps_its_properties():
     import re
     import shutil
     import subprocess
+    import pytest
     from turtlefsi_b200 import lib
     if shutil.which("cuobjdump") is None or not os.path.exists(lib.LIB_PATH):
         pytest.skip("cuobjdump or the built library is not here")
